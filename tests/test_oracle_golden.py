@@ -1,0 +1,120 @@
+"""Pin the CPU oracle (oracle/) against outputs of the real reference (tests/golden/*.npz).
+
+Tolerance: the reference computes in fp32 with MKLDNN summation order, the oracle accumulates
+in double and rounds once -> agreement to a few fp32 ulps of the output scale (1e-5 relative
+to max|ref|), far inside the 1e-3 budget of BASELINE.json's north_star.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err
+from oracle import sg3_oracle as orc
+
+TOL = 2e-5
+
+
+def _opt(c, k):
+    return c[k] if k in c else None
+
+
+@pytest.mark.parametrize('case', golden('ops.npz').cases('upfirdn'))
+def test_upfirdn2d(case):
+    c = golden('ops.npz').case('upfirdn', case)
+    kw = dict(up=[int(v) for v in c['up']], down=[int(v) for v in c['down']],
+              padding=[int(v) for v in c['padding']], flip_filter=bool(c['flip']), gain=float(c['gain']))
+    y = orc.upfirdn2d(c['x'], _opt(c, 'f'), **kw)
+    assert y.shape == c['y'].shape
+    assert rel_err(y, c['y']) < TOL
+    # adjoint (upfirdn2d.py:257-267): dx = upfirdn2d(dy, f, up=down, down=up, padding=p, flip=!flip, gain)
+    f = _opt(c, 'f')
+    fw, fh = orc._fsize(f)
+    _, _, ih, iw = c['x'].shape
+    _, _, oh, ow = c['y'].shape
+    (upx, upy), (dnx, dny) = kw['up'], kw['down']
+    px0, _, py0, _ = kw['padding']
+    p = [fw - px0 - 1, iw * upx - ow * dnx + px0 - upx + 1, fh - py0 - 1, ih * upy - oh * dny + py0 - upy + 1]
+    dx = orc.upfirdn2d(c['dy'], f, up=kw['down'], down=kw['up'], padding=p, flip_filter=not kw['flip_filter'],
+                       gain=kw['gain'])
+    assert dx.shape == c['dx'].shape
+    assert rel_err(dx, c['dx']) < TOL
+
+
+@pytest.mark.parametrize('case', golden('ops.npz').cases('bias_act'))
+def test_bias_act(case):
+    c = golden('ops.npz').case('bias_act', case)
+    act = case.rsplit('_', 1)[0]
+    kw = dict(dim=int(c['dim']), act=act,
+              alpha=None if np.isnan(c['alpha']) else float(c['alpha']),
+              gain=None if np.isnan(c['gain']) else float(c['gain']),
+              clamp=None if c['clamp'] < 0 else float(c['clamp']))
+    y = orc.bias_act(c['x'], c['b'], **kw)
+    assert rel_err(y, c['y']) < TOL
+    g = orc.bias_act_grads(c['x'], c['b'], c['dy'], ddx=c['ddx'], **kw)
+    assert rel_err(g['dx'], c['dx']) < TOL
+    assert rel_err(g['db'], c['db']) < TOL
+    assert rel_err(g['d_dy'], c['d_dy']) < TOL
+    if np.abs(c['d_x']).max() > 0:
+        assert rel_err(g['d_x'], c['d_x']) < 5e-5
+    else:
+        assert np.abs(g['d_x']).max() == 0
+
+
+@pytest.mark.parametrize('case', golden('ops.npz').cases('flrelu'))
+def test_filtered_lrelu(case):
+    c = golden('ops.npz').case('flrelu', case)
+    kw = dict(fu=_opt(c, 'fu'), fd=_opt(c, 'fd'), up=int(c['up']), down=int(c['down']),
+              padding=[int(v) for v in c['padding']], gain=float(c['gain']), slope=float(c['slope']),
+              flip_filter=bool(c['flip']))
+    clamp = None if c['clamp'] < 0 else float(c['clamp'])
+    y, signs = orc.filtered_lrelu(c['x'], b=c['b'], clamp=clamp, return_signs=True, **kw)
+    assert y.shape == c['y'].shape
+    assert rel_err(y, c['y']) < TOL
+    dx, db = orc.filtered_lrelu_bwd(c['dy'], signs, c['x'].shape, **kw)
+    # A sign decision can differ from the reference's only where the pre-activation is ~0 or ~clamp
+    # to rounding; the golden inputs are random so any such pixel contributes O(eps) to the result.
+    assert rel_err(dx, c['dx']) < 5e-5
+    assert rel_err(db, c['db']) < 5e-5
+
+
+@pytest.mark.parametrize('case', golden('modconv.npz').cases('modconv'))
+def test_modulated_conv2d(case):
+    c = golden('modconv.npz').case('modconv', case)
+    k = c['w'].shape[-1]
+    kw = dict(demodulate=bool(c['demodulate']), padding=k - 1, input_gain=_opt(c, 'input_gain'))
+    y = orc.modulated_conv2d(c['x'], c['w'], c['s'], **kw)
+    assert y.shape == c['y'].shape
+    assert rel_err(y, c['y']) < TOL
+    dx, dw, ds = orc.modulated_conv2d_bwd(c['x'], c['w'], c['s'], c['dy'], **kw)
+    assert rel_err(dx, c['dx']) < TOL
+    assert rel_err(dw, c['dw']) < 5e-5
+    assert rel_err(ds, c['ds']) < 5e-5
+
+
+TINY_CFG = dict(
+    tinyR=dict(img_resolution=64, w_dim=64, channel_base=2048, channel_max=32, conv_kernel=1, use_radial_filters=True),
+    tinyT=dict(img_resolution=64, w_dim=64, channel_base=2048, channel_max=32, conv_kernel=3, use_radial_filters=False),
+)
+
+
+@pytest.mark.parametrize('name', ['tinyR', 'tinyT'])
+def test_tiny_generator(name):
+    g = golden('tiny.npz')
+    state = g.sub(f'{name}/state/')
+    net = orc.SynthesisOracle(state, **TINY_CFG[name])
+    # the oracle's own filter design and padding math must reproduce the reference's buffers
+    for spec in net.specs:
+        for fk in ('up_filter', 'down_filter'):
+            key = f"{spec['name']}.{fk}"
+            if key in state:
+                assert np.allclose(spec[fk], state[key], rtol=0, atol=1e-7)
+            else:
+                assert spec[fk] is None
+    ws = g.z[f'{name}/ws']
+    x = net.input_features(ws[:, 0])
+    assert rel_err(x[:1, :8], g.z[f'{name}/feat/input']) < TOL
+    img = net.forward(ws)
+    assert img.shape == g.z[f'{name}/img'].shape
+    # 15 chained layers: fp32 rounding differences compound; still ~100x inside the 1e-3 budget
+    assert rel_err(img, g.z[f'{name}/img']) < 1e-4
+    feat = net.forward(ws, num_layers=3)
+    assert rel_err(feat[:1, :8], g.z[f'{name}/feat/after_2']) < 5e-5
