@@ -1,0 +1,155 @@
+/*
+ * sg3_b200.h -- C ABI of libsg3_b200.so: the B200 (sm_100a) kernels behind the
+ * StyleGAN3 synthesis hot path of krylea/stylegan3-editing.
+ *
+ * Every entry point takes plain device/host pointers, sizes and a cudaStream_t
+ * passed as void*; no torch types.  All functions are re-entrant and keep no
+ * device-global state (the reference's g_fbuf/c_fbuf filter staging,
+ * torch_utils/ops/filtered_lrelu.cu:74-84, is replaced by taps passed by value).
+ *
+ * Return convention (mirrors return_code of filtered_lrelu.cpp:52-56):
+ *    0  success, kernel(s) enqueued on `stream`
+ *   <0  SG3_E_*: bad arguments, or "no specialised kernel for these parameters"
+ *       (SG3_E_NOKERNEL; the caller composes upfirdn2d + act + upfirdn2d like
+ *       filtered_lrelu.py:224-230)
+ *   >0  a cudaError_t raised while launching
+ *
+ * Each declaration names the reference pybind entry point it replaces.
+ */
+#ifndef SG3_B200_H
+#define SG3_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG3_ABI_VERSION 1
+
+/* element types of activations */
+#define SG3_F32 0
+#define SG3_F16 1
+#define SG3_F64 2   /* bias_act / upfirdn2d / filtered_lrelu_act only */
+
+#define SG3_E_INVALID   (-1)  /* malformed arguments */
+#define SG3_E_NOKERNEL  (-2)  /* valid, but no fused specialisation: use the generic composition */
+#define SG3_E_TOOLARGE  (-3)  /* exceeds an indexing limit of this entry point */
+
+/* sign-tensor modes of the fused op (filtered_lrelu.cpp:146-160: signWrite / signRead / none) */
+#define SG3_SIGNS_NONE  0
+#define SG3_SIGNS_WRITE 1
+#define SG3_SIGNS_READ  2
+
+int         sg3_abi_version(void);
+const char* sg3_error_string(int code);       /* static string for SG3_E_* / cudaError_t codes */
+const char* sg3_build_info(void);             /* "sm_100a nvcc x.y ..." */
+
+/* ------------------------------------------------------------------------
+ * filtered_lrelu: bias -> zero-insert upsample + FIR -> gain*lrelu, clamp (+2-bit
+ * sign codes) -> FIR + decimate, one fused kernel.
+ * Replaces: filtered_lrelu_plugin.filtered_lrelu   (filtered_lrelu.cpp:16-209, .cu:139-1099)
+ *
+ * Tensors are [N][C][H][W] with BYTE strides (like filtered_lrelu.cpp:127-130); x and y
+ * have the same dtype; b is [C] of that dtype (stride in bytes) or NULL.
+ * fu / fd are HOST pointers to float32 taps: fuH == 0 means separable with fuW taps
+ * (applied along x then y), else a dense [fuH][fuW] filter; same for fd.  NULL = 1x1 identity.
+ * Taps are copied into the launch parameters, so the arrays may be freed on return.
+ * signs: uint8 [N][C][sH][sWb], 4 pixels per byte along x, pixel k at bits 2k..2k+1,
+ * code 1 = negative (scaled by slope), 2 = clamped (gradient 0)   (.cu:494-519).
+ * ---------------------------------------------------------------------- */
+typedef struct sg3_flrelu_desc {
+    const void* x;   void* y;   const void* b;   uint8_t* signs;
+    const float* fu; const float* fd;            /* host */
+    int32_t N, C, inH, inW, outH, outW;
+    int64_t xStride[4];                          /* bytes: n, c, h, w */
+    int64_t yStride[4];
+    int64_t bStride;                             /* bytes */
+    int32_t up, down;
+    int32_t fuW, fuH, fdW, fdH;                  /* fuH/fdH == 0: separable */
+    int32_t px0, py0;                            /* left / top padding in the upsampled domain */
+    float   gain, slope, clamp;                  /* clamp = +inf disables */
+    int32_t flip;                                /* 1 = correlation, 0 = true convolution */
+    int32_t signMode;                            /* SG3_SIGNS_* */
+    int32_t sH, sWb;                             /* sign tensor height, width in BYTES */
+    int32_t sx, sy;                              /* sign offset added to upsampled coords */
+    int32_t dtype;                               /* SG3_F32 / SG3_F16 */
+    int32_t reserved;
+} sg3_flrelu_desc;
+
+/* Output and sign-tensor geometry (filtered_lrelu.cpp:69-93).  Any out pointer may be NULL. */
+int sg3_filtered_lrelu_shape(int inH, int inW, int up, int down,
+                             int fuW, int fuH, int fdW, int fdH,
+                             int px0, int px1, int py0, int py1,
+                             int* outH, int* outW, int* sH, int* sWb);
+
+/* 0 if sg3_filtered_lrelu has a fused kernel for (up, down, filter shapes), SG3_E_NOKERNEL otherwise. */
+int sg3_filtered_lrelu_supported(int up, int down, int fuW, int fuH, int fdW, int fdH);
+
+int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream);
+
+/* sizeof(sg3_flrelu_desc) as compiled into the library, so FFI hosts can verify their struct layout. */
+int sg3_sizeof_flrelu_desc(void);
+
+/* In-place x = clamp(lrelu(x*gain)) with sign write / read at offset (sx, sy).
+ * Replaces: filtered_lrelu_plugin.filtered_lrelu_act_   (filtered_lrelu.cpp:213-290, .cu:1105-1211)
+ * x strides in ELEMENTS (n, c, h, w); signs contiguous [N][C][sH][sWb]. */
+int sg3_filtered_lrelu_act(void* x, uint8_t* signs,
+                           int N, int C, int H, int W, const int64_t xStride[4],
+                           int sH, int sWb, int sx, int sy,
+                           float gain, float slope, float clamp,
+                           int signMode, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * bias_act: y = clamp(act(x + b) * gain) and its first / second derivatives.
+ * Replaces: bias_act_plugin.bias_act   (bias_act.cpp:32-90, bias_act.cu:23-147)
+ * x, xref, yref, dy, y: dense, same layout, sizeX elements; b: [sizeB] or NULL,
+ * channel of element i is (i / stepB) % sizeB.  grad in {0,1,2}; act in 1..9
+ * (linear, relu, lrelu, tanh, sigmoid, elu, selu, softplus, swish); clamp < 0 disables.
+ * ---------------------------------------------------------------------- */
+int sg3_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                 int64_t sizeX, int32_t sizeB, int64_t stepB,
+                 int grad, int act, float alpha, float gain, float clamp,
+                 int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * upfirdn2d: pad / zero-insert upsample / 2-D FIR / decimate.
+ * Replaces: upfirdn2d_plugin.upfirdn2d   (upfirdn2d.cpp:16-98, upfirdn2d.cu:29-375)
+ * x [N][C][inH][inW], y [N][C][outH][outW], strides in ELEMENTS (n, c, h, w);
+ * f: HOST pointer to a dense [fH][fW] float32 filter (a separable filter is two calls).
+ * outW = (inW*upx + padx0 + padx1 - fW + downx) / downx      (upfirdn2d.cpp:35-36)
+ * ---------------------------------------------------------------------- */
+int sg3_upfirdn2d(const void* x, void* y, const float* f,
+                  int N, int C, int inH, int inW, int outH, int outW,
+                  const int64_t xStride[4], const int64_t yStride[4],
+                  int fW, int fH, int upx, int upy, int downx, int downy,
+                  int padx0, int pady0, int flip, float gain,
+                  int dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * modulated_conv2d (networks_stylegan3.py:24-63).  The reference has no native entry
+ * point here: it runs ~10 eager elementwise kernels and a cuDNN grouped convolution.
+ *
+ * sg3_modconv_weights: fused weight prologue (:39-56) ->
+ *   wmod[n][o][i][kh][kw] = w*rsqrt(mean w^2) * s*rsqrt(mean s^2) * rsqrt(sum(.)^2+1e-8) * input_gain
+ * w [O][I][k][k] f32, s [N][I] f32, input_gain: NULL, or f32 with gainMode 1 = scalar,
+ * 2 = [I], 3 = [N][I].  wmod is f32 [N][O][I*k*k]; if round_tf32 != 0 each value is
+ * rounded to the nearest TF32 so the tensor-core contraction sees unbiased operands.
+ * scratch: >= 4 bytes of device memory (batch-global style norm).
+ *
+ * sg3_modconv_fwd: y[n][o][p] = sum_{i,tap} wmod[n][o][i][tap] * x[n][i][p + tap - pad]
+ * x [N][I][H][W] contiguous, y [N][O][H+2pad-k+1][W+2pad-k+1] contiguous, dtype f32.
+ * mathMode 0: FP32 SIMT (exact fp32 accumulate);  1: TF32 tcgen05 implicit GEMM.
+ * ---------------------------------------------------------------------- */
+int sg3_modconv_weights(const float* w, const float* s, const float* input_gain, int gainMode,
+                        float* wmod, float* scratch,
+                        int N, int I, int O, int k, int demodulate, int round_tf32, void* stream);
+
+int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
+                    int N, int I, int O, int H, int W, int k, int pad,
+                    int mathMode, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SG3_B200_H */

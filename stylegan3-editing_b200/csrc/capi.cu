@@ -1,0 +1,39 @@
+// capi.cu -- ABI housekeeping for libsg3_b200.so.
+#include "common.cuh"
+
+#define SG3_STR2(x) #x
+#define SG3_STR(x) SG3_STR2(x)
+
+int sg3_sm_count()
+{
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+SG3_EXPORT int sg3_abi_version(void) { return SG3_ABI_VERSION; }
+
+SG3_EXPORT int sg3_sizeof_flrelu_desc(void) { return (int)sizeof(sg3_flrelu_desc); }
+
+SG3_EXPORT const char* sg3_build_info(void)
+{
+    return "libsg3_b200 sm_100a nvcc " SG3_STR(__CUDACC_VER_MAJOR__) "." SG3_STR(__CUDACC_VER_MINOR__) " abi " SG3_STR(SG3_ABI_VERSION);
+}
+
+SG3_EXPORT const char* sg3_error_string(int code)
+{
+    switch (code) {
+    case 0: return "success";
+    case SG3_E_INVALID: return "invalid arguments";
+    case SG3_E_NOKERNEL: return "no fused kernel for these parameters";
+    case SG3_E_TOOLARGE: return "size exceeds a limit of this entry point";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}

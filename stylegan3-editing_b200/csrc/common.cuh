@@ -1,0 +1,45 @@
+// common.cuh -- shared helpers for the sm_100a kernels of libsg3_b200.so.
+#pragma once
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sg3_b200.h"
+
+#define SG3_EXPORT extern "C" __attribute__((visibility("default")))
+
+// Storage type -> arithmetic type (reference rule, filtered_lrelu.cu:24-45, bias_act.cu:15-18:
+// half computes in float and rounds once at the store; double stays double).
+template <class T> struct Arith { typedef float type; };
+template <> struct Arith<double> { typedef double type; };
+
+template <class T> __device__ __forceinline__ typename Arith<T>::type ld_as(const T* p) { return (typename Arith<T>::type)(*p); }
+template <> __device__ __forceinline__ float ld_as<__half>(const __half* p) { return __half2float(*p); }
+
+template <class T> __device__ __forceinline__ void st_as(T* p, typename Arith<T>::type v) { *p = (T)v; }
+template <> __device__ __forceinline__ void st_as<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+static inline int sg3_launch_status()
+{
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    return 0;
+}
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__host__ __device__ __forceinline__ int floor_div(int a, int b)
+{
+    int q = a / b;
+    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+__host__ __device__ __forceinline__ int pos_mod(int a, int b)
+{
+    int r = a % b;
+    return r < 0 ? r + b : r;
+}
+
+// Cached SM count of the current device (grid sizing in multiples of the SM count).
+int sg3_sm_count();

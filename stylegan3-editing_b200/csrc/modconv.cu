@@ -1,0 +1,197 @@
+// modconv.cu -- modulated_conv2d of the StyleGAN3 synthesis layer
+// (models/stylegan3/networks_stylegan3.py:24-63), split into
+//   1. a fused weight prologue: pre-normalise, modulate, demodulate, input gain -> per-sample
+//      weights wmod[n][o][i*k*k]   (the ~10 eager elementwise/reduction kernels of :39-56);
+//   2. the contraction y[n][o][p] = sum_{i,tap} wmod[n][o][i][tap] * x[n][i][p + tap - pad]
+//      (the cuDNN grouped convolution of :59-62).
+// This file holds the prologue and the exact-FP32 SIMT contraction (mathMode 0) used for
+// fp32 parity; the TF32 tcgen05/TMEM implicit GEMM (mathMode 1) lives in modconv_tc.cu.
+#include "common.cuh"
+
+int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad,
+                       cudaStream_t stream);
+
+namespace {
+
+__device__ __forceinline__ float block_sum(float v, float* red)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    float t = l < nw ? red[l] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+}
+
+// scratch[0] = rsqrt(mean(s^2)) over the whole batch          (:42)
+__global__ void __launch_bounds__(1024) style_norm_kernel(const float* __restrict__ s, int count, float* scratch)
+{
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) { float v = s[i]; acc += v * v; }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) scratch[0] = rsqrtf(acc / (float)count);
+}
+
+__device__ __forceinline__ float round_tf32(float v)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// One CTA per output channel o: rw = rsqrt(mean w[o]^2), then for every sample n the
+// demodulation coefficient and the final weights.
+__global__ void __launch_bounds__(256) modconv_weights_kernel(
+    const float* __restrict__ w, const float* __restrict__ s, const float* __restrict__ gain, int gainMode,
+    float* __restrict__ wmod, const float* __restrict__ scratch,
+    int N, int I, int O, int kk, int demodulate, int roundTf32)
+{
+    __shared__ float red[32];
+    const int o = blockIdx.x;
+    const int cnt = I * kk;
+    const float* wo = w + (size_t)o * cnt;
+    float rw = 1.f, rs = 1.f;
+    if (demodulate) {
+        float acc = 0.f;
+        for (int q = threadIdx.x; q < cnt; q += blockDim.x) { float v = wo[q]; acc += v * v; }
+        acc = block_sum(acc, red);
+        rw = rsqrtf(acc / (float)cnt);
+        rs = scratch[0];
+    }
+    for (int n = blockIdx.y; n < N; n += gridDim.y) {
+        const float* sn = s + (size_t)n * I;
+        float d = 1.f;
+        if (demodulate) {
+            float acc = 0.f;
+            for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
+                float v = (wo[q] * rw) * (sn[q / kk] * rs);
+                acc += v * v;
+            }
+            acc = block_sum(acc, red);
+            d = rsqrtf(acc + 1e-8f);
+        }
+        float* dst = wmod + ((size_t)n * O + o) * cnt;
+        for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
+            const int i = q / kk;
+            float v = (wo[q] * rw) * (sn[i] * rs);
+            if (demodulate) v *= d;
+            if (gainMode == 1) v *= gain[0];
+            else if (gainMode == 2) v *= gain[i];
+            else if (gainMode == 3) v *= gain[(size_t)n * I + i];
+            dst[q] = roundTf32 ? round_tf32(v) : v;
+        }
+    }
+}
+
+// ---- exact FP32 contraction: 64 output channels x 64 pixels per CTA, K chunks of 16 --------
+constexpr int BO = 64, BP = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) modconv_fwd_simt_kernel(
+    const float* __restrict__ x, const float* __restrict__ wmod, float* __restrict__ y,
+    int N, int I, int O, int H, int W, int k, int pad, int OH, int OW)
+{
+    __shared__ float sA[BK][BO + 4];   // weights  [kchunk][o]
+    __shared__ float sB[BK][BP + 4];   // pixels   [kchunk][p]
+    const int P = OH * OW;
+    const int kk = k * k;
+    const int K = I * kk;
+    const int tilesP = (P + BP - 1) / BP, tilesO = (O + BO - 1) / BO;
+    const int64_t total = (int64_t)N * tilesO * tilesP;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16 threads, 4x4 outputs each
+    for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const int n = (int)(t / ((int64_t)tilesO * tilesP));
+        const int rem = (int)(t - (int64_t)n * tilesO * tilesP);
+        const int to = rem / tilesP, tp = rem - to * tilesP;
+        const int o0 = to * BO, p0 = tp * BP;
+        const float* wn = wmod + (size_t)n * O * K;
+        const float* xn = x + (size_t)n * I * H * W;
+        float acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+        for (int k0 = 0; k0 < K; k0 += BK) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < BK * BO; e += 256) {
+                const int o = e / BK, kc = e - o * BK;
+                float v = 0.f;
+                if (o0 + o < O && k0 + kc < K) v = wn[(size_t)(o0 + o) * K + k0 + kc];
+                sA[kc][o] = v;
+            }
+            for (int e = threadIdx.x; e < BK * BP; e += 256) {
+                const int kc = e / BP, pp = e - kc * BP;
+                float v = 0.f;
+                const int kidx = k0 + kc, p = p0 + pp;
+                if (kidx < K && p < P) {
+                    const int i = kidx / kk, tap = kidx - i * kk;
+                    const int ta = tap / k, tb = tap - ta * k;
+                    const int oy = p / OW, ox = p - oy * OW;
+                    const int iy = oy + ta - pad, ix = ox + tb - pad;
+                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = xn[((size_t)i * H + iy) * W + ix];
+                }
+                sB[kc][pp] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kc = 0; kc < BK; kc++) {
+                float a[4], b[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) { a[q] = sA[kc][ty * 4 + q]; b[q] = sB[kc][tx * 4 + q]; }
+#pragma unroll
+                for (int qa = 0; qa < 4; qa++)
+#pragma unroll
+                    for (int qb = 0; qb < 4; qb++) acc[qa][qb] = fmaf(a[qa], b[qb], acc[qa][qb]);
+            }
+        }
+#pragma unroll
+        for (int qa = 0; qa < 4; qa++) {
+            const int o = o0 + ty * 4 + qa;
+            if (o >= O) continue;
+#pragma unroll
+            for (int qb = 0; qb < 4; qb++) {
+                const int p = p0 + tx * 4 + qb;
+                if (p < P) y[((size_t)n * O + o) * P + p] = acc[qa][qb];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+SG3_EXPORT int sg3_modconv_weights(const float* w, const float* s, const float* input_gain, int gainMode,
+                                   float* wmod, float* scratch,
+                                   int N, int I, int O, int k, int demodulate, int round_tf32_flag, void* stream)
+{
+    if (!w || !s || !wmod || !scratch || N < 1 || I < 1 || O < 1 || k < 1) return SG3_E_INVALID;
+    if (gainMode < 0 || gainMode > 3 || (gainMode && !input_gain)) return SG3_E_INVALID;
+    if ((int64_t)N * I > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (demodulate) style_norm_kernel<<<1, 1024, 0, st>>>(s, N * I, scratch);
+    int gy = N < 8 ? N : 8;
+    modconv_weights_kernel<<<dim3((unsigned)O, (unsigned)gy), 256, 0, st>>>(w, s, input_gain, gainMode, wmod, scratch,
+                                                                            N, I, O, k * k, demodulate, round_tf32_flag);
+    return sg3_launch_status();
+}
+
+SG3_EXPORT int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
+                               int N, int I, int O, int H, int W, int k, int pad,
+                               int mathMode, int dtype, void* stream)
+{
+    if (!x || !wmod || !y || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || k < 1 || pad < 0) return SG3_E_INVALID;
+    if (dtype != SG3_F32) return SG3_E_NOKERNEL;
+    const int OH = H + 2 * pad - k + 1, OW = W + 2 * pad - k + 1;
+    if (OH < 1 || OW < 1) return SG3_E_INVALID;
+    if ((int64_t)OH * OW > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mathMode == 1) return sg3_modconv_fwd_tc((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, st);
+    if (mathMode != 0) return SG3_E_INVALID;
+    const int P = OH * OW;
+    int64_t total = (int64_t)N * ((O + BO - 1) / BO) * ((P + BP - 1) / BP);
+    int64_t cap = (int64_t)sg3_sm_count() * 32;
+    unsigned grid = (unsigned)(total < cap ? total : cap);
+    modconv_fwd_simt_kernel<<<grid, 256, 0, st>>>((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, OH, OW);
+    return sg3_launch_status();
+}

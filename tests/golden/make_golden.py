@@ -254,7 +254,8 @@ def gen_r256(out):
     out['r256/stats'] = np.asarray([float(img.mean()), float(img.std()), float(img.abs().max())])
     # a few weights to prove the package's seed-0 construction consumes the RNG identically
     sd = G.synthesis.state_dict()
-    for key in ['input.weight', 'input.freqs', 'L0_36_1024.weight', 'L13_256_128.weight', 'L14_256_3.affine.weight']:
+    names = G.synthesis.layer_names
+    for key in ['input.weight', 'input.freqs', names[0] + '.weight', names[13] + '.weight', names[14] + '.affine.weight']:
         out['r256/probe/' + key] = sd[key].flatten()[:64].numpy()
     print('r256 stats', out['r256/stats'])
 

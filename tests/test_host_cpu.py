@@ -1,0 +1,131 @@
+"""CPU-side checks (no GPU, no compute launches): the C-ABI library loads and exports every symbol
+that include/sg3_b200.h declares, geometry helpers agree with the oracle, host-side argument logic
+and the drop-in seam behave like the reference interface."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope='module')
+def pkg():
+    import __graft_entry__ as ge
+    ge.build()
+    import sg3_b200
+    return sg3_b200
+
+
+def test_header_symbols_exported(pkg):
+    hdr = open(os.path.join(ROOT, 'include', 'sg3_b200.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', '', hdr, flags=re.S)
+    declared = sorted(set(re.findall(r'\b(sg3_[a-z0-9_]+)\s*\(', hdr)))
+    assert len(declared) >= 10
+    lib = ctypes.CDLL(pkg.capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in sg3_b200.h but not exported'
+    assert sorted(pkg.capi.EXPORTS) == declared
+    assert pkg.capi.lib().sg3_abi_version() == 1
+    assert b'sm_100a' in pkg.capi.lib().sg3_build_info()
+
+
+def test_struct_layout_matches_header(pkg):
+    assert ctypes.sizeof(pkg.capi.FlreluDesc) == pkg.capi.lib().sg3_sizeof_flrelu_desc()
+    assert pkg.capi.FlreluDesc.xStride.offset == 6 * 8 + 6 * 4 and pkg.capi.FlreluDesc.dtype.offset == 212
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(inH=36, inW=36, up=2, down=2, fu=(12, 0), fd=(12, 12), pad=[11, 10, 11, 10]),
+    dict(inH=84, inW=84, up=4, down=2, fu=(24, 0), fd=(12, 12), pad=[-2, -5, -2, -5]),
+    dict(inH=1044, inW=1044, up=2, down=2, fu=(12, 0), fd=(12, 0), pad=[-9, -10, -9, -10]),
+    dict(inH=17, inW=23, up=1, down=1, fu=(1, 1), fd=(1, 1), pad=[0, 0, 0, 0]),
+    dict(inH=21, inW=33, up=2, down=4, fu=(12, 0), fd=(24, 0), pad=[7, 9, 12, 6]),
+])
+def test_shape_query_matches_oracle(pkg, cfg):
+    from oracle import sg3_oracle as orc
+    fuw, fuh = cfg['fu']
+    fdw, fdh = cfg['fd']
+    fu = np.zeros((fuh, fuw) if fuh else (fuw,), np.float32)
+    fd = np.zeros((fdh, fdw) if fdh else (fdw,), np.float32)
+    oh, ow, sh, swb = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    rc = pkg.capi.lib().sg3_filtered_lrelu_shape(cfg['inH'], cfg['inW'], cfg['up'], cfg['down'], fuw, fuh, fdw, fdh,
+                                                 *cfg['pad'], ctypes.byref(oh), ctypes.byref(ow), ctypes.byref(sh), ctypes.byref(swb))
+    assert rc == 0
+    eh, ew = orc.filtered_lrelu_out_shape(cfg['inH'], cfg['inW'], fu, fd, cfg['up'], cfg['down'], cfg['pad'])
+    assert (oh.value, ow.value) == (eh, ew)
+    assert (sh.value, swb.value) == orc.sign_shape(eh, ew, fd, cfg['down'])
+    fu_t = torch.from_numpy(fu)
+    fd_t = torch.from_numpy(fd)
+    assert pkg.filtered_lrelu.output_shape(cfg['inH'], cfg['inW'], fu_t, fd_t, cfg['up'], cfg['down'], cfg['pad']) == (eh, ew)
+
+
+def test_shape_query_rejects_tiny_buffer(pkg):
+    rc = pkg.capi.lib().sg3_filtered_lrelu_shape(4, 4, 2, 2, 12, 0, 12, 0, 0, 0, 0, 0, None, None, None, None)
+    assert rc == pkg.capi.SG3_E_INVALID
+
+
+def test_setup_filter_contract(pkg):
+    up = pkg.upfirdn2d
+    f = up.setup_filter([1, 3, 3, 1])
+    assert f.shape == (4, 4) and abs(float(f.sum()) - 1) < 1e-6          # short filters become dense outer products
+    f8 = up.setup_filter(np.arange(1, 9))
+    assert f8.shape == (8,) and abs(float(f8.sum()) - 1) < 1e-6          # >= 8 taps stay separable
+    assert up.setup_filter(None).shape == (1, 1)
+    g = up.setup_filter([1, 2, 1], gain=4, flip_filter=True)
+    assert abs(float(g.sum()) - 4) < 1e-5
+    assert up._padding(3) == (3, 3, 3, 3) and up._padding([1, 2]) == (1, 1, 2, 2) and up._padding([1, 2, 3, 4]) == (1, 2, 3, 4)
+
+
+def test_host_taps_cache_tracks_versions(pkg):
+    up = pkg.upfirdn2d
+    f = torch.arange(4, dtype=torch.float32)
+    a = up.host_taps(f)
+    assert up.host_taps(f) is a
+    f.mul_(2)
+    b = up.host_taps(f)
+    assert b is not a and np.allclose(b, [0, 2, 4, 6])
+
+
+def test_activation_table(pkg):
+    t = pkg.bias_act.activation_funcs
+    assert list(t) == ['linear', 'relu', 'lrelu', 'tanh', 'sigmoid', 'elu', 'selu', 'softplus', 'swish']
+    assert [t[k].cuda_idx for k in t] == list(range(1, 10))
+    assert t['lrelu'].def_alpha == 0.2 and abs(t['swish'].def_gain - np.sqrt(2)) < 1e-12
+    x = torch.randn(5)
+    assert torch.allclose(t['lrelu'].func(x, alpha=0.2), torch.nn.functional.leaky_relu(x, 0.2))
+
+
+def test_cpu_tensors_fail_loudly(pkg):
+    x = torch.zeros(1, 1, 8, 8)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        pkg.filtered_lrelu.filtered_lrelu(x)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        pkg.upfirdn2d.upfirdn2d(x, None)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        pkg.bias_act.bias_act(x, torch.zeros(1), act='lrelu')
+
+
+def test_dropin_seam(pkg):
+    saved = {k: v for k, v in sys.modules.items() if k == 'torch_utils' or k.startswith('torch_utils.')}
+    try:
+        for k in saved:
+            del sys.modules[k]
+        names = pkg.install()
+        assert 'torch_utils.ops.filtered_lrelu' in names
+        from torch_utils.ops import filtered_lrelu, bias_act, upfirdn2d, conv2d_gradfix   # the reference's import line
+        assert filtered_lrelu is pkg.filtered_lrelu and bias_act is pkg.bias_act and upfirdn2d is pkg.upfirdn2d
+        assert conv2d_gradfix.enabled is False
+        import inspect
+        sig = inspect.signature(filtered_lrelu.filtered_lrelu)
+        assert list(sig.parameters) == ['x', 'fu', 'fd', 'b', 'up', 'down', 'padding', 'gain', 'slope', 'clamp', 'flip_filter', 'impl']
+        assert list(inspect.signature(bias_act.bias_act).parameters) == ['x', 'b', 'dim', 'act', 'alpha', 'gain', 'clamp', 'impl']
+        assert list(inspect.signature(upfirdn2d.upfirdn2d).parameters) == ['x', 'f', 'up', 'down', 'padding', 'flip_filter', 'gain', 'impl']
+    finally:
+        for k in [k for k in sys.modules if k == 'torch_utils' or k.startswith('torch_utils.')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
