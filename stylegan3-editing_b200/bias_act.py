@@ -75,7 +75,10 @@ class _BiasAct(torch.autograd.Function):
         identity = act == 'linear' and gain == 1 and clamp < 0 and b is None
         y = x if identity else _launch(x, b, None, None, None, 0, dim, cfg)
         need_x = 'x' in spec.ref or spec.has_2nd_grad
-        ctx.save_for_backward(x if need_x else None, b if need_x else None, y if 'y' in spec.ref else None)
+        # 'linear' saves nothing in the reference (ref=''), which makes its CUDA path ignore the clamp in the
+        # gradient; the impl='ref' semantics (and the oracle) gate on the clamped output, so keep y then.
+        need_y = 'y' in spec.ref or (act == 'linear' and clamp >= 0)
+        ctx.save_for_backward(x if need_x else None, b if need_x else None, y if need_y else None)
         ctx.meta = (dim, act, cfg)
         return y
 
