@@ -1,0 +1,137 @@
+"""modulated_conv2d -- per-sample modulated convolution with weight demodulation on B200.
+
+Mirror of `modulated_conv2d()` in `models/stylegan3/networks_stylegan3.py:24-63` (same signature
+and semantics).  The reference materialises [N,O,I,k,k] weights with ~10 eager kernels and calls a
+cuDNN grouped convolution; here the weight chain is one fused prologue kernel
+(`sg3_modconv_weights`) and the contraction is `sg3_modconv_fwd`:
+  math='fp32'  exact FP32 SIMT contraction (parity mode, <= 1e-5 of the reference's fp32 result)
+  math='tf32'  TF32 tcgen05/TMEM implicit GEMM (the reference's default cuDNN path also allows TF32)
+The default follows `torch.backends.cudnn.allow_tf32`, like the reference's F.conv2d call.
+"""
+import torch
+
+from . import capi
+
+_default_math = None      # None -> follow torch.backends.cudnn.allow_tf32
+
+
+def set_math(mode):
+    """Force 'fp32' / 'tf32' for all modulated_conv2d calls, or None to follow cudnn.allow_tf32."""
+    global _default_math
+    assert mode in (None, 'fp32', 'tf32')
+    _default_math = mode
+
+
+def _math_mode():
+    if _default_math is not None:
+        return _default_math
+    return 'tf32' if torch.backends.cudnn.allow_tf32 else 'fp32'
+
+
+def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False):
+    """[N, O, I*k*k] float32 modulated (+demodulated, +input-gain) weights  (:39-56)."""
+    capi.require_cuda(w, 'modulated_conv2d')
+    O, I, kh, kw = w.shape
+    assert kh == kw
+    N = s.shape[0]
+    w = w.detach().contiguous().float()
+    s = s.detach().contiguous().float()
+    mode, g = 0, None
+    if input_gain is not None:
+        g = input_gain.detach().float()
+        if g.numel() == 1:
+            mode, g = 1, g.reshape(1).contiguous()                 # scalar (the synthesis layers' rsqrt(magnitude_ema))
+        elif g.ndim == 1 and g.shape[0] == I:
+            mode, g = 2, g.contiguous()                            # per input channel
+        else:
+            mode, g = 3, g.expand(N, I).contiguous()               # per (sample, input channel), broadcast like :55
+    wmod = torch.empty([N, O, I * kh * kw], dtype=torch.float32, device=w.device)
+    scratch = torch.empty([1], dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        rc = capi.lib().sg3_modconv_weights(w.data_ptr(), s.data_ptr(), g.data_ptr() if g is not None else None, mode,
+                                            wmod.data_ptr(), scratch.data_ptr(), N, I, O, kh, int(bool(demodulate)),
+                                            int(bool(round_tf32)), capi.stream_ptr(w.device))
+    capi.check(rc, 'sg3_modconv_weights')
+    return wmod
+
+
+def conv_forward(x, wmod, O, k, padding, math):
+    """y[n,o] = sum_i wmod[n,o,i] (*) x[n,i] with zero padding; x float32 contiguous."""
+    N, I, H, W = x.shape
+    OH, OW = H + 2 * padding - k + 1, W + 2 * padding - k + 1
+    y = torch.empty([N, O, OH, OW], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = capi.lib().sg3_modconv_fwd(x.data_ptr(), wmod.data_ptr(), y.data_ptr(), N, I, O, H, W, k, padding,
+                                        1 if math == 'tf32' else 0, capi.SG3_F32, capi.stream_ptr(x.device))
+        if rc == capi.SG3_E_NOKERNEL and math == 'tf32':
+            rc = capi.lib().sg3_modconv_fwd(x.data_ptr(), wmod.data_ptr(), y.data_ptr(), N, I, O, H, W, k, padding,
+                                            0, capi.SG3_F32, capi.stream_ptr(x.device))
+    capi.check(rc, 'sg3_modconv_fwd')
+    return y
+
+
+def _reference_formula(x, w, s, demodulate, padding, input_gain):
+    """The expression of networks_stylegan3.py:39-62 in torch ops; used only to differentiate."""
+    N = x.shape[0]
+    O, I, kh, kw = w.shape
+    if demodulate:
+        w = w * w.square().mean([1, 2, 3], keepdim=True).rsqrt()
+        s = s * s.square().mean().rsqrt()
+    w = w.unsqueeze(0) * s.unsqueeze(1).unsqueeze(3).unsqueeze(4)
+    if demodulate:
+        w = w * (w.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt().unsqueeze(2).unsqueeze(3).unsqueeze(4)
+    if input_gain is not None:
+        w = w * input_gain.expand(N, I).unsqueeze(1).unsqueeze(3).unsqueeze(4)
+    y = torch.nn.functional.conv2d(x.reshape(1, -1, *x.shape[2:]), w.reshape(-1, I, kh, kw).to(x.dtype),
+                                   padding=padding, groups=N)
+    return y.reshape(N, -1, *y.shape[2:])
+
+
+class _ModConv(torch.autograd.Function):
+    """Forward on the sm_100a kernels.  Backward (PTI / fine-tuning) currently differentiates the
+    reference expression with library convolutions (cuDNN dgrad/wgrad); native dgrad/wgrad kernels are
+    the next step and do not change this interface."""
+
+    @staticmethod
+    def forward(ctx, x, w, s, input_gain, demodulate, padding, math):
+        O, I, k, _ = w.shape
+        xin = x.contiguous()
+        x32 = xin if xin.dtype == torch.float32 else xin.float()
+        wmod = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, round_tf32=(math == 'tf32'))
+        y = conv_forward(x32, wmod, O, k, padding, math)
+        ctx.save_for_backward(x, w, s, input_gain)
+        ctx.cfg = (demodulate, padding, math)
+        return y if x.dtype == torch.float32 else y.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, s, input_gain = ctx.saved_tensors
+        demodulate, padding, math = ctx.cfg
+        need = ctx.needs_input_grad[:3]
+        higher_order = torch.is_grad_enabled()
+        with torch.enable_grad(), torch.backends.cudnn.flags(allow_tf32=(math == 'tf32')):
+            xs = x.detach().requires_grad_(need[0])
+            ws = w.detach().requires_grad_(need[1])
+            ss = s.detach().requires_grad_(need[2])
+            y = _reference_formula(xs, ws, ss, demodulate, padding, input_gain)
+            ins = [t for t, n in zip((xs, ws, ss), need) if n]
+            grads = list(torch.autograd.grad(y, ins, dy, create_graph=higher_order)) if ins else []
+        out = [grads.pop(0) if n else None for n in need]
+        return out[0], out[1], out[2], None, None, None, None
+
+
+def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, math=None):
+    """x [N, I, H, W], w [O, I, k, k], s [N, I] -> [N, O, H+2p-k+1, W+2p-k+1].
+
+    w is pre-normalised per output channel and s by the batch RMS when `demodulate`; the modulated
+    weights are demodulated per (sample, output channel); `input_gain` ([], [I] or [N, I]) scales
+    input channels.  `math` overrides the module default ('fp32' | 'tf32').
+    """
+    N = int(x.shape[0])
+    O, I, kh, kw = w.shape
+    assert x.ndim == 4 and x.shape[1] == I and tuple(s.shape) == (N, I) and kh == kw
+    if isinstance(padding, (list, tuple)):
+        assert padding[0] == padding[1]
+        padding = padding[0]
+    capi.require_cuda(x, 'modulated_conv2d')
+    return _ModConv.apply(x, w, s, input_gain, bool(demodulate), int(padding), math or _math_mode())

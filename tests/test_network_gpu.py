@@ -1,0 +1,163 @@
+"""GPU parity of modulated_conv2d and of whole generators against the golden vectors generated
+from the reference (tests/golden/make_golden.py).
+
+Tolerances (max |err| / max |ref|): fp32 math 1e-4 for a 15-layer network (north_star budget
+1e-3); the TF32 tensor-core contraction is stated separately: 2e-3 per conv, 1e-2 per network.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TINY_CFG = dict(
+    tinyR=dict(z_dim=64, c_dim=0, w_dim=64, img_resolution=64, img_channels=3, channel_base=2048, channel_max=32,
+               conv_kernel=1, use_radial_filters=True),
+    tinyT=dict(z_dim=64, c_dim=0, w_dim=64, img_resolution=64, img_channels=3, channel_base=2048, channel_max=32,
+               conv_kernel=3, use_radial_filters=False),
+)
+
+
+@pytest.fixture(scope='module')
+def pkg():
+    import sg3_b200
+    from sg3_b200 import modulated_conv, networks  # noqa: F401
+    sg3_b200.filtered_lrelu._quiet_fallback = True
+    return sg3_b200
+
+
+def cu(a, grad=False):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda().requires_grad_(grad)
+
+
+@pytest.mark.parametrize('math,tol', [('fp32', 2e-5), ('tf32', 2e-3)])
+@pytest.mark.parametrize('case', golden('modconv.npz').cases('modconv'))
+def test_modulated_conv2d_golden(pkg, case, math, tol):
+    c = golden('modconv.npz').case('modconv', case)
+    k = c['w'].shape[-1]
+    x, w, s = cu(c['x'], True), cu(c['w'], True), cu(c['s'], True)
+    g = cu(c['input_gain']) if 'input_gain' in c else None
+    y = pkg.modulated_conv.modulated_conv2d(x, w, s, demodulate=bool(c['demodulate']), padding=k - 1, input_gain=g, math=math)
+    assert tuple(y.shape) == c['y'].shape
+    assert rel_err(y.detach().cpu().numpy(), c['y']) < tol
+    dx, dw, ds = torch.autograd.grad(y, [x, w, s], cu(c['dy']))
+    assert rel_err(dx.cpu().numpy(), c['dx']) < 2e-3
+    assert rel_err(dw.cpu().numpy(), c['dw']) < 2e-3
+    assert rel_err(ds.cpu().numpy(), c['ds']) < 2e-3
+
+
+def test_modconv_weights_vs_oracle(pkg):
+    from oracle import sg3_oracle as orc
+    rng = np.random.RandomState(3)
+    w = rng.randn(37, 29, 3, 3).astype(np.float32)
+    s = (rng.randn(5, 29) + 1).astype(np.float32)
+    ref = orc.modconv_weights(w, s, True, np.float32(0.7)).reshape(5, 37, -1)
+    got = pkg.modulated_conv.modconv_weights(cu(w), cu(s), True, torch.tensor(0.7).cuda())
+    assert rel_err(got.cpu().numpy(), ref) < 1e-5
+    ref = orc.modconv_weights(w, s, False, None).reshape(5, 37, -1)
+    got = pkg.modulated_conv.modconv_weights(cu(w), cu(s), False, None)
+    assert rel_err(got.cpu().numpy(), ref) < 1e-6
+
+
+def _build(pkg, name):
+    torch.manual_seed(0)
+    G = pkg.networks.Generator(**TINY_CFG[name]).eval().requires_grad_(False)
+    g = golden('tiny.npz')
+    sd = {k: torch.from_numpy(v) for k, v in g.sub(f'{name}/state/').items()}
+    for k, v in G.synthesis.state_dict().items():     # same seed -> same random init as the reference
+        assert torch.equal(v, sd[k]), k
+    return G.cuda(), g
+
+
+@pytest.mark.parametrize('name', ['tinyR', 'tinyT'])
+def test_tiny_generator_fp32(pkg, name):
+    G, g = _build(pkg, name)
+    pkg.modulated_conv.set_math('fp32')
+    try:
+        z = cu(g.z[f'{name}/z'])
+        ws = G.mapping(z, None)
+        assert rel_err(ws.cpu().numpy(), g.z[f'{name}/ws']) < 1e-5          # mapping network (bias_act lrelu)
+        ws = cu(g.z[f'{name}/ws'])
+        img = G.synthesis(ws, noise_mode='const', force_fp32=True)
+        assert rel_err(img.cpu().numpy(), g.z[f'{name}/img']) < 1e-4
+        x = G.synthesis.input(ws[:, 0])
+        assert rel_err(x[:1, :8].cpu().numpy(), g.z[f'{name}/feat/input']) < 1e-5
+        for i, lname in enumerate(G.synthesis.layer_names[:13]):
+            x = getattr(G.synthesis, lname)(x, ws[:, i + 1], noise_mode='const', force_fp32=True)
+            if i in (0, 2, 7, 12):
+                assert rel_err(x[:1, :8].cpu().numpy(), g.z[f'{name}/feat/after_{i}']) < 1e-4, lname
+        # S-space path gives the same image
+        img2 = G.synthesis(None, all_s=G.synthesis.W2S(ws), noise_mode='const', force_fp32=True)
+        assert rel_err(img2.cpu().numpy(), g.z[f'{name}/img']) < 1e-4
+    finally:
+        pkg.modulated_conv.set_math(None)
+
+
+@pytest.mark.parametrize('name', ['tinyR', 'tinyT'])
+def test_tiny_generator_tf32(pkg, name):
+    G, g = _build(pkg, name)
+    pkg.modulated_conv.set_math('tf32')
+    try:
+        img = G.synthesis(cu(g.z[f'{name}/ws']), noise_mode='const', force_fp32=True)
+        assert rel_err(img.cpu().numpy(), g.z[f'{name}/img']) < 1e-2
+    finally:
+        pkg.modulated_conv.set_math(None)
+
+
+@pytest.mark.parametrize('name', ['tinyR', 'tinyT'])
+def test_tiny_generator_fp16_layers(pkg, name):
+    """force_fp32=False: layers flagged use_fp16 run with fp16 activations (reference :355)."""
+    G, g = _build(pkg, name)
+    img = G.synthesis(cu(g.z[f'{name}/ws']), noise_mode='const')
+    assert img.dtype == torch.float32
+    assert rel_err(img.cpu().numpy(), g.z[f'{name}/img']) < 2e-2
+
+
+@pytest.mark.parametrize('name', ['tinyR', 'tinyT'])
+def test_tiny_generator_gradients(pkg, name):
+    """PTI-style: gradients of a scalar loss wrt every synthesis parameter vs the reference's autograd."""
+    G, g = _build(pkg, name)
+    pkg.modulated_conv.set_math('fp32')
+    try:
+        G.requires_grad_(True)
+        img = G.synthesis(cu(g.z[f'{name}/ws']), noise_mode='const', force_fp32=True)
+        loss = (img * cu(g.z[f'{name}/tgt'])).mean()
+        assert abs(float(loss) - float(g.z[f'{name}/loss'])) < 1e-5 * max(1.0, abs(float(g.z[f'{name}/loss']))) + 1e-7
+        params = dict(G.synthesis.named_parameters())
+        grads = torch.autograd.grad(loss, list(params.values()), allow_unused=True)
+        checked = 0
+        for (k, _), gr in zip(params.items(), grads):
+            key = f'{name}/grad/{k}'
+            if key in g.z.files:
+                ref = g.z[key]
+                if np.abs(ref).max() > 0:
+                    assert rel_err(gr.cpu().numpy(), ref) < 2e-3, k
+                    checked += 1
+        assert checked >= 55
+    finally:
+        pkg.modulated_conv.set_math(None)
+
+
+def test_r256_config1(pkg):
+    """BASELINE.json configs[0]: StyleGAN3-R 256^2, seed-0 random init, batch 4, fp32 -- against the image the
+    reference produced on CPU with impl='ref' (strided subsample stored in tests/golden/r256.npz)."""
+    g = golden('r256.npz').z
+    torch.manual_seed(0)
+    G = pkg.networks.Generator(z_dim=512, c_dim=0, w_dim=512, img_resolution=256, img_channels=3,
+                               **pkg.networks.CONFIG_R).eval().requires_grad_(False)
+    sd = G.synthesis.state_dict()
+    names = G.synthesis.layer_names
+    for key in ['input.weight', 'input.freqs', names[0] + '.weight', names[13] + '.weight', names[14] + '.affine.weight']:
+        assert np.array_equal(sd[key].flatten()[:64].numpy(), g['r256/probe/' + key]), key
+    G = G.cuda()
+    pkg.modulated_conv.set_math('fp32')
+    try:
+        img = G.synthesis(cu(g['r256/ws']), noise_mode='const', force_fp32=True)
+    finally:
+        pkg.modulated_conv.set_math(None)
+    sub = img[:, :, ::4, ::4].cpu().numpy()
+    assert rel_err(sub, g['r256/img_sub4']) < 1e-3
+    stats = np.asarray([float(img.mean()), float(img.std()), float(img.abs().max())])
+    assert np.allclose(stats, g['r256/stats'], rtol=1e-3, atol=1e-5)
