@@ -44,6 +44,7 @@ extern "C" {
 int         sg3_abi_version(void);
 const char* sg3_error_string(int code);       /* static string for SG3_E_* / cudaError_t codes */
 const char* sg3_build_info(void);             /* "sm_100a nvcc x.y ..." */
+unsigned long long sg3_launch_count(void);    /* kernels launched by this library since load (all threads) */
 
 /* ------------------------------------------------------------------------
  * filtered_lrelu: bias -> zero-insert upsample + FIR -> gain*lrelu, clamp (+2-bit

@@ -44,6 +44,7 @@ _PROTOS = {
     'sg3_abi_version': (ctypes.c_int, []),
     'sg3_error_string': (ctypes.c_char_p, [_I]),
     'sg3_build_info': (ctypes.c_char_p, []),
+    'sg3_launch_count': (ctypes.c_ulonglong, []),
     'sg3_filtered_lrelu_shape': (_I, [_I] * 12 + [_IP] * 4),
     'sg3_filtered_lrelu_supported': (_I, [_I] * 6),
     'sg3_filtered_lrelu': (_I, [ctypes.POINTER(FlreluDesc), _P]),

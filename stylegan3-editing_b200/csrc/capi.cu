@@ -1,5 +1,10 @@
 // capi.cu -- ABI housekeeping for libsg3_b200.so.
 #include "common.cuh"
+#include <atomic>
+
+static std::atomic<unsigned long long> g_launches{0};
+void sg3_note_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+SG3_EXPORT unsigned long long sg3_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 #define SG3_STR2(x) #x
 #define SG3_STR(x) SG3_STR2(x)

@@ -20,8 +20,12 @@ template <> __device__ __forceinline__ float ld_as<__half>(const __half* p) { re
 template <class T> __device__ __forceinline__ void st_as(T* p, typename Arith<T>::type v) { *p = (T)v; }
 template <> __device__ __forceinline__ void st_as<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 
-static inline int sg3_launch_status()
+// Every kernel launch of this library is counted (sg3_launch_count) so callers can prove which path ran.
+void sg3_note_launches(int n);
+
+static inline int sg3_launch_status(int launches = 1)
 {
+    sg3_note_launches(launches);
     cudaError_t e = cudaPeekAtLastError();
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
     return 0;

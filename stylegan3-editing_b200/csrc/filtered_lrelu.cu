@@ -1,7 +1,15 @@
-// filtered_lrelu.cu -- host side of the fused filtered leaky-ReLU (geometry, dispatch).
-// The fused sm_100a kernel is in flrelu_fused.cuh; this first cut only answers geometry
-// queries and reports SG3_E_NOKERNEL so the caller runs the generic composition.
-#include "common.cuh"
+// filtered_lrelu.cu -- C-ABI entry points of the fused filtered leaky-ReLU: geometry queries,
+// specialisation table and launch of the warp-streaming kernel (flrelu_stream.cuh).
+//
+// Replaces filtered_lrelu.cpp:16-209 of the reference.  Differences by design: taps are passed by
+// value in the launch parameters (no setup kernel, no cudaMemcpyToSymbol, no global state -> one launch
+// per call and safe on any stream); tiles are scheduled as a 1-D list of warp strips (no grid-z limit,
+// 64-bit addressing throughout).
+#include <mutex>
+
+#include "flrelu_stream.cuh"
+
+namespace fs = flrelu_stream;
 
 SG3_EXPORT int sg3_filtered_lrelu_shape(int inH, int inW, int up, int down,
                                         int fuW, int fuH, int fdW, int fdH,
@@ -9,7 +17,7 @@ SG3_EXPORT int sg3_filtered_lrelu_shape(int inH, int inW, int up, int down,
                                         int* outH, int* outW, int* sH, int* sWb)
 {
     if (inH < 1 || inW < 1 || up < 1 || down < 1 || fuW < 1 || fdW < 1 || fuH < 0 || fdH < 0) return SG3_E_INVALID;
-    const int fuh = fuH ? fuH : fuW, fdh = fdH ? fdH : fdW;     // separable filters are square in effect
+    const int fuh = fuH ? fuH : fuW, fdh = fdH ? fdH : fdW;     // a separable filter acts as taps x taps
     const int64_t cw = (int64_t)inW * up + px0 + px1 - (fuW - 1);
     const int64_t ch = (int64_t)inH * up + py0 + py1 - (fuh - 1);
     if (cw <= fdW - 1 || ch <= fdh - 1) return SG3_E_INVALID;  // upsampled buffer smaller than the down filter
@@ -26,13 +34,106 @@ SG3_EXPORT int sg3_filtered_lrelu_shape(int inH, int inW, int up, int down,
 
 SG3_EXPORT int sg3_filtered_lrelu_supported(int up, int down, int fuW, int fuH, int fdW, int fdH)
 {
-    (void)up; (void)down; (void)fuW; (void)fuH; (void)fdW; (void)fdH;
-    return SG3_E_NOKERNEL;
+    if (down != 2 || (up != 2 && up != 4)) return SG3_E_NOKERNEL;
+    if (fuH != 0 || fuW < 1 || fuW > fs::kTapsPerPhase * up) return SG3_E_NOKERNEL;      // separable up filter only
+    if (fdW < 1 || fdW > fs::kDownTaps || fdH > fs::kDownTaps) return SG3_E_NOKERNEL;
+    return 0;
 }
+
+namespace {
+
+template <class T, int UP, bool FULL, int MODE>
+int launch_stream(const fs::Params& p, cudaStream_t stream)
+{
+    auto kern = fs::kernel<T, UP, FULL, MODE>;
+    const int smem = fs::kWarpsPerCta * fs::Geo<UP>::WARP_BYTES;
+    static std::once_flag once;
+    static cudaError_t attrErr = cudaSuccess;
+    std::call_once(once, [&] { attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    if (attrErr != cudaSuccess) return (int)attrErr;
+    const long long ctas = (p.totalStrips + fs::kWarpsPerCta - 1) / fs::kWarpsPerCta;
+    if (ctas > 0x7fffffffLL) return SG3_E_TOOLARGE;
+    kern<<<(unsigned)ctas, fs::kWarpsPerCta * 32, smem, stream>>>(p);
+    return sg3_launch_status();
+}
+
+template <class T, int UP, bool FULL>
+int dispatch_mode(const fs::Params& p, int mode, cudaStream_t stream)
+{
+    switch (mode) {
+    case SG3_SIGNS_NONE:  return launch_stream<T, UP, FULL, SG3_SIGNS_NONE>(p, stream);
+    case SG3_SIGNS_WRITE: return launch_stream<T, UP, FULL, SG3_SIGNS_WRITE>(p, stream);
+    case SG3_SIGNS_READ:  return launch_stream<T, UP, FULL, SG3_SIGNS_READ>(p, stream);
+    }
+    return SG3_E_INVALID;
+}
+
+template <class T>
+int dispatch_shape(const fs::Params& p, int up, bool full, int mode, cudaStream_t stream)
+{
+    if (up == 2) return full ? dispatch_mode<T, 2, true>(p, mode, stream) : dispatch_mode<T, 2, false>(p, mode, stream);
+    return full ? dispatch_mode<T, 4, true>(p, mode, stream) : dispatch_mode<T, 4, false>(p, mode, stream);
+}
+
+}  // namespace
 
 SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
 {
-    (void)stream;
-    if (!d) return SG3_E_INVALID;
-    return SG3_E_NOKERNEL;
+    if (!d || !d->x || !d->y) return SG3_E_INVALID;
+    if (d->N < 1 || d->C < 1 || d->inH < 1 || d->inW < 1 || d->outH < 1 || d->outW < 1) return SG3_E_INVALID;
+    if (d->dtype != SG3_F32 && d->dtype != SG3_F16) return SG3_E_NOKERNEL;
+    const int fuW = d->fu ? d->fuW : 1, fuH = d->fu ? d->fuH : 1;
+    const int fdW = d->fd ? d->fdW : 1, fdH = d->fd ? d->fdH : 1;
+    int rc = sg3_filtered_lrelu_supported(d->up, d->down, fuW, fuH, fdW, fdH);
+    if (rc != 0) return rc;
+    if (d->signMode != SG3_SIGNS_NONE && (!d->signs || d->sH < 1 || d->sWb < 1)) return SG3_E_INVALID;
+    if (d->signMode == SG3_SIGNS_WRITE && (d->sx & 3)) return SG3_E_NOKERNEL;   // sign bytes must align with strips
+
+    fs::Params p;
+    p.x = d->x; p.y = d->y; p.b = d->b; p.s = d->signs;
+    p.N = d->N; p.C = d->C; p.inH = d->inH; p.inW = d->inW; p.outH = d->outH; p.outW = d->outW;
+    for (int i = 0; i < 4; i++) { p.xs[i] = d->xStride[i]; p.ys[i] = d->yStride[i]; }
+    p.bs = d->bStride;
+    p.px0 = d->px0; p.py0 = d->py0;
+    p.gain = d->gain; p.slope = d->slope; p.clamp = d->clamp;
+    p.sH = d->sH; p.sWb = d->sWb; p.sx = d->sx; p.sy = d->sy;
+
+    // Correlation-ordered taps: F'[b] = f[b] if flip else f[last - b]; zero beyond the real filter.
+    const int up = d->up;
+    for (int ph = 0; ph < 4; ph++)
+        for (int k = 0; k < fs::kTapsPerPhase; k++) {
+            float v = 0.f;
+            if (ph < up) {
+                const int b = ((up - ph) % up) + up * k;
+                if (b < fuW) v = (float)up * (d->fu ? d->fu[d->flip ? b : fuW - 1 - b] : 1.0f);
+            }
+            p.tu[ph][k] = v;
+        }
+    const bool full = fdH != 0 && d->fd != nullptr;
+    for (int b = 0; b < fs::kDownTaps; b++)
+        p.fdx[b] = (!full && b < fdW) ? (d->fd ? d->fd[d->flip ? b : fdW - 1 - b] : 1.0f) : 0.f;
+    for (int a = 0; a < fs::kDownTaps; a++)
+        for (int b = 0; b < fs::kDownTaps; b++)
+            p.fd2[a][b] = (full && a < fdH && b < fdW) ? d->fd[(d->flip ? a : fdH - 1 - a) * fdW + (d->flip ? b : fdW - 1 - b)] : 0.f;
+
+    // Strip decomposition: 64-column strips; rows are chunked only when there are too few strips to
+    // fill the machine (one warp per strip, ~16 resident warps per SM, a few waves).
+    const long long planes = (long long)d->N * d->C;
+    p.stripsX = (d->outW + fs::kTW - 1) / fs::kTW;
+    const long long base = planes * p.stripsX;
+    const long long want = (long long)sg3_sm_count() * 16 * 3;
+    int chunks = 1;
+    if (base < want) {
+        chunks = (int)((want + base - 1) / base);
+        const int maxChunks = (d->outH + 31) / 32;            // at least 32 output rows per chunk
+        if (chunks > maxChunks) chunks = maxChunks;
+        if (chunks < 1) chunks = 1;
+    }
+    p.chunkRows = (d->outH + chunks - 1) / chunks;
+    p.chunksY = (d->outH + p.chunkRows - 1) / p.chunkRows;
+    p.totalStrips = base * p.chunksY;
+
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d->dtype == SG3_F32) return dispatch_shape<float>(p, up, full, d->signMode, st);
+    return dispatch_shape<__half>(p, up, full, d->signMode, st);
 }

@@ -1,0 +1,374 @@
+// flrelu_stream.cuh -- fused filtered leaky-ReLU, warp-streaming kernel for sm_100a.
+//
+// What it computes: torch_utils/ops/filtered_lrelu.py:122-154 / filtered_lrelu.cu:139-1099 of the
+// reference, for a separable up filter (UP = 2 or 4, <= 6 taps per phase) and a down-by-2 filter of
+// <= 12 taps, separable or dense 12x12 (the radial filters of config R):
+//   bias -> zero-insert x UP + FIR -> gain * lrelu, clamp (+ 2-bit sign codes) -> FIR + decimate by 2.
+//
+// How (B200-first; nothing here follows the reference's block-tile kernel):
+//  * One WARP owns one strip: 64 output columns x a chunk of output rows of one (n, c) plane, and
+//    streams down the rows.  Warps never synchronise with each other (no __syncthreads): each has a
+//    private shared-memory ring, so 16-20 resident warps per SM sit in different stages and the LSU,
+//    FMA and global-load latencies of one warp hide behind the others.
+//  * Per iteration a warp produces one GROUP = 4 activation rows = 2 output rows:
+//      A  global -> registers (prefetched one iteration ahead) -> smem, bias added, zero outside
+//      B  horizontal polyphase upsample of 2 input rows       (lane = input column)
+//      C  vertical polyphase upsample + gain/lrelu/clamp/signs (lane = 2 adjacent columns)
+//      D  down-by-2 FIR accumulated in registers               (lane = 2 adjacent output columns)
+//  * All FIR arithmetic is packed FFMA2 (fma.rn.f32x2): one instruction = 2 FMAs with the tap as a
+//    broadcast uniform-register operand (SASS: FFMA2 R, R.F32x2, UR.F32, R.F32x2).  The packed pair
+//    is always "same tap, two pixels": two input rows in B, two columns in C, and in D the two
+//    activation rows (Y, Y+2) that feed output rows (o, o+1) with the same filter row.  Measured on
+//    B200: 36.4 TFMA/s vs 30.3 for scalar FFMA, and the issue port is half idle for LDS/ALU work.
+//  * D never re-reads an activation: each loaded value feeds 6 (rows) x up to 2 (columns) x 2 (FFMA2
+//    lanes) MACs; the 6 live output-row pairs per column stay in registers and retire 2 rows per
+//    group.  Activations for D are laid out [column parity][column/2][4 rows permuted (0,2,1,3)] so
+//    one conflict-free LDS.128 yields both row pairs of a pixel.
+//  * Taps travel in the launch parameters (constant bank -> uniform registers); no global filter
+//    state, any stream.
+//
+// Roofline note: with fp32 math this op is FP32-pipe bound on B200 (144 MAC per output for
+// the dense 12x12 down filter against 8 bytes of HBM traffic), so the kernel is built to saturate the
+// FMA pipe; HBM time is ~4x smaller than FMA time for config R.
+#pragma once
+
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace flrelu_stream {
+
+constexpr int kTapsPerPhase = 6;      // up filter taps per polyphase branch
+constexpr int kDownTaps = 12;         // down filter taps (per axis)
+constexpr int kTW = 64;               // output columns per strip (2 per lane)
+constexpr int kAW = 2 * (kTW - 1) + kDownTaps;   // 138 activation columns feed one strip
+constexpr int kRing = 12;             // rows in the horizontally-upsampled ring
+constexpr int kWarpsPerCta = 4;
+
+template <int UP> struct Geo {
+    static constexpr int BW = ((kAW + UP - 1 + UP - 1) / UP) * UP;   // upsampled columns computed per strip (140 / 144)
+    static constexpr int NM = BW / UP;                               // input columns producing them (70 / 36)
+    static constexpr int TIW = NM + kTapsPerPhase;                   // input columns loaded (76 / 42)
+    static constexpr int A_ITEMS = (2 * TIW + 31) / 32;              // prefetch registers per lane
+    static constexpr int XH = 72;                                    // slots per parity plane (>= kAW/2 + 1, even)
+    static constexpr int SIN_BYTES = TIW * 2 * 4;
+    static constexpr int SB_BYTES = kRing * BW * 4;
+    static constexpr int SC_BYTES = 2 * XH * 16;
+    static constexpr int SS_ROW = 160;                               // sign staging bytes per row (>= BW + 3, mult of 16)
+    static constexpr int SS_BYTES = 4 * SS_ROW;
+    static constexpr int WARP_BYTES = ((SIN_BYTES + SB_BYTES + SC_BYTES + SS_BYTES + 127) / 128) * 128;
+};
+
+struct Params {
+    const void* x; void* y; const void* b; uint8_t* s;
+    int N, C, inH, inW, outH, outW;
+    long long xs[4], ys[4], bs;        // byte strides
+    int px0, py0;
+    float gain, slope, clamp;
+    int sH, sWb, sx, sy;
+    int stripsX, chunksY, chunkRows;
+    long long totalStrips;
+    float tu[4][kTapsPerPhase];        // tu[p][k]: up taps of phase p, pre-scaled by UP (both axes use them)
+    float fdx[kDownTaps];              // separable down taps (correlation order); unused when dense
+    float fd2[kDownTaps][kDownTaps];   // dense down taps fd2[a][b] (correlation order); unused when separable
+};
+
+__device__ __forceinline__ float2 ffma2(float2 a, float t, float2 c) { return __ffma2_rn(a, make_float2(t, t), c); }
+
+__device__ __forceinline__ int swz(int xh) { return xh ^ ((xh >> 3) & 1); }
+
+// gain / leaky ReLU / clamp of one value; returns the 2-bit sign code.
+template <int MODE>
+__device__ __forceinline__ float act1(float u, float gain, float slope, float clamp, unsigned rd_code, unsigned& wr_code)
+{
+    float v = u * gain;
+    if (MODE == SG3_SIGNS_READ) {
+        if (rd_code & 1u) v *= slope;
+        if (rd_code & 2u) v = 0.f;
+        return v;
+    }
+    const bool neg = v < 0.f;
+    v = neg ? v * slope : v;
+    const bool cl = fabsf(v) > clamp;
+    v = cl ? copysignf(clamp, v) : v;
+    if (MODE == SG3_SIGNS_WRITE) wr_code = cl ? 2u : (neg ? 1u : 0u);
+    return v;
+}
+
+template <class T, int UP, bool FD_FULL, int MODE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_constant__ Params p)
+{
+    typedef Geo<UP> G;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long strip = (long long)blockIdx.x * kWarpsPerCta + warp;
+    if (strip >= p.totalStrips) return;
+
+    unsigned char* wsm = smem_raw + warp * G::WARP_BYTES;
+    float2* sIn = (float2*)wsm;                                        // [TIW] (row 2t, row 2t+1)
+    float* sB = (float*)(wsm + G::SIN_BYTES);                          // [kRing][BW]
+    float4* sC = (float4*)(wsm + G::SIN_BYTES + G::SB_BYTES);          // [2][XH] rows (0,2,1,3) of one pixel
+    unsigned char* sS = wsm + G::SIN_BYTES + G::SB_BYTES + G::SC_BYTES;  // [4][SS_ROW] sign codes, one byte per pixel
+
+    // ---- strip geometry --------------------------------------------------------------------------
+    const int sxi = (int)(strip % p.stripsX);
+    const long long rest = strip / p.stripsX;
+    const int cyi = (int)(rest % p.chunksY);
+    const long long plane = rest / p.chunksY;
+    const int n = (int)(plane / p.C), c = (int)(plane - (long long)n * p.C);
+    const int ox0 = sxi * kTW;
+    const int oy0 = cyi * p.chunkRows;
+    const int tws = min(kTW, p.outW - ox0);                  // valid output columns in this strip
+    const int chs = min(p.chunkRows, p.outH - oy0);          // valid output rows in this chunk
+    const int Xs = 2 * ox0, Ys = 2 * oy0;                    // activation-space origin of D
+    const int ex = pos_mod(Xs - p.px0, UP), ey = pos_mod(Ys - p.py0, UP);
+    const int jBase = (Xs - ex - p.px0) / UP;                // exact: first input column of the strip (may be < 0)
+    const int iBase = (Ys - ey - p.py0) / UP;
+    const int numGroups = (2 * chs + 10 + 3) >> 2;           // activation rows 0 .. 2*(chs-1)+11 in groups of 4
+
+    const char* xPlane = (const char*)p.x + n * p.xs[0] + c * p.xs[1];
+    char* yPlane = (char*)p.y + n * p.ys[0] + c * p.ys[1];
+    const float bias = p.b ? (float)ld_as<T>((const T*)((const char*)p.b + c * p.bs)) : 0.f;
+
+    // ---- stage A: global -> registers (pair t = input rows 2t, 2t+1 of the strip) -----------------
+    float pre[G::A_ITEMS];
+    auto loadPair = [&](int t) {
+#pragma unroll
+        for (int r = 0; r < G::A_ITEMS; r++) {
+            const int e = lane + 32 * r;
+            const int row = e >= G::TIW ? 1 : 0;
+            const int jl = e - row * G::TIW;
+            const int i = iBase + 2 * t + row, j = jBase + jl;
+            float v = 0.f;
+            if (e < 2 * G::TIW && i >= 0 && i < p.inH && j >= 0 && j < p.inW)
+                v = (float)ld_as<T>((const T*)(xPlane + i * p.xs[2] + j * p.xs[3])) + bias;
+            pre[r] = v;
+        }
+    };
+    auto storePair = [&]() {
+#pragma unroll
+        for (int r = 0; r < G::A_ITEMS; r++) {
+            const int e = lane + 32 * r;
+            const int row = e >= G::TIW ? 1 : 0;
+            const int jl = e - row * G::TIW;
+            if (e < 2 * G::TIW) ((float*)sIn)[jl * 2 + row] = pre[r];
+        }
+    };
+
+    // ---- stage B: horizontal upsample of the pair held in sIn -> ring rows 2t, 2t+1 ----------------
+    auto stageB = [&](int t) {
+        float* row0 = sB + ((2 * t) % kRing) * G::BW;
+        float* row1 = sB + ((2 * t + 1) % kRing) * G::BW;
+#pragma unroll
+        for (int r = 0; r < (G::NM + 31) / 32; r++) {
+            const int m = lane + 32 * r;
+            if (m < G::NM) {
+                float2 v[kTapsPerPhase + 1];
+#pragma unroll
+                for (int q = 0; q <= kTapsPerPhase; q++) v[q] = sIn[m + q];
+                float2 acc[UP];
+#pragma unroll
+                for (int ph = 0; ph < UP; ph++) {
+                    acc[ph] = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < kTapsPerPhase; k++) acc[ph] = ffma2(v[k + (ph > 0 ? 1 : 0)], p.tu[ph][k], acc[ph]);
+                }
+                if (UP == 2) {
+                    *(float2*)(row0 + 2 * m) = make_float2(acc[0].x, acc[1].x);
+                    *(float2*)(row1 + 2 * m) = make_float2(acc[0].y, acc[1].y);
+                } else {
+                    *(float4*)(row0 + 4 * m) = make_float4(acc[0].x, acc[1].x, acc[2 % UP].x, acc[3 % UP].x);
+                    *(float4*)(row1 + 4 * m) = make_float4(acc[0].y, acc[1].y, acc[2 % UP].y, acc[3 % UP].y);
+                }
+            }
+        }
+    };
+
+    // ---- stage C: vertical upsample + activation of group g -> sC (+ sign codes) --------------------
+    const long long sPlane = (long long)plane * p.sH;
+    auto stageC = [&](int g, auto EYc) {
+        constexpr int EY = decltype(EYc)::value;
+        const int wbase = (UP == 2 ? 2 * g : g) % kRing;
+#pragma unroll
+        for (int r = 0; r < (G::BW / 2 + 31) / 32; r++) {
+            const int pr = lane + 32 * r;
+            if (pr < G::BW / 2) {
+                const int xp = 2 * pr;
+                float2 w[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    int slot = wbase + q;
+                    slot -= slot >= kRing ? kRing : 0;
+                    w[q] = *(const float2*)(sB + slot * G::BW + xp);
+                }
+                float2 v[4];
+                unsigned code0[4], code1[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int yq = j + EY;                  // row offset in the UP-aligned grid
+                    const int ph = yq % UP;                 // compile-time after unrolling
+                    const int start = yq / UP + (ph > 0 ? 1 : 0);
+                    float2 u = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < kTapsPerPhase; k++) u = ffma2(w[start + k], p.tu[ph][k], u);
+                    unsigned rc0 = 0, rc1 = 0;
+                    if (MODE == SG3_SIGNS_READ) {
+                        const int sY = Ys + 4 * g + j + p.sy;
+                        const int sX = Xs - ex + xp + p.sx;
+                        if (sY >= 0 && sY < p.sH) {
+                            const uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
+                            if (sX >= 0 && (sX >> 2) < p.sWb) rc0 = (unsigned)__ldg(srow + (sX >> 2)) >> ((sX & 3) * 2);
+                            if (sX + 1 >= 0 && ((sX + 1) >> 2) < p.sWb) rc1 = (unsigned)__ldg(srow + ((sX + 1) >> 2)) >> (((sX + 1) & 3) * 2);
+                        }
+                    }
+                    v[j].x = act1<MODE>(u.x, p.gain, p.slope, p.clamp, rc0, code0[j]);
+                    v[j].y = act1<MODE>(u.y, p.gain, p.slope, p.clamp, rc1, code1[j]);
+                }
+                const int xd0 = xp - ex, xd1 = xd0 + 1;     // column index in D's frame
+                if (xd0 >= 0 && xd0 < kAW) {
+                    sC[(xd0 & 1) * G::XH + swz(xd0 >> 1)] = make_float4(v[0].x, v[2].x, v[1].x, v[3].x);
+                    if (MODE == SG3_SIGNS_WRITE) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) sS[j * G::SS_ROW + xd0] = (unsigned char)code0[j];
+                    }
+                }
+                if (xd1 >= 0 && xd1 < kAW) {
+                    sC[(xd1 & 1) * G::XH + swz(xd1 >> 1)] = make_float4(v[0].y, v[2].y, v[1].y, v[3].y);
+                    if (MODE == SG3_SIGNS_WRITE) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) sS[j * G::SS_ROW + xd1] = (unsigned char)code1[j];
+                    }
+                }
+            }
+        }
+    };
+
+    // sign bytes this strip owns: columns [0, ownW) of D's frame (whole bytes: Xs + sx is a multiple of 4),
+    // rows [0, ownH) -- the last strip/chunk also owns the filter tail.
+    const int ownW = (sxi == p.stripsX - 1) ? 2 * (tws - 1) + kDownTaps : 2 * kTW;
+    const int ownH = (cyi == p.chunksY - 1) ? 2 * (chs - 1) + kDownTaps : 2 * p.chunkRows;
+    auto flushSigns = [&](int g) {
+        if (MODE != SG3_SIGNS_WRITE) return;
+        const int nb = (ownW + 3) >> 2;
+        const int byte0 = (Xs + p.sx) >> 2;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int rd = 4 * g + j;
+            const int sY = Ys + rd + p.sy;
+            if (rd >= ownH || sY < 0 || sY >= p.sH) continue;
+            uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
+            for (int q = lane; q < nb; q += 32) {
+                const unsigned wv = *(const unsigned*)(sS + j * G::SS_ROW + 4 * q);
+                const unsigned packed = (wv | (wv >> 6) | (wv >> 12) | (wv >> 18)) & 0xffu;
+                const int bq = byte0 + q;
+                if (bq >= 0 && bq < p.sWb) srow[bq] = (uint8_t)packed;
+            }
+        }
+    };
+
+    // ---- stage D: down-by-2 FIR, accumulated in registers -------------------------------------------
+    // acc[k][c] = (partial of output row 2g-k, partial of output row 2g-k+1) for output column 2*lane+c.
+    float2 acc[6][2];
+    float carry[2] = {0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 6; k++) { acc[k][0] = make_float2(0.f, 0.f); acc[k][1] = make_float2(0.f, 0.f); }
+
+    auto stageD = [&](int g) {
+        const float4* planeE = sC;
+        const float4* planeO = sC + G::XH;
+        if (FD_FULL) {
+#pragma unroll
+            for (int q = 0; q < kDownTaps + 2; q++) {         // pixel 4*lane + q of D's frame
+                const float4 px = (q & 1) ? planeO[swz(2 * lane + (q >> 1))] : planeE[swz(2 * lane + (q >> 1))];
+                const float2 pa = make_float2(px.x, px.y);  // rows 4g, 4g+2
+                const float2 pb = make_float2(px.z, px.w);  // rows 4g+1, 4g+3
+#pragma unroll
+                for (int cc = 0; cc < 2; cc++) {
+                    const int b = q - 2 * cc;               // tap column for output column 2*lane+cc
+                    if (b >= 0 && b < kDownTaps) {
+#pragma unroll
+                        for (int k = 0; k < 6; k++) {
+                            acc[k][cc] = ffma2(pa, p.fd2[2 * k][b], acc[k][cc]);
+                            acc[k][cc] = ffma2(pb, p.fd2[2 * k + 1][b], acc[k][cc]);
+                        }
+                    }
+                }
+            }
+        } else {
+            float2 ha[2], hb[2];
+            ha[0] = ha[1] = hb[0] = hb[1] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < kDownTaps + 2; q++) {
+                const float4 px = (q & 1) ? planeO[swz(2 * lane + (q >> 1))] : planeE[swz(2 * lane + (q >> 1))];
+                const float2 pa = make_float2(px.x, px.y);
+                const float2 pb = make_float2(px.z, px.w);
+#pragma unroll
+                for (int cc = 0; cc < 2; cc++) {
+                    const int b = q - 2 * cc;
+                    if (b >= 0 && b < kDownTaps) {
+                        ha[cc] = ffma2(pa, p.fdx[b], ha[cc]);
+                        hb[cc] = ffma2(pb, p.fdx[b], hb[cc]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < 2; cc++)
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    acc[k][cc] = ffma2(ha[cc], p.fdx[2 * k], acc[k][cc]);
+                    acc[k][cc] = ffma2(hb[cc], p.fdx[2 * k + 1], acc[k][cc]);
+                }
+        }
+        // retire output rows 2g-5 and 2g-4, then slide the accumulators down by two rows
+        const int oA = 2 * g - 5, oB = 2 * g - 4;
+        const float a0 = acc[5][0].x + carry[0], a1 = acc[5][1].x + carry[1];
+        const float b0 = acc[4][0].x + acc[5][0].y, b1 = acc[4][1].x + acc[5][1].y;
+        carry[0] = acc[4][0].y; carry[1] = acc[4][1].y;
+        const int oxl = 2 * lane;
+        if (oxl < tws) {
+            const bool two = oxl + 1 < tws;
+            if (oA >= 0 && oA < chs) {
+                T* dst = (T*)(yPlane + (long long)(oy0 + oA) * p.ys[2] + (long long)(ox0 + oxl) * p.ys[3]);
+                st_as<T>(dst, a0);
+                if (two) st_as<T>((T*)((char*)dst + p.ys[3]), a1);
+            }
+            if (oB >= 0 && oB < chs) {
+                T* dst = (T*)(yPlane + (long long)(oy0 + oB) * p.ys[2] + (long long)(ox0 + oxl) * p.ys[3]);
+                st_as<T>(dst, b0);
+                if (two) st_as<T>((T*)((char*)dst + p.ys[3]), b1);
+            }
+        }
+#pragma unroll
+        for (int k = 5; k >= 2; k--) { acc[k][0] = acc[k - 2][0]; acc[k][1] = acc[k - 2][1]; }
+        acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = make_float2(0.f, 0.f);
+    };
+
+    // ---- schedule -----------------------------------------------------------------------------------
+    // Group g reads ring rows [2g, 2g+7] (UP=2) or [g, g+7] (UP=4); pairs are produced just in time.
+    int nextPair = 0;
+    auto producePair = [&]() {            // pre[] holds pair `nextPair`
+        storePair();
+        __syncwarp();
+        loadPair(nextPair + 1);           // prefetch the following pair while computing
+        stageB(nextPair);
+        __syncwarp();
+        nextPair++;
+    };
+    loadPair(0);
+    for (int g = 0; g < numGroups; g++) {
+        const int lastRow = (UP == 2 ? 2 * g : g) + 7;       // highest ring row group g reads
+        while (2 * nextPair <= lastRow) producePair();
+        switch (ey) {
+        case 0: stageC(g, std::integral_constant<int, 0>()); break;
+        case 1: stageC(g, std::integral_constant<int, 1>()); break;
+        case 2: if (UP == 4) stageC(g, std::integral_constant<int, (UP == 4 ? 2 : 0)>()); break;
+        default: if (UP == 4) stageC(g, std::integral_constant<int, (UP == 4 ? 3 : 0)>()); break;
+        }
+        __syncwarp();
+        flushSigns(g);
+        stageD(g);
+        __syncwarp();
+    }
+}
+
+}  // namespace flrelu_stream

@@ -173,7 +173,7 @@ SG3_EXPORT int sg3_modconv_weights(const float* w, const float* s, const float* 
     int gy = N < 8 ? N : 8;
     modconv_weights_kernel<<<dim3((unsigned)O, (unsigned)gy), 256, 0, st>>>(w, s, input_gain, gainMode, wmod, scratch,
                                                                             N, I, O, k * k, demodulate, round_tf32_flag);
-    return sg3_launch_status();
+    return sg3_launch_status(demodulate ? 2 : 1);
 }
 
 SG3_EXPORT int sg3_modconv_fwd(const void* x, const float* wmod, void* y,

@@ -150,3 +150,120 @@ def test_errors(ops):
         ops.filtered_lrelu.filtered_lrelu(torch.zeros(1, 2, 4, 4), None, None, None)     # CPU tensor: no fallback
     with pytest.raises(TypeError):
         ops.bias_act.bias_act(x, torch.zeros(2, device='cuda', dtype=torch.float16))
+
+
+# ---------------------------------------------------------------------------------------------
+# The fused warp-streaming kernel (flrelu_stream.cuh): multi-strip / multi-chunk shapes, every
+# sign mode, both dtypes -- against the oracle, and proof that the fused path (not the generic
+# composition) produced the result.
+
+def _design(up_taps, radial_down):
+    from oracle import sg3_oracle as orc
+    fu = orc.design_lowpass_filter(up_taps, 11.3, 26.0, 128 if up_taps == 12 else 256)
+    fd = orc.design_lowpass_filter(12, 16.0, 36.0, 128, radial=radial_down)
+    return fu, fd
+
+
+FUSED_CASES = [
+    # name, up, radial, N, C, in, padding
+    ('R_same_148', 2, True, 1, 3, 148, [11, 10, 11, 10]),       # 3 strips wide, row chunks
+    ('R_up4_84', 4, True, 1, 2, 84, [-2, -5, -2, -5]),
+    ('T_same_150', 2, False, 2, 2, 150, [9, 8, 9, 8]),
+    ('T_up4_86', 4, False, 1, 3, 86, [-6, -9, -6, -9]),
+    ('crit_70', 2, False, 1, 2, 70, [-9, -10, -9, -10]),
+    ('odd_pad_phase', 4, True, 1, 2, 37, [3, 2, 1, 4]),         # exercises ex, ey = 1..3
+    ('odd_pad_phase2', 2, False, 1, 2, 41, [6, 7, 9, 4]),
+    ('many_planes', 2, True, 4, 40, 36, [11, 10, 11, 10]),
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('case', FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_fused_stream_forward(ops, case, dtype):
+    from oracle import sg3_oracle as orc
+    name, up, radial, N, C, size, pad = case
+    fu, fd = _design(6 * up, radial)
+    rng = np.random.RandomState(hash(name) % 1000)
+    x = (rng.randn(N, C, size, size + 3) * 3).astype(np.float32)
+    b = rng.randn(C).astype(np.float32)
+    if dtype == torch.float16:
+        x, b = x.astype(np.float16).astype(np.float32), b.astype(np.float16).astype(np.float32)
+    kw = dict(up=up, down=2, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=6.0)
+    ref, ref_signs = orc.filtered_lrelu(x, fu, fd, b, return_signs=True, **kw)
+    fl = ops.filtered_lrelu
+    cfg = (up, 2) + tuple(pad) + (float(np.sqrt(2)), 0.2, 6.0, False)
+    xt, bt = cu(x, dtype=dtype), cu(b, dtype=dtype)
+    for write in (False, True):
+        res = fl._fused(xt, cu(fu), cu(fd), bt, None, 0, 0, cfg, write)
+        assert res is not None, 'fused kernel must support this configuration'
+        y, so = res
+        assert tuple(y.shape) == ref.shape
+        assert rel_err(y.float().cpu().numpy(), ref) < (TOL32 if dtype == torch.float32 else TOL16)
+        if write:
+            assert tuple(so.shape) == ref_signs.shape
+            sw_active = 2 * ref.shape[3] + 10
+            got = so.cpu().numpy()
+            # unpack 2-bit codes over the active width and compare; a code may differ only where the
+            # pre-activation sits within rounding of 0 or of the clamp
+            def unpack(s):
+                s = s.astype(np.uint8)
+                return np.stack([(s >> (2 * k)) & 3 for k in range(4)], axis=-1).reshape(*s.shape[:3], -1)[..., :sw_active]
+            diff = unpack(got) != unpack(ref_signs)
+            assert diff.mean() < (1e-4 if dtype == torch.float32 else 5e-3), diff.mean()
+
+
+@pytest.mark.parametrize('case', ['T_same_150', 'crit_70', 'odd_pad_phase2'])
+def test_fused_stream_backward_signs(ops, case):
+    """up2/down2 separable layers are self-adjoint in shape: backward runs the fused kernel in sign-READ mode."""
+    from oracle import sg3_oracle as orc
+    name, up, radial, N, C, size, pad = [c for c in FUSED_CASES if c[0] == case][0]
+    fu, fd = _design(12, False)
+    rng = np.random.RandomState(11)
+    x = (rng.randn(N, C, size, size) * 3).astype(np.float32)
+    b = rng.randn(C).astype(np.float32)
+    kw = dict(up=2, down=2, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=6.0)
+    y_ref, signs = orc.filtered_lrelu(x, fu, fd, b, return_signs=True, **kw)
+    dy = rng.randn(*y_ref.shape).astype(np.float32)
+    kwb = dict(kw)
+    kwb.pop('clamp')
+    dx_ref, db_ref = orc.filtered_lrelu_bwd(dy, signs, x.shape, fu, fd, **kwb)
+    xt, bt = cu(x, True), cu(b, True)
+    calls = []
+    orig = ops.filtered_lrelu._fused
+
+    def spy(*a, **k):
+        r = orig(*a, **k)
+        calls.append(r is not None)
+        return r
+    ops.filtered_lrelu._fused = spy
+    try:
+        y = ops.filtered_lrelu.filtered_lrelu(xt, cu(fu), cu(fd), bt, **kw)
+        dx, db = torch.autograd.grad(y, [xt, bt], cu(dy))
+    finally:
+        ops.filtered_lrelu._fused = orig
+    assert calls == [True, True], calls            # forward (sign write) and backward (sign read) both fused
+    assert rel_err(dx.cpu().numpy(), dx_ref) < 5e-5
+    assert rel_err(db.cpu().numpy(), db_ref) < 5e-5
+
+
+def test_fused_stream_full_size_properties(ops):
+    """Size-independent properties at a BASELINE-size layer (R-1024 L11: 102ch 1044^2): linearity of the
+    op in the unclamped positive regime and exact zero-response to zero input with zero bias."""
+    from oracle import sg3_oracle as orc
+    fu, fd = _design(12, True)
+    fl = ops.filtered_lrelu
+    x = torch.rand(1, 6, 1044, 1044, device='cuda') + 0.5          # strictly positive -> lrelu is identity
+    kw = dict(up=2, down=2, padding=[11, 10, 11, 10], gain=1.0, slope=0.2, clamp=None)
+    y1 = fl.filtered_lrelu(x, cu(fu), cu(fd), None, **kw)
+    y2 = fl.filtered_lrelu(2 * x, cu(fu), cu(fd), None, **kw)
+    assert tuple(y1.shape) == (1, 6, 1044, 1044)
+    inner = (slice(None), slice(None), slice(16, -16), slice(16, -16))   # borders see the zero padding ripple (may go negative)
+    assert float((y2[inner] - 2 * y1[inner]).abs().max()) < 1e-4 * float(y1.abs().max())
+    # DC gain of both low-pass filters is 1: the interior of a constant image stays constant
+    yc = fl.filtered_lrelu(torch.ones(1, 2, 1044, 1044, device='cuda'), cu(fu), cu(fd), None, **kw)
+    assert float((yc[inner] - 1).abs().max()) < 1e-4
+    z = fl.filtered_lrelu(torch.zeros(1, 2, 1044, 1044, device='cuda'), cu(fu), cu(fd), None, **kw)
+    assert float(z.abs().max()) == 0.0
+    # one plane against the oracle at full size
+    ref = orc.filtered_lrelu(x[:, :1].cpu().numpy(), fu, fd, None, **kw)
+    assert rel_err(y1[:, :1].cpu().numpy(), ref) < TOL32
