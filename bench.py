@@ -1,0 +1,334 @@
+"""bench.py -- StyleGAN3-R 1024^2 generator-forward throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+One process per GPU (the driver launches N>1 with torch.distributed.run); the batch is sharded
+across ranks with no data-path collective (weak scaling, fixed per-GPU batch).  A "step" is one
+`G.synthesis(ws)` forward of the per-GPU batch on synthetic latents with random-init weights.
+Rank 0 prints ONE JSON line.  Keys:
+  value          images/s, whole job, inputs resident in HBM (CUDA events, max over ranks)
+  e2e            images/s through the public API with HOST buffers: pinned ws -> H2D, forward, D2H of the images
+  roofline       filtered_lrelu (the dominant kernel): algorithmic bytes / CUDA-event time vs measured HBM peak,
+                 plus the FP32-pipe fraction that actually binds it
+  cpu_baseline   the CPU oracle (port of the reference's impl='ref' path) timed on this box's cores on a bounded sample
+`--impl reference` times the reference's own CPU algorithm (oracle port; the Python reference tree cannot
+travel to the GPU box) with all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+R1024 = dict(z_dim=512, c_dim=0, w_dim=512, img_resolution=1024, img_channels=3,
+             channel_base=65536, channel_max=1024, conv_kernel=1, use_radial_filters=True)
+METRIC = 'StyleGAN3-R 1024^2 G-forward images/sec'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=8, help='images per GPU per step')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--math', default='tf32', choices=['tf32', 'fp32'], help='modulated_conv2d contraction')
+    ap.add_argument('--cpu-seconds', type=float, default=20.0, help='time budget of the cpu_baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# Algorithmic work of the workload: per image, fp32.
+
+def layer_work(specs, esize=4):
+    """Per-layer algorithmic bytes of filtered_lrelu and FLOPs of the conv, per image."""
+    rows = []
+    for sp in specs:
+        k = sp['conv_kernel']
+        conv_hw = sp['in_size'] + k - 1
+        fl_bytes = esize * sp['out_channels'] * (conv_hw ** 2 + sp['out_size'] ** 2) + 4 * sp['out_channels']
+        conv_flops = 2 * sp['out_channels'] * sp['in_channels'] * k * k * conv_hw ** 2
+        # polyphase FMAs of the fused op: H-up on in rows, V-up on up rows, down filter per output
+        upw = conv_hw * sp['up'] + sp['padding'][0] + sp['padding'][1] - (sp['up_taps'] - 1)
+        fut = max(sp['up_taps'] // sp['up'], 1)
+        fd = sp['down_filter']
+        dn = 1 if fd is None else (fd.shape[0] * fd.shape[1] if fd.ndim == 2 else 2 * fd.shape[0])
+        fma = sp['out_channels'] * (conv_hw * upw * fut + upw * upw * fut + sp['out_size'] ** 2 * dn) if sp['up_taps'] > 1 else 0
+        rows.append(dict(name=sp['name'], flrelu_bytes=fl_bytes, conv_flops=conv_flops, flrelu_fma=fma))
+    return rows
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference's impl='ref' path, bounded sample.
+
+def cpu_sample(seconds, threads=None):
+    """Run the oracle's R-1024 synthesis forward for ONE image layer by layer until `seconds` are used up;
+    returns images/s extrapolated by the fraction of the per-image algorithmic FLOPs covered."""
+    import torch
+    from oracle import sg3_oracle as orc
+    import sg3_b200  # noqa: F401  (only for the random-init weights; no kernel is launched here)
+    from sg3_b200 import networks
+    if threads:
+        orc.set_num_threads(threads)
+    cores = orc.num_threads()
+    torch.manual_seed(0)
+    G = networks.Generator(**R1024).eval().requires_grad_(False)
+    z = torch.randn(1, 512, generator=torch.Generator().manual_seed(1))
+    # mapping network on CPU in plain torch (negligible work; bias_act has no CPU path by design)
+    x = z * (z.square().mean(1, keepdim=True) + 1e-8).rsqrt()
+    for i in range(2):
+        fc = getattr(G.mapping, f'fc{i}')
+        x = torch.nn.functional.leaky_relu(x @ (fc.weight * fc.weight_gain).t() + fc.bias * fc.bias_gain, 0.2) * np.sqrt(2)
+    ws = x.unsqueeze(1).repeat(1, G.num_ws, 1).numpy()
+    state = {k: v.numpy() for k, v in G.synthesis.state_dict().items()}
+    cfg = {k: v for k, v in R1024.items() if k not in ('z_dim', 'c_dim', 'w_dim', 'img_resolution', 'img_channels')}
+    net = orc.SynthesisOracle(state, img_resolution=1024, w_dim=512, **cfg)
+    work = layer_work(net.specs)
+    total = sum(r['conv_flops'] + 2 * r['flrelu_fma'] for r in work)
+    t0 = time.perf_counter()
+    xa = net.input_features(ws[:, 0])
+    done, nl = 0.0, 0
+    for i, sp in enumerate(net.specs):
+        xa = net.layer(sp, xa, ws[:, i + 1])
+        done += work[i]['conv_flops'] + 2 * work[i]['flrelu_fma']
+        nl = i + 1
+        if time.perf_counter() - t0 > seconds:
+            break
+    dt = time.perf_counter() - t0
+    frac = done / total
+    return dict(value=frac / dt, unit='images/s', cores=cores, kind='port',
+                sample=f'1 image, StyleGAN3-R 1024^2 synthesis layers L0..L{nl - 1} of 15 on the CPU oracle '
+                       f'({100 * frac:.1f}% of per-image FLOPs, {dt:.1f} s); images/s extrapolated by FLOP share')
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    per_step = max(args.cpu_seconds / max(args.steps + args.warmup, 1), 5.0)
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = cpu_sample(per_step)
+        if i >= args.warmup:
+            vals.append(info['value'])
+    v = float(np.mean(vals))
+    info['value'] = v
+    out = dict(metric=METRIC, value=v, unit='images/s', impl='reference', n_gpus=args.gpus, steps=args.steps,
+               warmup=args.warmup, ms_per_step=1e3 / v if v > 0 else None, higher_is_better=True, scaling='weak',
+               vs_baseline=None, dtype='f32', data='synthetic',
+               config=dict(workload='StyleGAN3-R 1024^2 synthesis forward, random-init, fp32 (force_fp32)',
+                           note='reference CPU algorithm (impl=ref composition) via the oracle port; bounded sample per step'),
+               cpu_baseline=info, e2e=dict(value=v, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-i', str(self.index), '-lms', '200'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                    if val.lower().startswith('active'):
+                        reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import sg3_b200
+    from sg3_b200 import capi, filtered_lrelu as fl_mod, modulated_conv, networks
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs CUDA (no CPU fallback for the product path)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    capi.lib()
+    modulated_conv.set_math(args.math)
+    fl_mod._quiet_fallback = True
+
+    torch.manual_seed(0)
+    G = networks.Generator(**R1024).eval().requires_grad_(False).to(dev)
+    B = args.batch
+    z = torch.randn(B, 512, generator=torch.Generator().manual_seed(1 + rank)).to(dev)
+    with torch.no_grad():
+        ws = G.mapping(z, None).contiguous()
+    ws_host = ws.cpu().pin_memory()
+    img_host = torch.empty([B, 3, 1024, 1024], dtype=torch.float32).pin_memory()
+
+    # per-call CUDA-event timing of filtered_lrelu (the dominant kernel) inside the timed region
+    fl_events = []
+    orig_fl = fl_mod.filtered_lrelu
+    record = {'on': False}
+
+    def timed_fl(x, *a, **k):
+        if not record['on']:
+            return orig_fl(x, *a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = orig_fl(x, *a, **k)
+        e1.record()
+        esz = x.element_size()
+        fl_events.append((e0, e1, esz * (x.numel() + y.numel()) + 4 * x.shape[1]))
+        return y
+    fl_mod.filtered_lrelu = timed_fl
+
+    def step_resident():
+        with torch.no_grad():
+            return G.synthesis(ws, noise_mode='const', force_fp32=True)
+
+    def step_e2e():
+        with torch.no_grad():
+            w = ws_host.to(dev, non_blocking=True)
+            img = G.synthesis(w, noise_mode='const', force_fp32=True)
+            img_host.copy_(img, non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+
+    # ---- timed: resident inputs ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = capi.lib().sg3_launch_count()
+    record['on'] = True
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    record['on'] = False
+    launches = capi.lib().sg3_launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    fl_ms = sum(a.elapsed_time(b) for a, b, _ in fl_events)
+    fl_bytes = sum(nb for _, _, nb in fl_events)
+    fl_mod.filtered_lrelu = orig_fl
+
+    # ---- timed: end to end with host buffers ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    from oracle import sg3_oracle as orc   # layer geometry only (host arithmetic), for the algorithmic-work table
+    _, specs = orc.layer_specs(1024, **{k: v for k, v in R1024.items() if k in ('channel_base', 'channel_max', 'conv_kernel', 'use_radial_filters')})
+    work = layer_work(specs)
+    fma_per_img = sum(r['flrelu_fma'] for r in work)
+    n_calls = len(fl_events)
+    achieved = fl_bytes / (fl_ms * 1e-3) / 1e9 if fl_ms > 0 else 0.0
+    fp32_peak_tfma = 148 * 128 * 1.965e9 / 1e12          # 37.2 TFMA/s at max SM clock
+    fma_rate = fma_per_img * B * args.steps / (fl_ms * 1e-3) / 1e12 if fl_ms > 0 else 0.0
+
+    value = world * B * args.steps / (ms_total * 1e-3)
+    out = dict(
+        metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
+        ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+        dtype='f32' if args.math == 'fp32' else 'f32 (tf32 tensor-core conv)', data='synthetic',
+        config=dict(workload='StyleGAN3-R 1024^2 synthesis forward (BASELINE.json configs[2]), random-init seed 0, '
+                             'force_fp32, noise_mode=const', per_gpu_batch=B, global_batch=world * B,
+                    parallelism=f'batch-sharded x{world}, no collective', conv_math=args.math,
+                    l2='activations of every layer exceed the 126 MB L2 (inputs larger than L2, no flush needed)'),
+        clocks=clocks,
+        e2e=dict(value=world * B * args.steps / (e2e_ms * 1e-3), unit='images/s',
+                 h2d_bytes_per_step=int(ws_host.numel() * 4), d2h_bytes_per_step=int(img_host.numel() * 4)),
+        gpu_launches=int(launches),
+        roofline=dict(bound='hbm', achieved=achieved, peak=hbm_peak, unit='GB/s', frac=achieved / hbm_peak,
+                      traffic=None, kernel='filtered_lrelu (15 calls per step, all timed with CUDA events)',
+                      launches_timed=n_calls, ms_per_step=fl_ms / args.steps,
+                      peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s (of fallback)',
+                      fp32_pipe=dict(achieved_tfma=fma_rate, peak_tfma=fp32_peak_tfma, frac=fma_rate / fp32_peak_tfma,
+                                     note='polyphase FMAs of the fused op; fp32 SIMT is the roof that binds it (DESIGN.md)')),
+    )
+    if not args.no_cpu_baseline:
+        out['cpu_baseline'] = cpu_sample(args.cpu_seconds)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

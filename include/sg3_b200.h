@@ -134,7 +134,8 @@ int sg3_upfirdn2d(const void* x, void* y, const float* f,
  * sg3_modconv_weights: fused weight prologue (:39-56) ->
  *   wmod[n][o][i][kh][kw] = w*rsqrt(mean w^2) * s*rsqrt(mean s^2) * rsqrt(sum(.)^2+1e-8) * input_gain
  * w [O][I][k][k] f32, s [N][I] f32, input_gain: NULL, or f32 with gainMode 1 = scalar,
- * 2 = [I], 3 = [N][I].  wmod is f32 [N][O][I*k*k]; if round_tf32 != 0 each value is
+ * 2 = [I], 3 = [N][I].  wmod is f32 [N][O][ldw] with row pitch ldw >= I*k*k floats (zero padded;
+ * the tensor-core path needs ldw % 4 == 0); if round_tf32 != 0 each value is
  * rounded to the nearest TF32 so the tensor-core contraction sees unbiased operands.
  * scratch: >= 4 bytes of device memory (batch-global style norm).
  *
@@ -144,10 +145,10 @@ int sg3_upfirdn2d(const void* x, void* y, const float* f,
  * ---------------------------------------------------------------------- */
 int sg3_modconv_weights(const float* w, const float* s, const float* input_gain, int gainMode,
                         float* wmod, float* scratch,
-                        int N, int I, int O, int k, int demodulate, int round_tf32, void* stream);
+                        int N, int I, int O, int k, int ldw, int demodulate, int round_tf32, void* stream);
 
 int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
-                    int N, int I, int O, int H, int W, int k, int pad,
+                    int N, int I, int O, int H, int W, int k, int pad, int ldw,
                     int mathMode, int dtype, void* stream);
 
 #ifdef __cplusplus

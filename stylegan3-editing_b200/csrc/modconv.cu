@@ -8,7 +8,7 @@
 // fp32 parity; the TF32 tcgen05/TMEM implicit GEMM (mathMode 1) lives in modconv_tc.cu.
 #include "common.cuh"
 
-int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad,
+int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
                        cudaStream_t stream);
 
 namespace {
@@ -47,7 +47,7 @@ __device__ __forceinline__ float round_tf32(float v)
 __global__ void __launch_bounds__(256) modconv_weights_kernel(
     const float* __restrict__ w, const float* __restrict__ s, const float* __restrict__ gain, int gainMode,
     float* __restrict__ wmod, const float* __restrict__ scratch,
-    int N, int I, int O, int kk, int demodulate, int roundTf32)
+    int N, int I, int O, int kk, int ldw, int demodulate, int roundTf32)
 {
     __shared__ float red[32];
     const int o = blockIdx.x;
@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
             acc = block_sum(acc, red);
             d = rsqrtf(acc + 1e-8f);
         }
-        float* dst = wmod + ((size_t)n * O + o) * cnt;
+        float* dst = wmod + ((size_t)n * O + o) * ldw;
+        for (int q = cnt + threadIdx.x; q < ldw; q += blockDim.x) dst[q] = 0.f;      // row padding (TMA pitch)
         for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
             const int i = q / kk;
             float v = (wo[q] * rw) * (sn[i] * rs);
@@ -91,7 +92,7 @@ constexpr int BO = 64, BP = 64, BK = 16;
 
 __global__ void __launch_bounds__(256) modconv_fwd_simt_kernel(
     const float* __restrict__ x, const float* __restrict__ wmod, float* __restrict__ y,
-    int N, int I, int O, int H, int W, int k, int pad, int OH, int OW)
+    int N, int I, int O, int H, int W, int k, int pad, int OH, int OW, int ldw)
 {
     __shared__ float sA[BK][BO + 4];   // weights  [kchunk][o]
     __shared__ float sB[BK][BP + 4];   // pixels   [kchunk][p]
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(256) modconv_fwd_simt_kernel(
         const int rem = (int)(t - (int64_t)n * tilesO * tilesP);
         const int to = rem / tilesP, tp = rem - to * tilesP;
         const int o0 = to * BO, p0 = tp * BP;
-        const float* wn = wmod + (size_t)n * O * K;
+        const float* wn = wmod + (size_t)n * O * ldw;
         const float* xn = x + (size_t)n * I * H * W;
         float acc[4][4];
 #pragma unroll
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) modconv_fwd_simt_kernel(
             for (int e = threadIdx.x; e < BK * BO; e += 256) {
                 const int o = e / BK, kc = e - o * BK;
                 float v = 0.f;
-                if (o0 + o < O && k0 + kc < K) v = wn[(size_t)(o0 + o) * K + k0 + kc];
+                if (o0 + o < O && k0 + kc < K) v = wn[(size_t)(o0 + o) * ldw + k0 + kc];
                 sA[kc][o] = v;
             }
             for (int e = threadIdx.x; e < BK * BP; e += 256) {
@@ -163,35 +164,35 @@ __global__ void __launch_bounds__(256) modconv_fwd_simt_kernel(
 
 SG3_EXPORT int sg3_modconv_weights(const float* w, const float* s, const float* input_gain, int gainMode,
                                    float* wmod, float* scratch,
-                                   int N, int I, int O, int k, int demodulate, int round_tf32_flag, void* stream)
+                                   int N, int I, int O, int k, int ldw, int demodulate, int round_tf32_flag, void* stream)
 {
-    if (!w || !s || !wmod || !scratch || N < 1 || I < 1 || O < 1 || k < 1) return SG3_E_INVALID;
+    if (!w || !s || !wmod || !scratch || N < 1 || I < 1 || O < 1 || k < 1 || ldw < I * k * k) return SG3_E_INVALID;
     if (gainMode < 0 || gainMode > 3 || (gainMode && !input_gain)) return SG3_E_INVALID;
     if ((int64_t)N * I > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
     cudaStream_t st = (cudaStream_t)stream;
     if (demodulate) style_norm_kernel<<<1, 1024, 0, st>>>(s, N * I, scratch);
     int gy = N < 8 ? N : 8;
     modconv_weights_kernel<<<dim3((unsigned)O, (unsigned)gy), 256, 0, st>>>(w, s, input_gain, gainMode, wmod, scratch,
-                                                                            N, I, O, k * k, demodulate, round_tf32_flag);
+                                                                            N, I, O, k * k, ldw, demodulate, round_tf32_flag);
     return sg3_launch_status(demodulate ? 2 : 1);
 }
 
 SG3_EXPORT int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
-                               int N, int I, int O, int H, int W, int k, int pad,
+                               int N, int I, int O, int H, int W, int k, int pad, int ldw,
                                int mathMode, int dtype, void* stream)
 {
-    if (!x || !wmod || !y || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || k < 1 || pad < 0) return SG3_E_INVALID;
+    if (!x || !wmod || !y || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || k < 1 || pad < 0 || ldw < I * k * k) return SG3_E_INVALID;
     if (dtype != SG3_F32) return SG3_E_NOKERNEL;
     const int OH = H + 2 * pad - k + 1, OW = W + 2 * pad - k + 1;
     if (OH < 1 || OW < 1) return SG3_E_INVALID;
     if ((int64_t)OH * OW > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
     cudaStream_t st = (cudaStream_t)stream;
-    if (mathMode == 1) return sg3_modconv_fwd_tc((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, st);
+    if (mathMode == 1) return sg3_modconv_fwd_tc((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, ldw, st);
     if (mathMode != 0) return SG3_E_INVALID;
     const int P = OH * OW;
     int64_t total = (int64_t)N * ((O + BO - 1) / BO) * ((P + BP - 1) / BP);
     int64_t cap = (int64_t)sg3_sm_count() * 32;
     unsigned grid = (unsigned)(total < cap ? total : cap);
-    modconv_fwd_simt_kernel<<<grid, 256, 0, st>>>((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, OH, OW);
+    modconv_fwd_simt_kernel<<<grid, 256, 0, st>>>((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, OH, OW, ldw);
     return sg3_launch_status();
 }

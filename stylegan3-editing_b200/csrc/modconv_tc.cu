@@ -1,8 +1,296 @@
-// modconv_tc.cu -- TF32 tcgen05/TMEM implicit-GEMM contraction for modulated_conv2d (placeholder
-// until the tensor-core kernel lands: reports "no kernel" so callers use mathMode 0).
+// modconv_tc.cu -- TF32 tcgen05/TMEM GEMM for the contraction of modulated_conv2d (1x1 kernels,
+// StyleGAN3 config R; the grouped cuDNN convolution of networks_stylegan3.py:59-62).
+//
+// Per sample n:  Y[o][p] = sum_i Wn[o][i] * X[i][p]     X: [I][P] (pixels contiguous), Wn: [O][ldw]
+// mapped onto UMMA as  D[M = 128 pixels][N = BN out-channels] += A[M][K] * B[K][N]  with
+//   A = X^T  : MN-major (pixels contiguous), four TMA boxes [32 k-rows][32 px] per stage,
+//              SWIZZLE_128B_ATOM_32B (the layout tcgen05 requires for 32-bit MN-major operands)
+//   B = Wn   : K-major  (i contiguous),      one TMA box  [BN rows][32 k],      SWIZZLE_128B
+//   D in TMEM: lane = pixel, column = out-channel, fp32
+// so the epilogue (tcgen05.ld 32x32b: one thread = one pixel, 32 channels per load) stores, for a fixed
+// channel, 32 consecutive pixels per warp instruction = one full 128-byte line; no smem staging.
+// K is consumed 32 input channels per pipeline stage (4 x tcgen05.mma K=8); out-of-range rows/columns of
+// both operands are zero-filled by TMA, so I, O and P need no padding in the activations (the weight
+// rows are padded to `ldw` floats by the prologue so that their pitch is 16-byte aligned).
+//
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32w..32w+31), warp 4 TMA producer,
+// warp 5 TMEM allocator + MMA issuer.  One output tile per CTA; 2 CTAs per SM overlap one tile's
+// epilogue with the other's loads.  Every mbarrier wait is bounded (trap instead of hang).
+#include <cuda.h>
+#include <mutex>
+
 #include "common.cuh"
 
-int sg3_modconv_fwd_tc(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t)
+namespace {
+
+constexpr int BM = 128;            // pixels per tile (UMMA M)
+constexpr int BK = 32;             // input channels per stage (one 128-byte swizzle row of the K-major operand)
+constexpr int kStages = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 4;      // 16 KB: 4 boxes of [32 rows][128 B]
+constexpr int kThreads = 192;
+
+struct TcParams {
+    float* y;
+    int N, I, O, P;
+    int BN;                // out-channels per tile (multiple of 16, <= 256)
+    int tmemCols;          // power of two >= max(BN, 32)
+    int tilesM, tilesN;
+    int kTiles;
+    int stages;            // pipeline depth (3 when two CTAs share an SM, else 4)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    return SG3_E_NOKERNEL;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
+        if (spins > (1u << 24)) __trap();
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64): SWIZZLE_128B = 2 (K-major operand),
+// SWIZZLE_128B_BASE32B = 1 (32-bit MN-major operand: 32-byte swizzle granules, 4-row atoms).
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lboBytes, uint32_t sboBytes, uint32_t layout = kLayoutSw128)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lboBytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sboBytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout << 61;
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmemD), "l"(descA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const TcParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t barFull[kStages], barEmpty[kStages], barAccum;
+    __shared__ uint32_t tmemBase;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bStageBytes = p.BN * BK * 4;
+    const int stageBytes = A_STAGE_BYTES + bStageBytes;
+    // SWIZZLE_128B operands need 1024-byte aligned tiles
+    const uint32_t tiles = (smem_u32(smem) + 1023u) & ~1023u;
+
+    // tile coordinates: n-tile fastest so that CTAs sharing a pixel block run together (L2 reuse of X)
+    const long long t = blockIdx.x;
+    const int tn = (int)(t % p.tilesN);
+    const long long rest = t / p.tilesN;
+    const int tm = (int)(rest % p.tilesM);
+    const int n = (int)(rest / p.tilesM);
+    const int p0 = tm * BM, o0 = tn * p.BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(smem_u32(&barFull[s]), 1); mbar_init(smem_u32(&barEmpty[s]), 1); }
+        mbar_init(smem_u32(&barAccum), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmemBase)), "r"((uint32_t)p.tmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmemBase;
+
+    if (warp == 4) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            for (int kt = 0; kt < p.kTiles; kt++) {
+                const int s = kt % p.stages;
+                const uint32_t round = kt / p.stages;
+                if (kt >= p.stages) mbar_wait(smem_u32(&barEmpty[s]), (round - 1) & 1);
+                const uint32_t full = smem_u32(&barFull[s]);
+                mbar_expect_tx(full, (uint32_t)stageBytes);
+                const uint32_t aDst = tiles + s * stageBytes;
+#pragma unroll
+                for (int j = 0; j < 4; j++) tma_load_3d(aDst + j * (BK * 128), &mapX, full, p0 + 32 * j, kt * BK, n);
+                tma_load_3d(aDst + A_STAGE_BYTES, &mapW, full, kt * BK, o0, n);
+            }
+        }
+    } else if (warp == 5) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, A MN-major, B K-major, N, M=128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
+                                   ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kt = 0; kt < p.kTiles; kt++) {
+                const int s = kt % p.stages;
+                mbar_wait(smem_u32(&barFull[s]), (kt / p.stages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t aBase = tiles + s * stageBytes, bBase = aBase + A_STAGE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ks++) {
+                    // A (fp32, MN-major): 8 k-rows of 128 B per step = two 4-row swizzle atoms 512 B apart (SBO);
+                    // 32-pixel blocks BK*128 B apart (LBO)
+                    const uint64_t da = umma_desc(aBase + ks * 1024, BK * 128, 512, kLayoutSw128Base32);
+                    // B: step 8 tf32 = 32 B inside the 128-byte row; 8-row groups 1024 B apart
+                    const uint64_t db = umma_desc(bBase + ks * 32, 16, 1024);
+                    umma_tf32(tmem, da, db, idesc, (kt > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&barEmpty[s]));            // frees the stage when these MMAs retire
+            }
+            umma_commit(smem_u32(&barAccum));                   // accumulator complete
+        }
+    } else {
+        // ---------------- epilogue: TMEM -> registers -> global ----------------
+        mbar_wait(smem_u32(&barAccum), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int pix = p0 + 32 * warp + lane;
+        float* yn = p.y + ((size_t)n * p.O) * (size_t)p.P;
+        for (int c = 0; c < p.BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c, r);
+            if (pix < p.P) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int o = o0 + c + j;
+                    if (c + j < p.BN && o < p.O) yn[(size_t)o * p.P + pix] = __uint_as_float(r[j]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmemCols) : "memory");
+    }
+}
+
+// ---- host: tensor maps through the driver entry point (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    });
+    return fn;
+}
+
+bool make_map3(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1Bytes, uint64_t s2Bytes,
+               uint32_t b0, uint32_t b1, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {s1Bytes, s2Bytes};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+// x [N][I][P], wmod [N][O][ldw] (ldw % 4 == 0, zero beyond I), y [N][O][P]; k must be 1.
+int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
+                       cudaStream_t stream)
+{
+    if (k != 1 || pad != 0) return SG3_E_NOKERNEL;
+    const long long P = (long long)H * W;
+    if (P % 4 != 0 || ldw % 4 != 0 || ldw < I) return SG3_E_NOKERNEL;        // TMA needs 16-byte global strides
+    if (((uintptr_t)x & 15) || ((uintptr_t)wmod & 15)) return SG3_E_NOKERNEL;
+    if (P > INT32_MAX) return SG3_E_TOOLARGE;
+
+    TcParams p;
+    p.y = y; p.N = N; p.I = I; p.O = O; p.P = (int)P;
+    // out-channel tile: split O evenly into the fewest tiles of <= 256, rounded up to the UMMA N granule (16)
+    const int nt = (O + 255) / 256;
+    int bn = ((O + nt - 1) / nt + 15) & ~15;
+    if (bn < 16) bn = 16;
+    p.BN = bn;
+    p.tilesN = (O + bn - 1) / bn;
+    p.tilesM = (int)((P + BM - 1) / BM);
+    p.kTiles = (I + BK - 1) / BK;
+    int cols = 32;
+    while (cols < bn) cols <<= 1;
+    p.tmemCols = cols;
+    const long long ctas = (long long)N * p.tilesM * p.tilesN;
+    if (ctas > 0x7fffffffLL) return SG3_E_TOOLARGE;
+
+    alignas(64) CUtensorMap mapX, mapW;
+    if (!make_map3(&mapX, x, (uint64_t)P, (uint64_t)I, (uint64_t)N, (uint64_t)P * 4, (uint64_t)P * I * 4, 32, BK,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return SG3_E_NOKERNEL;
+    if (!make_map3(&mapW, wmod, (uint64_t)ldw, (uint64_t)O, (uint64_t)N, (uint64_t)ldw * 4, (uint64_t)ldw * O * 4, BK, (uint32_t)bn)) return SG3_E_NOKERNEL;
+
+    p.stages = bn > 128 ? 4 : 3;                            // <= 113 KB per CTA keeps two CTAs per SM for narrow tiles
+    const int smemBytes = p.stages * (A_STAGE_BYTES + bn * BK * 4) + 1024;
+    static std::once_flag once;
+    static cudaError_t attrErr = cudaSuccess;
+    std::call_once(once, [] { attrErr = cudaFuncSetAttribute(modconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    if (attrErr != cudaSuccess) return (int)attrErr;
+    modconv_tc_kernel<<<(unsigned)ctas, kThreads, smemBytes, stream>>>(mapX, mapW, p);
+    return sg3_launch_status();
 }

@@ -29,7 +29,7 @@ def _math_mode():
 
 
 def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False):
-    """[N, O, I*k*k] float32 modulated (+demodulated, +input-gain) weights  (:39-56)."""
+    """[N, O, ldw >= I*k*k] float32 modulated (+demodulated, +input-gain) weights, rows zero padded  (:39-56)."""
     capi.require_cuda(w, 'modulated_conv2d')
     O, I, kh, kw = w.shape
     assert kh == kw
@@ -45,11 +45,12 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False):
             mode, g = 2, g.contiguous()                            # per input channel
         else:
             mode, g = 3, g.expand(N, I).contiguous()               # per (sample, input channel), broadcast like :55
-    wmod = torch.empty([N, O, I * kh * kw], dtype=torch.float32, device=w.device)
+    ldw = (I * kh * kw + 31) // 32 * 32            # row pitch: 128-byte multiple for the TMA-fed tensor-core path
+    wmod = torch.empty([N, O, ldw], dtype=torch.float32, device=w.device)
     scratch = torch.empty([1], dtype=torch.float32, device=w.device)
     with torch.cuda.device(w.device):
         rc = capi.lib().sg3_modconv_weights(w.data_ptr(), s.data_ptr(), g.data_ptr() if g is not None else None, mode,
-                                            wmod.data_ptr(), scratch.data_ptr(), N, I, O, kh, int(bool(demodulate)),
+                                            wmod.data_ptr(), scratch.data_ptr(), N, I, O, kh, ldw, int(bool(demodulate)),
                                             int(bool(round_tf32)), capi.stream_ptr(w.device))
     capi.check(rc, 'sg3_modconv_weights')
     return wmod
@@ -61,10 +62,11 @@ def conv_forward(x, wmod, O, k, padding, math):
     OH, OW = H + 2 * padding - k + 1, W + 2 * padding - k + 1
     y = torch.empty([N, O, OH, OW], dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        rc = capi.lib().sg3_modconv_fwd(x.data_ptr(), wmod.data_ptr(), y.data_ptr(), N, I, O, H, W, k, padding,
+        ldw = wmod.shape[2]
+        rc = capi.lib().sg3_modconv_fwd(x.data_ptr(), wmod.data_ptr(), y.data_ptr(), N, I, O, H, W, k, padding, ldw,
                                         1 if math == 'tf32' else 0, capi.SG3_F32, capi.stream_ptr(x.device))
-        if rc == capi.SG3_E_NOKERNEL and math == 'tf32':
-            rc = capi.lib().sg3_modconv_fwd(x.data_ptr(), wmod.data_ptr(), y.data_ptr(), N, I, O, H, W, k, padding,
+        if rc == capi.SG3_E_NOKERNEL and math == 'tf32':       # shapes the tensor-core kernel does not cover yet (3x3)
+            rc = capi.lib().sg3_modconv_fwd(x.data_ptr(), wmod.data_ptr(), y.data_ptr(), N, I, O, H, W, k, padding, ldw,
                                             0, capi.SG3_F32, capi.stream_ptr(x.device))
     capi.check(rc, 'sg3_modconv_fwd')
     return y
