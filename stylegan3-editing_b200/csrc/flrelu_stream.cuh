@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             if (rd >= ownH || sY < 0 || sY >= p.sH) continue;
             uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
             for (int q = lane; q < nb; q += 32) {
-                const unsigned wv = *(const unsigned*)(sS + j * G::SS_ROW + 4 * q);
+                // & 0x03030303: staging bytes of columns this strip never computes are uninitialised
+                const unsigned wv = *(const unsigned*)(sS + j * G::SS_ROW + 4 * q) & 0x03030303u;
                 const unsigned packed = (wv | (wv >> 6) | (wv >> 12) | (wv >> 18)) & 0xffu;
                 const int bq = byte0 + q;
                 if (bq >= 0 && bq < p.sWb) srow[bq] = (uint8_t)packed;

@@ -174,6 +174,8 @@ FUSED_CASES = [
     ('odd_pad_phase', 4, True, 1, 2, 37, [3, 2, 1, 4]),         # exercises ex, ey = 1..3
     ('odd_pad_phase2', 2, False, 1, 2, 41, [6, 7, 9, 4]),
     ('many_planes', 2, True, 4, 40, 36, [11, 10, 11, 10]),
+    ('full_last_strip', 2, False, 1, 2, 84, [-9, -10, -9, -10]),   # out 64: the last strip is exactly 64 wide
+    ('two_full_strips', 2, True, 1, 2, 128, [11, 10, 11, 10]),      # out 128
 ]
 
 
@@ -209,7 +211,7 @@ def test_fused_stream_forward(ops, case, dtype):
                 s = s.astype(np.uint8)
                 return np.stack([(s >> (2 * k)) & 3 for k in range(4)], axis=-1).reshape(*s.shape[:3], -1)[..., :sw_active]
             diff = unpack(got) != unpack(ref_signs)
-            assert diff.mean() < (1e-4 if dtype == torch.float32 else 5e-3), diff.mean()
+            assert diff.sum() <= (2 if dtype == torch.float32 else 5e-3 * diff.size), (int(diff.sum()), np.argwhere(diff)[:8])
 
 
 @pytest.mark.parametrize('case', ['T_same_150', 'crit_70', 'odd_pad_phase2'])

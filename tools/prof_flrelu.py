@@ -1,0 +1,22 @@
+"""One filtered_lrelu launch at a BASELINE-size layer, for ncu: python tools/prof_flrelu.py [L11|L10|L12] [N]"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import sg3_b200
+from oracle import sg3_oracle as orc
+which = sys.argv[1] if len(sys.argv) > 1 else 'L11'
+N = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+_, specs = orc.layer_specs(1024, channel_base=65536, channel_max=1024, conv_kernel=1, use_radial_filters=True)
+sp = specs[int(which[1:])]
+C, size = sp['out_channels'], sp['in_size']
+x = torch.randn(N, C, size, size, device='cuda') * 2
+b = torch.randn(C, device='cuda')
+fu = torch.from_numpy(sp['up_filter']).cuda(); fd = torch.from_numpy(sp['down_filter']).cuda()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+for it in range(4):
+    if it == 3: ev[0].record()
+    y = sg3_b200.filtered_lrelu.filtered_lrelu(x, fu, fd, b, up=sp['up'], down=sp['down'], padding=sp['padding'], clamp=256)
+ev[1].record(); torch.cuda.synchronize()
+ms = ev[0].elapsed_time(ev[1])
+byts = 4 * (x.numel() + y.numel())
+print(f'{sp["name"]} up{sp["up"]} N={N} C={C} {size}->{y.shape[-1]}: {ms:.3f} ms, {byts / ms / 1e6:.1f} GB/s, {y.numel() / ms / 1e6:.1f} Gpix/s out')
