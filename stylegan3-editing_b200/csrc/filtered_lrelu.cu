@@ -42,10 +42,10 @@ SG3_EXPORT int sg3_filtered_lrelu_supported(int up, int down, int fuW, int fuH, 
 
 namespace {
 
-template <class T, int UP, bool FULL, int MODE>
+template <class T, int UP, int FD, int MODE>
 int launch_stream(const fs::Params& p, cudaStream_t stream)
 {
-    auto kern = fs::kernel<T, UP, FULL, MODE>;
+    auto kern = fs::kernel<T, UP, FD, MODE>;
     const int smem = fs::kWarpsPerCta * fs::Geo<UP>::WARP_BYTES;
     static std::once_flag once;
     static cudaError_t attrErr = cudaSuccess;
@@ -57,22 +57,28 @@ int launch_stream(const fs::Params& p, cudaStream_t stream)
     return sg3_launch_status();
 }
 
-template <class T, int UP, bool FULL>
+template <class T, int UP, int FD>
 int dispatch_mode(const fs::Params& p, int mode, cudaStream_t stream)
 {
     switch (mode) {
-    case SG3_SIGNS_NONE:  return launch_stream<T, UP, FULL, SG3_SIGNS_NONE>(p, stream);
-    case SG3_SIGNS_WRITE: return launch_stream<T, UP, FULL, SG3_SIGNS_WRITE>(p, stream);
-    case SG3_SIGNS_READ:  return launch_stream<T, UP, FULL, SG3_SIGNS_READ>(p, stream);
+    case SG3_SIGNS_NONE:  return launch_stream<T, UP, FD, SG3_SIGNS_NONE>(p, stream);
+    case SG3_SIGNS_WRITE: return launch_stream<T, UP, FD, SG3_SIGNS_WRITE>(p, stream);
+    case SG3_SIGNS_READ:  return launch_stream<T, UP, FD, SG3_SIGNS_READ>(p, stream);
     }
     return SG3_E_INVALID;
 }
 
 template <class T>
-int dispatch_shape(const fs::Params& p, int up, bool full, int mode, cudaStream_t stream)
+int dispatch_shape(const fs::Params& p, int up, int fdMode, int mode, cudaStream_t stream)
 {
-    if (up == 2) return full ? dispatch_mode<T, 2, true>(p, mode, stream) : dispatch_mode<T, 2, false>(p, mode, stream);
-    return full ? dispatch_mode<T, 4, true>(p, mode, stream) : dispatch_mode<T, 4, false>(p, mode, stream);
+    if (up == 2) {
+        if (fdMode == 0) return dispatch_mode<T, 2, 0>(p, mode, stream);
+        if (fdMode == 1) return dispatch_mode<T, 2, 1>(p, mode, stream);
+        return dispatch_mode<T, 2, 2>(p, mode, stream);
+    }
+    if (fdMode == 0) return dispatch_mode<T, 4, 0>(p, mode, stream);
+    if (fdMode == 1) return dispatch_mode<T, 4, 1>(p, mode, stream);
+    return dispatch_mode<T, 4, 2>(p, mode, stream);
 }
 
 }  // namespace
@@ -108,7 +114,10 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
                 if (b < fuW) v = (float)up * (d->fu ? d->fu[d->flip ? b : fuW - 1 - b] : 1.0f);
             }
             p.tu[ph][k] = v;
+            p.tv[ph][k] = v * d->gain;
         }
+    p.lreluA = 0.5f * (1.0f + d->slope);
+    p.lreluB = 0.5f * (1.0f - d->slope);
     const bool full = fdH != 0 && d->fd != nullptr;
     for (int b = 0; b < fs::kDownTaps; b++)
         p.fdx[b] = (!full && b < fdW) ? (d->fd ? d->fd[d->flip ? b : fdW - 1 - b] : 1.0f) : 0.f;
@@ -133,7 +142,19 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
     p.chunksY = (d->outH + p.chunkRows - 1) / p.chunkRows;
     p.totalStrips = base * p.chunksY;
 
+    // Dense filters that are mirror-symmetric along x (the radial jinc filters are) take the variant that
+    // pre-adds mirrored pixels.  Exact tap equality is required; anything else runs the general dense path.
+    int fdMode = full ? 1 : 0;
+    if (full && fdW == fs::kDownTaps) {
+        bool sym = true;
+        for (int a = 0; a < fs::kDownTaps && sym; a++)
+            for (int b = 0; b < fs::kDownTaps / 2; b++)
+                if (p.fd2[a][b] != p.fd2[a][fs::kDownTaps - 1 - b]) { sym = false; break; }
+        if (sym) fdMode = 2;
+    }
+    if ((long long)d->inW * (d->xStride[3] < 0 ? -d->xStride[3] : d->xStride[3]) > 0x7fffffffLL) return SG3_E_NOKERNEL;
+
     cudaStream_t st = (cudaStream_t)stream;
-    if (d->dtype == SG3_F32) return dispatch_shape<float>(p, up, full, d->signMode, st);
-    return dispatch_shape<__half>(p, up, full, d->signMode, st);
+    if (d->dtype == SG3_F32) return dispatch_shape<float>(p, up, fdMode, d->signMode, st);
+    return dispatch_shape<__half>(p, up, fdMode, d->signMode, st);
 }

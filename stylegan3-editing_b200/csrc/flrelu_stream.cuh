@@ -68,7 +68,9 @@ struct Params {
     int sH, sWb, sx, sy;
     int stripsX, chunksY, chunkRows;
     long long totalStrips;
-    float tu[4][kTapsPerPhase];        // tu[p][k]: up taps of phase p, pre-scaled by UP (both axes use them)
+    float tu[4][kTapsPerPhase];        // tu[p][k]: up taps of phase p, pre-scaled by UP (horizontal pass)
+    float tv[4][kTapsPerPhase];        // vertical pass: tu * gain (the activation gain rides on the taps)
+    float lreluA, lreluB;              // lrelu(v) = v*lreluA + |v|*lreluB = v*(1+slope)/2 + |v|*(1-slope)/2
     float fdx[kDownTaps];              // separable down taps (correlation order); unused when dense
     float fd2[kDownTaps][kDownTaps];   // dense down taps fd2[a][b] (correlation order); unused when separable
 };
@@ -77,27 +79,30 @@ __device__ __forceinline__ float2 ffma2(float2 a, float t, float2 c) { return __
 
 __device__ __forceinline__ int swz(int xh) { return xh ^ ((xh >> 3) & 1); }
 
-// gain / leaky ReLU / clamp of one value; returns the 2-bit sign code.
+// leaky ReLU + clamp of one value that already carries the gain; returns the 2-bit sign code in WRITE mode.
+//   NONE : v*a + |v|*b (one FMUL + one FFMA with |.| source modifier), then clamp by two FMNMX
+//   WRITE: same value, plus code = clamped ? 2 : negative ? 1 : 0
+//   READ : backward pass: scale by {1, slope, 0} according to the stored code, no clamp
 template <int MODE>
-__device__ __forceinline__ float act1(float u, float gain, float slope, float clamp, unsigned rd_code, unsigned& wr_code)
+__device__ __forceinline__ float act1(float v, float slope, float la, float lb, float clamp, unsigned rd_code, unsigned& wr_code)
 {
-    float v = u * gain;
     if (MODE == SG3_SIGNS_READ) {
         if (rd_code & 1u) v *= slope;
         if (rd_code & 2u) v = 0.f;
         return v;
     }
-    const bool neg = v < 0.f;
-    v = neg ? v * slope : v;
-    const bool cl = fabsf(v) > clamp;
-    v = cl ? copysignf(clamp, v) : v;
-    if (MODE == SG3_SIGNS_WRITE) wr_code = cl ? 2u : (neg ? 1u : 0u);
-    return v;
+    const float r = fmaf(fabsf(v), lb, v * la);
+    const float c = fminf(fmaxf(r, -clamp), clamp);
+    if (MODE == SG3_SIGNS_WRITE) wr_code = (fabsf(r) > clamp) ? 2u : ((v < 0.f) ? 1u : 0u);
+    return c;
 }
 
-template <class T, int UP, bool FD_FULL, int MODE>
+// FD: 0 = separable down filter, 1 = dense 12x12, 2 = dense 12x12 with fd2[a][b] == fd2[a][11-b]
+// (the radial filters): column pairs are pre-added, 6 taps per filter row instead of 12.
+template <class T, int UP, int FD, int MODE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_constant__ Params p)
 {
+    constexpr bool FD_FULL = FD != 0;
     typedef Geo<UP> G;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,18 +136,40 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     const float bias = p.b ? (float)ld_as<T>((const T*)((const char*)p.b + c * p.bs)) : 0.f;
 
     // ---- stage A: global -> registers (pair t = input rows 2t, 2t+1 of the strip) -----------------
-    float pre[G::A_ITEMS];
+    // The raw bits stay in registers until the next iteration (nothing consumes them earlier, so the
+    // global-load latency is covered by a whole B/C/D round); bias and the zero border are applied when
+    // they are stored to shared memory.  Column offsets and validity are per-lane constants of the strip.
+    unsigned pre[G::A_ITEMS];
+    unsigned preValid = 0;                     // bit r: pre[r] holds a real pixel
+    int colOff[G::A_ITEMS];                    // byte offset of the lane's column, or -1 when outside the image
+    unsigned rowSel = 0;                       // bit r: item r belongs to the second row of the pair
+#pragma unroll
+    for (int r = 0; r < G::A_ITEMS; r++) {
+        const int e = lane + 32 * r;
+        const int row = e >= G::TIW ? 1 : 0;
+        const int jl = e - row * G::TIW;
+        const int j = jBase + jl;
+        rowSel |= (unsigned)row << r;
+        colOff[r] = (e < 2 * G::TIW && j >= 0 && j < p.inW) ? (int)(j * p.xs[3]) : -1;
+    }
     auto loadPair = [&](int t) {
+        const int i0 = iBase + 2 * t, i1 = i0 + 1;
+        const bool ok0 = i0 >= 0 && i0 < p.inH, ok1 = i1 >= 0 && i1 < p.inH;
+        const char* r0 = xPlane + (long long)i0 * p.xs[2];
+        const char* r1 = xPlane + (long long)i1 * p.xs[2];
+        preValid = 0;
 #pragma unroll
         for (int r = 0; r < G::A_ITEMS; r++) {
-            const int e = lane + 32 * r;
-            const int row = e >= G::TIW ? 1 : 0;
-            const int jl = e - row * G::TIW;
-            const int i = iBase + 2 * t + row, j = jBase + jl;
-            float v = 0.f;
-            if (e < 2 * G::TIW && i >= 0 && i < p.inH && j >= 0 && j < p.inW)
-                v = (float)ld_as<T>((const T*)(xPlane + i * p.xs[2] + j * p.xs[3])) + bias;
-            pre[r] = v;
+            const bool second = (rowSel >> r) & 1u;
+            const bool ok = colOff[r] >= 0 && (second ? ok1 : ok0);
+            unsigned bits = 0;
+            if (ok) {
+                const char* src = (second ? r1 : r0) + colOff[r];
+                if (sizeof(T) == 4) bits = __ldg((const unsigned*)src);
+                else bits = (unsigned)__ldg((const unsigned short*)src);
+            }
+            pre[r] = bits;
+            preValid |= (ok ? 1u : 0u) << r;
         }
     };
     auto storePair = [&]() {
@@ -151,14 +178,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             const int e = lane + 32 * r;
             const int row = e >= G::TIW ? 1 : 0;
             const int jl = e - row * G::TIW;
-            if (e < 2 * G::TIW) ((float*)sIn)[jl * 2 + row] = pre[r];
+            float v = 0.f;
+            if ((preValid >> r) & 1u) {
+                if (sizeof(T) == 4) v = __uint_as_float(pre[r]) + bias;
+                else v = __half2float(__ushort_as_half((unsigned short)pre[r])) + bias;
+            }
+            if (e < 2 * G::TIW) ((float*)sIn)[jl * 2 + row] = v;
         }
     };
 
+    int pairSlot = 0, groupSlot = 0;      // ring slots of input row 2*nextPair and of group g's first row
+
     // ---- stage B: horizontal upsample of the pair held in sIn -> ring rows 2t, 2t+1 ----------------
     auto stageB = [&](int t) {
-        float* row0 = sB + ((2 * t) % kRing) * G::BW;
-        float* row1 = sB + ((2 * t + 1) % kRing) * G::BW;
+        float* row0 = sB + pairSlot * G::BW;              // pairSlot == (2t) % kRing, kept incrementally
+        float* row1 = row0 + G::BW;
 #pragma unroll
         for (int r = 0; r < (G::NM + 31) / 32; r++) {
             const int m = lane + 32 * r;
@@ -188,7 +222,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     const long long sPlane = (long long)plane * p.sH;
     auto stageC = [&](int g, auto EYc) {
         constexpr int EY = decltype(EYc)::value;
-        const int wbase = (UP == 2 ? 2 * g : g) % kRing;
+        const int wbase = groupSlot;                      // == (UP == 2 ? 2g : g) % kRing
 #pragma unroll
         for (int r = 0; r < (G::BW / 2 + 31) / 32; r++) {
             const int pr = lane + 32 * r;
@@ -210,7 +244,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                     const int start = yq / UP + (ph > 0 ? 1 : 0);
                     float2 u = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int k = 0; k < kTapsPerPhase; k++) u = ffma2(w[start + k], p.tu[ph][k], u);
+                    for (int k = 0; k < kTapsPerPhase; k++) u = ffma2(w[start + k], p.tv[ph][k], u);
                     unsigned rc0 = 0, rc1 = 0;
                     if (MODE == SG3_SIGNS_READ) {
                         const int sY = Ys + 4 * g + j + p.sy;
@@ -221,8 +255,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                             if (sX + 1 >= 0 && ((sX + 1) >> 2) < p.sWb) rc1 = (unsigned)__ldg(srow + ((sX + 1) >> 2)) >> (((sX + 1) & 3) * 2);
                         }
                     }
-                    v[j].x = act1<MODE>(u.x, p.gain, p.slope, p.clamp, rc0, code0[j]);
-                    v[j].y = act1<MODE>(u.y, p.gain, p.slope, p.clamp, rc1, code1[j]);
+                    v[j].x = act1<MODE>(u.x, p.slope, p.lreluA, p.lreluB, p.clamp, rc0, code0[j]);
+                    v[j].y = act1<MODE>(u.y, p.slope, p.lreluA, p.lreluB, p.clamp, rc1, code1[j]);
                 }
                 const int xd0 = xp - ex, xd1 = xd0 + 1;     // column index in D's frame
                 if (xd0 >= 0 && xd0 < kAW) {
@@ -277,7 +311,27 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     auto stageD = [&](int g) {
         const float4* planeE = sC;
         const float4* planeO = sC + G::XH;
-        if (FD_FULL) {
+        if (FD == 2) {
+            // x-symmetric dense filter: per row pair, add mirrored pixels first (12 FADD2), then 6 taps per filter row.
+            const float2* pE = (const float2*)planeE;
+            const float2* pO = (const float2*)planeO;
+#pragma unroll
+            for (int half = 0; half < 2; half++) {          // half 0: rows (4g, 4g+2); half 1: rows (4g+1, 4g+3)
+                float2 px[kDownTaps + 2];
+#pragma unroll
+                for (int q = 0; q < kDownTaps + 2; q++)
+                    px[q] = ((q & 1) ? pO : pE)[2 * swz(2 * lane + (q >> 1)) + half];
+#pragma unroll
+                for (int cc = 0; cc < 2; cc++) {
+#pragma unroll
+                    for (int b = 0; b < kDownTaps / 2; b++) {
+                        const float2 sm = __fadd2_rn(px[2 * cc + b], px[2 * cc + kDownTaps - 1 - b]);
+#pragma unroll
+                        for (int k = 0; k < 6; k++) acc[k][cc] = ffma2(sm, p.fd2[2 * k + half][b], acc[k][cc]);
+                    }
+                }
+            }
+        } else if (FD_FULL) {
 #pragma unroll
             for (int q = 0; q < kDownTaps + 2; q++) {         // pixel 4*lane + q of D's frame
                 const float4 px = (q & 1) ? planeO[swz(2 * lane + (q >> 1))] : planeE[swz(2 * lane + (q >> 1))];
@@ -354,6 +408,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
         stageB(nextPair);
         __syncwarp();
         nextPair++;
+        pairSlot = pairSlot + 2 >= kRing ? 0 : pairSlot + 2;
     };
     loadPair(0);
     for (int g = 0; g < numGroups; g++) {
@@ -369,6 +424,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
         flushSigns(g);
         stageD(g);
         __syncwarp();
+        groupSlot += (UP == 2 ? 2 : 1);
+        groupSlot -= groupSlot >= kRing ? kRing : 0;
     }
 }
 
