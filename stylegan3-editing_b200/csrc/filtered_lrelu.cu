@@ -125,10 +125,11 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
         for (int b = 0; b < fs::kDownTaps; b++)
             p.fd2[a][b] = (full && a < fdH && b < fdW) ? d->fd[(d->flip ? a : fdH - 1 - a) * fdW + (d->flip ? b : fdW - 1 - b)] : 0.f;
 
-    // Strip decomposition: 64-column strips; rows are chunked only when there are too few strips to
+    // Strip decomposition: TW-column strips (58 / 56 outputs for up 2 / 4); rows are chunked only when there are too few strips to
     // fill the machine (one warp per strip, ~16 resident warps per SM, a few waves).
     const long long planes = (long long)d->N * d->C;
-    p.stripsX = (d->outW + fs::kTW - 1) / fs::kTW;
+    const int tw = up == 2 ? fs::Geo<2>::TW : fs::Geo<4>::TW;
+    p.stripsX = (d->outW + tw - 1) / tw;
     const long long base = planes * p.stripsX;
     const long long want = (long long)sg3_sm_count() * 16 * 3;
     int chunks = 1;

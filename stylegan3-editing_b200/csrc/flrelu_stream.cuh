@@ -6,30 +6,34 @@
 //   bias -> zero-insert x UP + FIR -> gain * lrelu, clamp (+ 2-bit sign codes) -> FIR + decimate by 2.
 //
 // How (B200-first; nothing here follows the reference's block-tile kernel):
-//  * One WARP owns one strip: 64 output columns x a chunk of output rows of one (n, c) plane, and
+//  * One WARP owns one strip: TW output columns x a chunk of output rows of one (n, c) plane, and
 //    streams down the rows.  Warps never synchronise with each other (no __syncthreads): each has a
-//    private shared-memory ring, so 16-20 resident warps per SM sit in different stages and the LSU,
+//    private shared-memory ring, so the ~16 resident warps per SM sit in different stages and the LSU,
 //    FMA and global-load latencies of one warp hide behind the others.
 //  * Per iteration a warp produces one GROUP = 4 activation rows = 2 output rows:
-//      A  global -> registers (prefetched one iteration ahead) -> smem, bias added, zero outside
+//      A  global -> registers (prefetched one iteration ahead, raw bits) -> smem, bias added, zero outside
 //      B  horizontal polyphase upsample of 2 input rows       (lane = input column)
 //      C  vertical polyphase upsample + gain/lrelu/clamp/signs (lane = 2 adjacent columns)
 //      D  down-by-2 FIR accumulated in registers               (lane = 2 adjacent output columns)
+//    TW (58 for UP=2, 56 for UP=4) is chosen so that B and C need exactly 128 upsampled columns =
+//    whole rounds of 32 lanes.
 //  * All FIR arithmetic is packed FFMA2 (fma.rn.f32x2): one instruction = 2 FMAs with the tap as a
-//    broadcast uniform-register operand (SASS: FFMA2 R, R.F32x2, UR.F32, R.F32x2).  The packed pair
-//    is always "same tap, two pixels": two input rows in B, two columns in C, and in D the two
-//    activation rows (Y, Y+2) that feed output rows (o, o+1) with the same filter row.  Measured on
-//    B200: 36.4 TFMA/s vs 30.3 for scalar FFMA, and the issue port is half idle for LDS/ALU work.
-//  * D never re-reads an activation: each loaded value feeds 6 (rows) x up to 2 (columns) x 2 (FFMA2
-//    lanes) MACs; the 6 live output-row pairs per column stay in registers and retire 2 rows per
-//    group.  Activations for D are laid out [column parity][column/2][4 rows permuted (0,2,1,3)] so
-//    one conflict-free LDS.128 yields both row pairs of a pixel.
+//    broadcast scalar operand.  The packed pair is always "same tap, two pixels": two input rows in B,
+//    two columns in C, and in D the two activation rows (Y, Y+2) that feed output rows (o, o+1) with the
+//    same filter row.  Measured on B200: 36.4 TFMA/s vs 30.3 for scalar FFMA, with half the issue slots.
+//  * D never re-reads an activation: the 6 live output-row pairs per column stay in registers and retire
+//    2 rows per group; the register roles rotate by compile-time renaming (3 code copies of D), not by moves.
+//    Activations for D are laid out [column parity][column/2][4 rows permuted (0,2,1,3)] so one
+//    conflict-free LDS.128 yields both row pairs of a pixel.  Dense filters that are mirror-symmetric in x
+//    (the radial jinc filters) pre-add mirrored pixels: 6 taps per filter row instead of 12.
+//  * The ring of horizontally-upsampled rows keeps a duplicate of its first 7 rows behind its end, so the
+//    8-row window of every group is contiguous: one address register, immediate offsets.
 //  * Taps travel in the launch parameters (constant bank -> uniform registers); no global filter
 //    state, any stream.
 //
-// Roofline note: with fp32 math this op is FP32-pipe bound on B200 (144 MAC per output for
-// the dense 12x12 down filter against 8 bytes of HBM traffic), so the kernel is built to saturate the
-// FMA pipe; HBM time is ~4x smaller than FMA time for config R.
+// Roofline note: with fp32 math this op is FP32-pipe bound on B200 (>= 84 packed-pair MACs
+// per output for the dense 12x12 down filter against 8 bytes of HBM traffic), so the kernel is built to
+// keep the FMA pipe busy; HBM time is ~3-4x smaller than FMA time for config R.
 #pragma once
 
 #include <type_traits>
@@ -40,23 +44,25 @@ namespace flrelu_stream {
 
 constexpr int kTapsPerPhase = 6;      // up filter taps per polyphase branch
 constexpr int kDownTaps = 12;         // down filter taps (per axis)
-constexpr int kTW = 64;               // output columns per strip (2 per lane)
-constexpr int kAW = 2 * (kTW - 1) + kDownTaps;   // 138 activation columns feed one strip
-constexpr int kRing = 12;             // rows in the horizontally-upsampled ring
 constexpr int kWarpsPerCta = 4;
+constexpr int kDup = 7;               // ring rows mirrored behind the ring end (window height - 1)
 
 template <int UP> struct Geo {
-    static constexpr int BW = ((kAW + UP - 1 + UP - 1) / UP) * UP;   // upsampled columns computed per strip (140 / 144)
-    static constexpr int NM = BW / UP;                               // input columns producing them (70 / 36)
-    static constexpr int TIW = NM + kTapsPerPhase;                   // input columns loaded (76 / 42)
-    static constexpr int A_ITEMS = (2 * TIW + 31) / 32;              // prefetch registers per lane
-    static constexpr int XH = 72;                                    // slots per parity plane (>= kAW/2 + 1, even)
-    static constexpr int SIN_BYTES = TIW * 2 * 4;
-    static constexpr int SB_BYTES = kRing * BW * 4;
+    static constexpr int TW = UP == 2 ? 58 : 56;                     // output columns per strip (2 per lane)
+    static constexpr int AW = 2 * (TW - 1) + kDownTaps;              // activation columns feeding one strip (126 / 122)
+    static constexpr int BW = ((AW + UP - 1 + UP - 1) / UP) * UP;    // upsampled columns computed per strip (128 / 128)
+    static constexpr int NM = BW / UP;                               // input columns producing them (64 / 32)
+    static constexpr int TIW = NM + kTapsPerPhase;                   // input columns loaded (70 / 38)
+    static constexpr int A_ITEMS = (TIW + 31) / 32;                  // prefetch registers per lane and row (3 / 2)
+    static constexpr int RING = UP == 2 ? 8 : 10;                    // live rows of the upsampled ring
+    static constexpr int XH = 64;                                    // slots per parity plane (>= AW/2 + 1)
+    static constexpr int SIN_BYTES = ((TIW * 2 * 4 + 15) / 16) * 16;
+    static constexpr int SB_BYTES = (RING + kDup) * BW * 4;
     static constexpr int SC_BYTES = 2 * XH * 16;
-    static constexpr int SS_ROW = 160;                               // sign staging bytes per row (>= BW + 3, mult of 16)
+    static constexpr int SS_ROW = 144;                               // sign staging bytes per row (>= AW + 3, mult of 16)
     static constexpr int SS_BYTES = 4 * SS_ROW;
     static constexpr int WARP_BYTES = ((SIN_BYTES + SB_BYTES + SC_BYTES + SS_BYTES + 127) / 128) * 128;
+    static_assert(BW == 128 && AW / 2 + 1 <= XH, "strip geometry");
 };
 
 struct Params {
@@ -79,22 +85,27 @@ __device__ __forceinline__ float2 ffma2(float2 a, float t, float2 c) { return __
 
 __device__ __forceinline__ int swz(int xh) { return xh ^ ((xh >> 3) & 1); }
 
-// leaky ReLU + clamp of one value that already carries the gain; returns the 2-bit sign code in WRITE mode.
-//   NONE : v*a + |v|*b (one FMUL + one FFMA with |.| source modifier), then clamp by two FMNMX
+// leaky ReLU + clamp of two values that already carry the gain; 2-bit sign codes in WRITE mode.
+//   NONE : v*a + |v|*b (one packed FMUL2 + FFMA with |.| source modifier), then clamp by two FMNMX
 //   WRITE: same value, plus code = clamped ? 2 : negative ? 1 : 0
 //   READ : backward pass: scale by {1, slope, 0} according to the stored code, no clamp
 template <int MODE>
-__device__ __forceinline__ float act1(float v, float slope, float la, float lb, float clamp, unsigned rd_code, unsigned& wr_code)
+__device__ __forceinline__ float2 act2(float2 v, const Params& p, unsigned rc0, unsigned rc1, unsigned& wc0, unsigned& wc1)
 {
     if (MODE == SG3_SIGNS_READ) {
-        if (rd_code & 1u) v *= slope;
-        if (rd_code & 2u) v = 0.f;
+        if (rc0 & 1u) v.x *= p.slope;
+        if (rc0 & 2u) v.x = 0.f;
+        if (rc1 & 1u) v.y *= p.slope;
+        if (rc1 & 2u) v.y = 0.f;
         return v;
     }
-    const float r = fmaf(fabsf(v), lb, v * la);
-    const float c = fminf(fmaxf(r, -clamp), clamp);
-    if (MODE == SG3_SIGNS_WRITE) wr_code = (fabsf(r) > clamp) ? 2u : ((v < 0.f) ? 1u : 0u);
-    return c;
+    const float2 va = __fmul2_rn(v, make_float2(p.lreluA, p.lreluA));
+    const float r0 = fmaf(fabsf(v.x), p.lreluB, va.x), r1 = fmaf(fabsf(v.y), p.lreluB, va.y);
+    if (MODE == SG3_SIGNS_WRITE) {
+        wc0 = (fabsf(r0) > p.clamp) ? 2u : ((v.x < 0.f) ? 1u : 0u);
+        wc1 = (fabsf(r1) > p.clamp) ? 2u : ((v.y < 0.f) ? 1u : 0u);
+    }
+    return make_float2(fminf(fmaxf(r0, -p.clamp), p.clamp), fminf(fmaxf(r1, -p.clamp), p.clamp));
 }
 
 // FD: 0 = separable down filter, 1 = dense 12x12, 2 = dense 12x12 with fd2[a][b] == fd2[a][11-b]
@@ -102,7 +113,6 @@ __device__ __forceinline__ float act1(float v, float slope, float la, float lb, 
 template <class T, int UP, int FD, int MODE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_constant__ Params p)
 {
-    constexpr bool FD_FULL = FD != 0;
     typedef Geo<UP> G;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,7 +121,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
 
     unsigned char* wsm = smem_raw + warp * G::WARP_BYTES;
     float2* sIn = (float2*)wsm;                                        // [TIW] (row 2t, row 2t+1)
-    float* sB = (float*)(wsm + G::SIN_BYTES);                          // [kRing][BW]
+    float* sB = (float*)(wsm + G::SIN_BYTES);                          // [RING + kDup][BW]
     float4* sC = (float4*)(wsm + G::SIN_BYTES + G::SB_BYTES);          // [2][XH] rows (0,2,1,3) of one pixel
     unsigned char* sS = wsm + G::SIN_BYTES + G::SB_BYTES + G::SC_BYTES;  // [4][SS_ROW] sign codes, one byte per pixel
 
@@ -121,9 +131,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     const int cyi = (int)(rest % p.chunksY);
     const long long plane = rest / p.chunksY;
     const int n = (int)(plane / p.C), c = (int)(plane - (long long)n * p.C);
-    const int ox0 = sxi * kTW;
+    const int ox0 = sxi * G::TW;
     const int oy0 = cyi * p.chunkRows;
-    const int tws = min(kTW, p.outW - ox0);                  // valid output columns in this strip
+    const int tws = min(G::TW, p.outW - ox0);                // valid output columns in this strip
     const int chs = min(p.chunkRows, p.outH - oy0);          // valid output rows in this chunk
     const int Xs = 2 * ox0, Ys = 2 * oy0;                    // activation-space origin of D
     const int ex = pos_mod(Xs - p.px0, UP), ey = pos_mod(Ys - p.py0, UP);
@@ -138,140 +148,147 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     // ---- stage A: global -> registers (pair t = input rows 2t, 2t+1 of the strip) -----------------
     // The raw bits stay in registers until the next iteration (nothing consumes them earlier, so the
     // global-load latency is covered by a whole B/C/D round); bias and the zero border are applied when
-    // they are stored to shared memory.  Column offsets and validity are per-lane constants of the strip.
-    unsigned pre[G::A_ITEMS];
-    unsigned preValid = 0;                     // bit r: pre[r] holds a real pixel
+    // they are stored to shared memory.  Column offsets are per-lane constants of the strip.
+    unsigned pre[2][G::A_ITEMS];
+    unsigned preValid = 0;                     // bit (row * A_ITEMS + r): pre[row][r] holds a real pixel
     int colOff[G::A_ITEMS];                    // byte offset of the lane's column, or -1 when outside the image
-    unsigned rowSel = 0;                       // bit r: item r belongs to the second row of the pair
 #pragma unroll
     for (int r = 0; r < G::A_ITEMS; r++) {
-        const int e = lane + 32 * r;
-        const int row = e >= G::TIW ? 1 : 0;
-        const int jl = e - row * G::TIW;
-        const int j = jBase + jl;
-        rowSel |= (unsigned)row << r;
-        colOff[r] = (e < 2 * G::TIW && j >= 0 && j < p.inW) ? (int)(j * p.xs[3]) : -1;
+        const int jl = lane + 32 * r, j = jBase + jl;
+        colOff[r] = (jl < G::TIW && j >= 0 && j < p.inW) ? (int)(j * p.xs[3]) : -1;
     }
     auto loadPair = [&](int t) {
-        const int i0 = iBase + 2 * t, i1 = i0 + 1;
-        const bool ok0 = i0 >= 0 && i0 < p.inH, ok1 = i1 >= 0 && i1 < p.inH;
-        const char* r0 = xPlane + (long long)i0 * p.xs[2];
-        const char* r1 = xPlane + (long long)i1 * p.xs[2];
+        const int i0 = iBase + 2 * t;
         preValid = 0;
 #pragma unroll
-        for (int r = 0; r < G::A_ITEMS; r++) {
-            const bool second = (rowSel >> r) & 1u;
-            const bool ok = colOff[r] >= 0 && (second ? ok1 : ok0);
-            unsigned bits = 0;
-            if (ok) {
-                const char* src = (second ? r1 : r0) + colOff[r];
-                if (sizeof(T) == 4) bits = __ldg((const unsigned*)src);
-                else bits = (unsigned)__ldg((const unsigned short*)src);
+        for (int row = 0; row < 2; row++) {
+            const int i = i0 + row;
+            const bool rowOk = i >= 0 && i < p.inH;
+            const char* rp = xPlane + (long long)i * p.xs[2];
+#pragma unroll
+            for (int r = 0; r < G::A_ITEMS; r++) {
+                const bool ok = rowOk && colOff[r] >= 0;
+                unsigned bits = 0;
+                if (ok) {
+                    if (sizeof(T) == 4) bits = __ldg((const unsigned*)(rp + colOff[r]));
+                    else bits = (unsigned)__ldg((const unsigned short*)(rp + colOff[r]));
+                }
+                pre[row][r] = bits;
+                preValid |= (ok ? 1u : 0u) << (row * G::A_ITEMS + r);
             }
-            pre[r] = bits;
-            preValid |= (ok ? 1u : 0u) << r;
         }
     };
     auto storePair = [&]() {
 #pragma unroll
         for (int r = 0; r < G::A_ITEMS; r++) {
-            const int e = lane + 32 * r;
-            const int row = e >= G::TIW ? 1 : 0;
-            const int jl = e - row * G::TIW;
-            float v = 0.f;
-            if ((preValid >> r) & 1u) {
-                if (sizeof(T) == 4) v = __uint_as_float(pre[r]) + bias;
-                else v = __half2float(__ushort_as_half((unsigned short)pre[r])) + bias;
+            const int jl = lane + 32 * r;
+            float2 v;
+#pragma unroll
+            for (int row = 0; row < 2; row++) {
+                float f = 0.f;
+                if ((preValid >> (row * G::A_ITEMS + r)) & 1u) {
+                    if (sizeof(T) == 4) f = __uint_as_float(pre[row][r]) + bias;
+                    else f = __half2float(__ushort_as_half((unsigned short)pre[row][r])) + bias;
+                }
+                if (row == 0) v.x = f; else v.y = f;
             }
-            if (e < 2 * G::TIW) ((float*)sIn)[jl * 2 + row] = v;
+            if (jl < G::TIW) sIn[jl] = v;
         }
     };
 
-    int pairSlot = 0, groupSlot = 0;      // ring slots of input row 2*nextPair and of group g's first row
+    int pairSlot = 0, groupSlot = 0;      // ring slots of input row 2*nextPair and of group g's first window row
 
     // ---- stage B: horizontal upsample of the pair held in sIn -> ring rows 2t, 2t+1 ----------------
-    auto stageB = [&](int t) {
-        float* row0 = sB + pairSlot * G::BW;              // pairSlot == (2t) % kRing, kept incrementally
+    // Rows landing in the first kDup ring slots are also written behind the ring end.
+    auto stageB = [&]() {
+        float* row0 = sB + pairSlot * G::BW;              // pairSlot == (2t) % RING, kept incrementally (always even)
         float* row1 = row0 + G::BW;
+        const bool dup0 = pairSlot < kDup, dup1 = pairSlot + 1 < kDup;
 #pragma unroll
-        for (int r = 0; r < (G::NM + 31) / 32; r++) {
+        for (int r = 0; r < G::NM / 32; r++) {
             const int m = lane + 32 * r;
-            if (m < G::NM) {
-                float2 v[kTapsPerPhase + 1];
+            float2 v[kTapsPerPhase + 1];
 #pragma unroll
-                for (int q = 0; q <= kTapsPerPhase; q++) v[q] = sIn[m + q];
-                float2 acc[UP];
+            for (int q = 0; q <= kTapsPerPhase; q++) v[q] = sIn[m + q];
+            float2 acc[UP];
 #pragma unroll
-                for (int ph = 0; ph < UP; ph++) {
-                    acc[ph] = make_float2(0.f, 0.f);
+            for (int ph = 0; ph < UP; ph++) {
+                acc[ph] = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int k = 0; k < kTapsPerPhase; k++) acc[ph] = ffma2(v[k + (ph > 0 ? 1 : 0)], p.tu[ph][k], acc[ph]);
-                }
-                if (UP == 2) {
-                    *(float2*)(row0 + 2 * m) = make_float2(acc[0].x, acc[1].x);
-                    *(float2*)(row1 + 2 * m) = make_float2(acc[0].y, acc[1].y);
-                } else {
-                    *(float4*)(row0 + 4 * m) = make_float4(acc[0].x, acc[1].x, acc[2 % UP].x, acc[3 % UP].x);
-                    *(float4*)(row1 + 4 * m) = make_float4(acc[0].y, acc[1].y, acc[2 % UP].y, acc[3 % UP].y);
-                }
+                for (int k = 0; k < kTapsPerPhase; k++) acc[ph] = ffma2(v[k + (ph > 0 ? 1 : 0)], p.tu[ph][k], acc[ph]);
+            }
+            if (UP == 2) {
+                const float2 o0 = make_float2(acc[0].x, acc[1].x), o1 = make_float2(acc[0].y, acc[1].y);
+                *(float2*)(row0 + 2 * m) = o0;
+                *(float2*)(row1 + 2 * m) = o1;
+                if (dup0) *(float2*)(row0 + G::RING * G::BW + 2 * m) = o0;
+                if (dup1) *(float2*)(row1 + G::RING * G::BW + 2 * m) = o1;
+            } else {
+                const float4 o0 = make_float4(acc[0].x, acc[1].x, acc[2 % UP].x, acc[3 % UP].x);
+                const float4 o1 = make_float4(acc[0].y, acc[1].y, acc[2 % UP].y, acc[3 % UP].y);
+                *(float4*)(row0 + 4 * m) = o0;
+                *(float4*)(row1 + 4 * m) = o1;
+                if (dup0) *(float4*)(row0 + G::RING * G::BW + 4 * m) = o0;
+                if (dup1) *(float4*)(row1 + G::RING * G::BW + 4 * m) = o1;
             }
         }
     };
 
     // ---- stage C: vertical upsample + activation of group g -> sC (+ sign codes) --------------------
+    // Per-lane store slots of the two columns of each round (constants of the strip); -1 = outside D's frame.
+    int cSlot0[2], cSlot1[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int xd0 = 2 * (lane + 32 * r) - ex, xd1 = xd0 + 1;
+        cSlot0[r] = (xd0 >= 0 && xd0 < G::AW) ? (xd0 & 1) * G::XH + swz(xd0 >> 1) : -1;
+        cSlot1[r] = (xd1 >= 0 && xd1 < G::AW) ? (xd1 & 1) * G::XH + swz(xd1 >> 1) : -1;
+    }
     const long long sPlane = (long long)plane * p.sH;
     auto stageC = [&](int g, auto EYc) {
         constexpr int EY = decltype(EYc)::value;
-        const int wbase = groupSlot;                      // == (UP == 2 ? 2g : g) % kRing
+        const float* win = sB + groupSlot * G::BW;       // 8 contiguous window rows (ring + mirrored tail)
 #pragma unroll
-        for (int r = 0; r < (G::BW / 2 + 31) / 32; r++) {
-            const int pr = lane + 32 * r;
-            if (pr < G::BW / 2) {
-                const int xp = 2 * pr;
-                float2 w[8];
+        for (int r = 0; r < 2; r++) {
+            const int xp = 2 * (lane + 32 * r);
+            float2 w[8];
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    int slot = wbase + q;
-                    slot -= slot >= kRing ? kRing : 0;
-                    w[q] = *(const float2*)(sB + slot * G::BW + xp);
-                }
-                float2 v[4];
-                unsigned code0[4], code1[4];
+            for (int q = 0; q < 8; q++) w[q] = *(const float2*)(win + q * G::BW + xp);
+            float2 v[4];
+            unsigned code0[4], code1[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int yq = j + EY;                  // row offset in the UP-aligned grid
-                    const int ph = yq % UP;                 // compile-time after unrolling
-                    const int start = yq / UP + (ph > 0 ? 1 : 0);
-                    float2 u = make_float2(0.f, 0.f);
+            for (int j = 0; j < 4; j++) {
+                const int yq = j + EY;                  // row offset in the UP-aligned grid
+                const int ph = yq % UP;                 // compile-time after unrolling
+                const int start = yq / UP + (ph > 0 ? 1 : 0);
+                float2 u = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int k = 0; k < kTapsPerPhase; k++) u = ffma2(w[start + k], p.tv[ph][k], u);
-                    unsigned rc0 = 0, rc1 = 0;
-                    if (MODE == SG3_SIGNS_READ) {
-                        const int sY = Ys + 4 * g + j + p.sy;
-                        const int sX = Xs - ex + xp + p.sx;
-                        if (sY >= 0 && sY < p.sH) {
-                            const uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
-                            if (sX >= 0 && (sX >> 2) < p.sWb) rc0 = (unsigned)__ldg(srow + (sX >> 2)) >> ((sX & 3) * 2);
-                            if (sX + 1 >= 0 && ((sX + 1) >> 2) < p.sWb) rc1 = (unsigned)__ldg(srow + ((sX + 1) >> 2)) >> (((sX + 1) & 3) * 2);
-                        }
-                    }
-                    v[j].x = act1<MODE>(u.x, p.slope, p.lreluA, p.lreluB, p.clamp, rc0, code0[j]);
-                    v[j].y = act1<MODE>(u.y, p.slope, p.lreluA, p.lreluB, p.clamp, rc1, code1[j]);
-                }
-                const int xd0 = xp - ex, xd1 = xd0 + 1;     // column index in D's frame
-                if (xd0 >= 0 && xd0 < kAW) {
-                    sC[(xd0 & 1) * G::XH + swz(xd0 >> 1)] = make_float4(v[0].x, v[2].x, v[1].x, v[3].x);
-                    if (MODE == SG3_SIGNS_WRITE) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) sS[j * G::SS_ROW + xd0] = (unsigned char)code0[j];
+                for (int k = 0; k < kTapsPerPhase; k++) u = ffma2(w[start + k], p.tv[ph][k], u);
+                unsigned rc0 = 0, rc1 = 0;
+                if (MODE == SG3_SIGNS_READ) {
+                    const int sY = Ys + 4 * g + j + p.sy;
+                    const int sX = Xs - ex + xp + p.sx;
+                    if (sY >= 0 && sY < p.sH) {
+                        const uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
+                        if (sX >= 0 && (sX >> 2) < p.sWb) rc0 = (unsigned)__ldg(srow + (sX >> 2)) >> ((sX & 3) * 2);
+                        if (sX + 1 >= 0 && ((sX + 1) >> 2) < p.sWb) rc1 = (unsigned)__ldg(srow + ((sX + 1) >> 2)) >> (((sX + 1) & 3) * 2);
                     }
                 }
-                if (xd1 >= 0 && xd1 < kAW) {
-                    sC[(xd1 & 1) * G::XH + swz(xd1 >> 1)] = make_float4(v[0].y, v[2].y, v[1].y, v[3].y);
-                    if (MODE == SG3_SIGNS_WRITE) {
+                v[j] = act2<MODE>(u, p, rc0, rc1, code0[j], code1[j]);
+            }
+            if (cSlot0[r] >= 0) {
+                sC[cSlot0[r]] = make_float4(v[0].x, v[2].x, v[1].x, v[3].x);
+                if (MODE == SG3_SIGNS_WRITE) {
+                    const int xd0 = xp - ex;
 #pragma unroll
-                        for (int j = 0; j < 4; j++) sS[j * G::SS_ROW + xd1] = (unsigned char)code1[j];
-                    }
+                    for (int j = 0; j < 4; j++) sS[j * G::SS_ROW + xd0] = (unsigned char)code0[j];
+                }
+            }
+            if (cSlot1[r] >= 0) {
+                sC[cSlot1[r]] = make_float4(v[0].y, v[2].y, v[1].y, v[3].y);
+                if (MODE == SG3_SIGNS_WRITE) {
+                    const int xd1 = xp - ex + 1;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) sS[j * G::SS_ROW + xd1] = (unsigned char)code1[j];
                 }
             }
         }
@@ -279,7 +296,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
 
     // sign bytes this strip owns: columns [0, ownW) of D's frame (whole bytes: Xs + sx is a multiple of 4),
     // rows [0, ownH) -- the last strip/chunk also owns the filter tail.
-    const int ownW = (sxi == p.stripsX - 1) ? 2 * (tws - 1) + kDownTaps : 2 * kTW;
+    const int ownW = (sxi == p.stripsX - 1) ? 2 * (tws - 1) + kDownTaps : 2 * G::TW;
     const int ownH = (cyi == p.chunksY - 1) ? 2 * (chs - 1) + kDownTaps : 2 * p.chunkRows;
     auto flushSigns = [&](int g) {
         if (MODE != SG3_SIGNS_WRITE) return;
@@ -302,13 +319,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     };
 
     // ---- stage D: down-by-2 FIR, accumulated in registers -------------------------------------------
-    // acc[k][c] = (partial of output row 2g-k, partial of output row 2g-k+1) for output column 2*lane+c.
+    // Logical accumulator k of group g = (partial of output row 2g-k, partial of output row 2g-k+1) for output
+    // column 2*lane+c; it lives in physical slot (k + 4*(g % 3)) % 6, so sliding by two rows per group is a
+    // renaming (ROT = g % 3 is a template argument) instead of register moves.
     float2 acc[6][2];
     float carry[2] = {0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 6; k++) { acc[k][0] = make_float2(0.f, 0.f); acc[k][1] = make_float2(0.f, 0.f); }
+    const int dl = min(lane, G::TW / 2 - 1);             // idle lanes read a valid column
+    int dSlot[7];                                        // swizzled slots of the 7 pixel pairs a lane reads
+#pragma unroll
+    for (int h = 0; h < 7; h++) dSlot[h] = swz(2 * dl + h);
 
-    auto stageD = [&](int g) {
+    auto stageD = [&](int g, auto ROTc) {
+        constexpr int ROT = decltype(ROTc)::value;
+#define ACC(k, cc) acc[((k) + 4 * ROT) % 6][cc]
         const float4* planeE = sC;
         const float4* planeO = sC + G::XH;
         if (FD == 2) {
@@ -319,22 +344,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             for (int half = 0; half < 2; half++) {          // half 0: rows (4g, 4g+2); half 1: rows (4g+1, 4g+3)
                 float2 px[kDownTaps + 2];
 #pragma unroll
-                for (int q = 0; q < kDownTaps + 2; q++)
-                    px[q] = ((q & 1) ? pO : pE)[2 * swz(2 * lane + (q >> 1)) + half];
+                for (int q = 0; q < kDownTaps + 2; q++) px[q] = ((q & 1) ? pO : pE)[2 * dSlot[q >> 1] + half];
 #pragma unroll
                 for (int cc = 0; cc < 2; cc++) {
 #pragma unroll
                     for (int b = 0; b < kDownTaps / 2; b++) {
                         const float2 sm = __fadd2_rn(px[2 * cc + b], px[2 * cc + kDownTaps - 1 - b]);
 #pragma unroll
-                        for (int k = 0; k < 6; k++) acc[k][cc] = ffma2(sm, p.fd2[2 * k + half][b], acc[k][cc]);
+                        for (int k = 0; k < 6; k++) ACC(k, cc) = ffma2(sm, p.fd2[2 * k + half][b], ACC(k, cc));
                     }
                 }
             }
-        } else if (FD_FULL) {
+        } else if (FD == 1) {
 #pragma unroll
             for (int q = 0; q < kDownTaps + 2; q++) {         // pixel 4*lane + q of D's frame
-                const float4 px = (q & 1) ? planeO[swz(2 * lane + (q >> 1))] : planeE[swz(2 * lane + (q >> 1))];
+                const float4 px = (q & 1) ? planeO[dSlot[q >> 1]] : planeE[dSlot[q >> 1]];
                 const float2 pa = make_float2(px.x, px.y);  // rows 4g, 4g+2
                 const float2 pb = make_float2(px.z, px.w);  // rows 4g+1, 4g+3
 #pragma unroll
@@ -343,8 +367,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                     if (b >= 0 && b < kDownTaps) {
 #pragma unroll
                         for (int k = 0; k < 6; k++) {
-                            acc[k][cc] = ffma2(pa, p.fd2[2 * k][b], acc[k][cc]);
-                            acc[k][cc] = ffma2(pb, p.fd2[2 * k + 1][b], acc[k][cc]);
+                            ACC(k, cc) = ffma2(pa, p.fd2[2 * k][b], ACC(k, cc));
+                            ACC(k, cc) = ffma2(pb, p.fd2[2 * k + 1][b], ACC(k, cc));
                         }
                     }
                 }
@@ -354,7 +378,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             ha[0] = ha[1] = hb[0] = hb[1] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < kDownTaps + 2; q++) {
-                const float4 px = (q & 1) ? planeO[swz(2 * lane + (q >> 1))] : planeE[swz(2 * lane + (q >> 1))];
+                const float4 px = (q & 1) ? planeO[dSlot[q >> 1]] : planeE[dSlot[q >> 1]];
                 const float2 pa = make_float2(px.x, px.y);
                 const float2 pb = make_float2(px.z, px.w);
 #pragma unroll
@@ -370,15 +394,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             for (int cc = 0; cc < 2; cc++)
 #pragma unroll
                 for (int k = 0; k < 6; k++) {
-                    acc[k][cc] = ffma2(ha[cc], p.fdx[2 * k], acc[k][cc]);
-                    acc[k][cc] = ffma2(hb[cc], p.fdx[2 * k + 1], acc[k][cc]);
+                    ACC(k, cc) = ffma2(ha[cc], p.fdx[2 * k], ACC(k, cc));
+                    ACC(k, cc) = ffma2(hb[cc], p.fdx[2 * k + 1], ACC(k, cc));
                 }
         }
-        // retire output rows 2g-5 and 2g-4, then slide the accumulators down by two rows
+        // retire output rows 2g-5 and 2g-4; their two slots become the fresh logical 0 and 1 of the next group
         const int oA = 2 * g - 5, oB = 2 * g - 4;
-        const float a0 = acc[5][0].x + carry[0], a1 = acc[5][1].x + carry[1];
-        const float b0 = acc[4][0].x + acc[5][0].y, b1 = acc[4][1].x + acc[5][1].y;
-        carry[0] = acc[4][0].y; carry[1] = acc[4][1].y;
+        const float a0 = ACC(5, 0).x + carry[0], a1 = ACC(5, 1).x + carry[1];
+        const float b0 = ACC(4, 0).x + ACC(5, 0).y, b1 = ACC(4, 1).x + ACC(5, 1).y;
+        carry[0] = ACC(4, 0).y; carry[1] = ACC(4, 1).y;
+        ACC(4, 0) = ACC(4, 1) = ACC(5, 0) = ACC(5, 1) = make_float2(0.f, 0.f);
         const int oxl = 2 * lane;
         if (oxl < tws) {
             const bool two = oxl + 1 < tws;
@@ -393,9 +418,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                 if (two) st_as<T>((T*)((char*)dst + p.ys[3]), b1);
             }
         }
-#pragma unroll
-        for (int k = 5; k >= 2; k--) { acc[k][0] = acc[k - 2][0]; acc[k][1] = acc[k - 2][1]; }
-        acc[0][0] = acc[0][1] = acc[1][0] = acc[1][1] = make_float2(0.f, 0.f);
+#undef ACC
     };
 
     // ---- schedule -----------------------------------------------------------------------------------
@@ -405,12 +428,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
         storePair();
         __syncwarp();
         loadPair(nextPair + 1);           // prefetch the following pair while computing
-        stageB(nextPair);
+        stageB();
         __syncwarp();
         nextPair++;
-        pairSlot = pairSlot + 2 >= kRing ? 0 : pairSlot + 2;
+        pairSlot = pairSlot + 2 >= G::RING ? 0 : pairSlot + 2;
     };
     loadPair(0);
+    int rot = 0;
     for (int g = 0; g < numGroups; g++) {
         const int lastRow = (UP == 2 ? 2 * g : g) + 7;       // highest ring row group g reads
         while (2 * nextPair <= lastRow) producePair();
@@ -422,10 +446,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
         }
         __syncwarp();
         flushSigns(g);
-        stageD(g);
+        if (rot == 0) stageD(g, std::integral_constant<int, 0>());
+        else if (rot == 1) stageD(g, std::integral_constant<int, 1>());
+        else stageD(g, std::integral_constant<int, 2>());
+        rot = rot == 2 ? 0 : rot + 1;
         __syncwarp();
         groupSlot += (UP == 2 ? 2 : 1);
-        groupSlot -= groupSlot >= kRing ? kRing : 0;
+        groupSlot -= groupSlot >= G::RING ? G::RING : 0;
     }
 }
 
