@@ -175,11 +175,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import sg3_b200
-    from sg3_b200 import capi, filtered_lrelu as fl_mod, modulated_conv, networks
+    from sg3_b200 import capi, filtered_lrelu as fl_mod, modulated_conv, networks, sharding
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
+    rank, world, local = sharding.rank_info()
     assert torch.cuda.is_available(), 'bench.py needs CUDA (no CPU fallback for the product path)'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -193,7 +191,8 @@ def run_ours(args):
     torch.manual_seed(0)
     G = networks.Generator(**R1024).eval().requires_grad_(False).to(dev)
     B = args.batch
-    z = torch.randn(B, 512, generator=torch.Generator().manual_seed(1 + rank)).to(dev)
+    z_all = torch.randn(world * B, 512, generator=torch.Generator().manual_seed(1))      # the global batch of latents ...
+    z = sharding.shard_batch(z_all, rank, world).to(dev)                                 # ... sharded contiguously, no collective
     with torch.no_grad():
         ws = G.mapping(z, None).contiguous()
     ws_host = ws.cpu().pin_memory()
@@ -234,11 +233,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def max_over_ranks(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t)
+        return sharding.max_over_ranks(ms, device=dev)
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
