@@ -5,8 +5,6 @@
 // value in the launch parameters (no setup kernel, no cudaMemcpyToSymbol, no global state -> one launch
 // per call and safe on any stream); tiles are scheduled as a 1-D list of warp strips (no grid-z limit,
 // 64-bit addressing throughout).
-#include <mutex>
-
 #include "flrelu_stream.cuh"
 
 namespace fs = flrelu_stream;
@@ -40,45 +38,15 @@ SG3_EXPORT int sg3_filtered_lrelu_supported(int up, int down, int fuW, int fuH, 
     return 0;
 }
 
+// Kernel instantiations live in flrelu_inst_*.cu (one translation unit per dtype x up factor, built in parallel).
+template <class T, int UP> int flrelu_stream_launch(const fs::Params& p, int fdMode, int signMode, cudaStream_t stream);
+
 namespace {
-
-template <class T, int UP, int FD, int MODE>
-int launch_stream(const fs::Params& p, cudaStream_t stream)
-{
-    auto kern = fs::kernel<T, UP, FD, MODE>;
-    const int smem = fs::kWarpsPerCta * fs::Geo<UP>::WARP_BYTES;
-    static std::once_flag once;
-    static cudaError_t attrErr = cudaSuccess;
-    std::call_once(once, [&] { attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
-    if (attrErr != cudaSuccess) return (int)attrErr;
-    const long long ctas = (p.totalStrips + fs::kWarpsPerCta - 1) / fs::kWarpsPerCta;
-    if (ctas > 0x7fffffffLL) return SG3_E_TOOLARGE;
-    kern<<<(unsigned)ctas, fs::kWarpsPerCta * 32, smem, stream>>>(p);
-    return sg3_launch_status();
-}
-
-template <class T, int UP, int FD>
-int dispatch_mode(const fs::Params& p, int mode, cudaStream_t stream)
-{
-    switch (mode) {
-    case SG3_SIGNS_NONE:  return launch_stream<T, UP, FD, SG3_SIGNS_NONE>(p, stream);
-    case SG3_SIGNS_WRITE: return launch_stream<T, UP, FD, SG3_SIGNS_WRITE>(p, stream);
-    case SG3_SIGNS_READ:  return launch_stream<T, UP, FD, SG3_SIGNS_READ>(p, stream);
-    }
-    return SG3_E_INVALID;
-}
 
 template <class T>
 int dispatch_shape(const fs::Params& p, int up, int fdMode, int mode, cudaStream_t stream)
 {
-    if (up == 2) {
-        if (fdMode == 0) return dispatch_mode<T, 2, 0>(p, mode, stream);
-        if (fdMode == 1) return dispatch_mode<T, 2, 1>(p, mode, stream);
-        return dispatch_mode<T, 2, 2>(p, mode, stream);
-    }
-    if (fdMode == 0) return dispatch_mode<T, 4, 0>(p, mode, stream);
-    if (fdMode == 1) return dispatch_mode<T, 4, 1>(p, mode, stream);
-    return dispatch_mode<T, 4, 2>(p, mode, stream);
+    return up == 2 ? flrelu_stream_launch<T, 2>(p, fdMode, mode, stream) : flrelu_stream_launch<T, 4>(p, fdMode, mode, stream);
 }
 
 }  // namespace
@@ -119,11 +87,20 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
     p.lreluA = 0.5f * (1.0f + d->slope);
     p.lreluB = 0.5f * (1.0f - d->slope);
     const bool full = fdH != 0 && d->fd != nullptr;
+    float fd2[fs::kDownTaps][fs::kDownTaps];
     for (int b = 0; b < fs::kDownTaps; b++)
         p.fdx[b] = (!full && b < fdW) ? (d->fd ? d->fd[d->flip ? b : fdW - 1 - b] : 1.0f) : 0.f;
     for (int a = 0; a < fs::kDownTaps; a++)
         for (int b = 0; b < fs::kDownTaps; b++)
-            p.fd2[a][b] = (full && a < fdH && b < fdW) ? d->fd[(d->flip ? a : fdH - 1 - a) * fdW + (d->flip ? b : fdW - 1 - b)] : 0.f;
+            fd2[a][b] = (full && a < fdH && b < fdW) ? d->fd[(d->flip ? a : fdH - 1 - a) * fdW + (d->flip ? b : fdW - 1 - b)] : 0.f;
+    for (int rot = 0; rot < 3; rot++)
+        for (int i = 0; i < 6; i++) {
+            const int k = (i + 2 * rot) % 6;                      // logical accumulator held by slot i at this rotation
+            for (int half = 0; half < 2; half++) {
+                p.fdvr[rot][i][half] = p.fdx[2 * k + half];
+                for (int b = 0; b < fs::kDownTaps; b++) p.fdr[rot][i][half][b] = fd2[2 * k + half][b];
+            }
+        }
 
     // Strip decomposition: TW-column strips (58 / 56 outputs for up 2 / 4); rows are chunked only when there are too few strips to
     // fill the machine (one warp per strip, ~16 resident warps per SM, a few waves).
@@ -150,7 +127,7 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
         bool sym = true;
         for (int a = 0; a < fs::kDownTaps && sym; a++)
             for (int b = 0; b < fs::kDownTaps / 2; b++)
-                if (p.fd2[a][b] != p.fd2[a][fs::kDownTaps - 1 - b]) { sym = false; break; }
+                if (fd2[a][b] != fd2[a][fs::kDownTaps - 1 - b]) { sym = false; break; }
         if (sym) fdMode = 2;
     }
     if ((long long)d->inW * (d->xStride[3] < 0 ? -d->xStride[3] : d->xStride[3]) > 0x7fffffffLL) return SG3_E_NOKERNEL;

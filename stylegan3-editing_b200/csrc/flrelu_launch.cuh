@@ -1,0 +1,52 @@
+// flrelu_launch.cuh -- launch + mode dispatch of flrelu_stream::kernel for one (dtype, up) pair.
+#pragma once
+
+#include <mutex>
+
+#include "flrelu_stream.cuh"
+
+namespace flrelu_stream {
+
+template <class T, int UP, int FD, int MODE>
+int launch_one(const Params& p, cudaStream_t stream)
+{
+    auto kern = kernel<T, UP, FD, MODE>;
+    const int smem = kWarpsPerCta * Geo<UP>::WARP_BYTES;
+    static std::once_flag once;
+    static cudaError_t attrErr = cudaSuccess;
+    std::call_once(once, [&] { attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    if (attrErr != cudaSuccess) return (int)attrErr;
+    const long long ctas = (p.totalStrips + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (ctas > 0x7fffffffLL) return SG3_E_TOOLARGE;
+    kern<<<(unsigned)ctas, kWarpsPerCta * 32, smem, stream>>>(p);
+    return sg3_launch_status();
+}
+
+template <class T, int UP, int FD>
+int launch_mode(const Params& p, int mode, cudaStream_t stream)
+{
+    switch (mode) {
+    case SG3_SIGNS_NONE:  return launch_one<T, UP, FD, SG3_SIGNS_NONE>(p, stream);
+    case SG3_SIGNS_WRITE: return launch_one<T, UP, FD, SG3_SIGNS_WRITE>(p, stream);
+    case SG3_SIGNS_READ:  return launch_one<T, UP, FD, SG3_SIGNS_READ>(p, stream);
+    }
+    return SG3_E_INVALID;
+}
+
+template <class T, int UP>
+int launch_fd(const Params& p, int fdMode, int mode, cudaStream_t stream)
+{
+    switch (fdMode) {
+    case 0: return launch_mode<T, UP, 0>(p, mode, stream);
+    case 1: return launch_mode<T, UP, 1>(p, mode, stream);
+    case 2: return launch_mode<T, UP, 2>(p, mode, stream);
+    }
+    return SG3_E_INVALID;
+}
+
+}  // namespace flrelu_stream
+
+#define SG3_FLRELU_INSTANTIATE(T, UP)                                                                          \
+    template <class TT, int U> int flrelu_stream_launch(const flrelu_stream::Params&, int, int, cudaStream_t); \
+    template <> int flrelu_stream_launch<T, UP>(const flrelu_stream::Params& p, int fdMode, int signMode, cudaStream_t stream) \
+    { return flrelu_stream::launch_fd<T, UP>(p, fdMode, signMode, stream); }

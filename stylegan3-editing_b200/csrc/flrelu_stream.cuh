@@ -22,7 +22,7 @@
 //    two columns in C, and in D the two activation rows (Y, Y+2) that feed output rows (o, o+1) with the
 //    same filter row.  Measured on B200: 36.4 TFMA/s vs 30.3 for scalar FFMA, with half the issue slots.
 //  * D never re-reads an activation: the 6 live output-row pairs per column stay in registers and retire
-//    2 rows per group; the register roles rotate by compile-time renaming (3 code copies of D), not by moves.
+//    2 rows per group; instead of moving registers the tap tables rotate (uniform constant-bank offset).
 //    Activations for D are laid out [column parity][column/2][4 rows permuted (0,2,1,3)] so one
 //    conflict-free LDS.128 yields both row pairs of a pixel.  Dense filters that are mirror-symmetric in x
 //    (the radial jinc filters) pre-add mirrored pixels: 6 taps per filter row instead of 12.
@@ -77,8 +77,12 @@ struct Params {
     float tu[4][kTapsPerPhase];        // tu[p][k]: up taps of phase p, pre-scaled by UP (horizontal pass)
     float tv[4][kTapsPerPhase];        // vertical pass: tu * gain (the activation gain rides on the taps)
     float lreluA, lreluB;              // lrelu(v) = v*lreluA + |v|*lreluB = v*(1+slope)/2 + |v|*(1-slope)/2
-    float fdx[kDownTaps];              // separable down taps (correlation order); unused when dense
-    float fd2[kDownTaps][kDownTaps];   // dense down taps fd2[a][b] (correlation order); unused when separable
+    float fdx[kDownTaps];              // separable down taps (correlation order), horizontal pass; unused when dense
+    // Down taps as seen by the 6 physical accumulator slots of stage D for each of the 3 rotations (g % 3):
+    // slot i holds logical accumulator k = (i + 2*rot) % 6, which pairs with filter rows 2k (half 0) and 2k+1
+    // (half 1).  fdr[rot][i][half][b] = FD'[2k + half][b] (dense), fdvr[rot][i][half] = fdx[2k + half] (separable).
+    float fdr[3][6][2][kDownTaps];
+    float fdvr[3][6][2];
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float t, float2 c) { return __ffma2_rn(a, make_float2(t, t), c); }
@@ -115,7 +119,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
 {
     typedef Geo<UP> G;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // The warp index comes from a lane-0 broadcast so that the compiler treats everything derived from it (strip
+    // geometry, loop counters, ring slots, tap-table offsets) as warp-uniform and keeps it on the uniform datapath.
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const long long strip = (long long)blockIdx.x * kWarpsPerCta + warp;
     if (strip >= p.totalStrips) return;
 
@@ -319,9 +325,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     };
 
     // ---- stage D: down-by-2 FIR, accumulated in registers -------------------------------------------
-    // Logical accumulator k of group g = (partial of output row 2g-k, partial of output row 2g-k+1) for output
-    // column 2*lane+c; it lives in physical slot (k + 4*(g % 3)) % 6, so sliding by two rows per group is a
-    // renaming (ROT = g % 3 is a template argument) instead of register moves.
+    // Physical accumulator slot i holds one pair of output rows (o, o+1) of output column 2*lane+c from the group
+    // that first touches it until it retires; its logical index k = 2g - o grows by 2 per group, so instead of
+    // moving registers the taps rotate: slot i uses the tap rows of logical k = (i + 2*rot) % 6, rot = g % 3,
+    // fetched from rotated tables in the constant bank with a uniform offset.  One copy of the FMA code.
     float2 acc[6][2];
     float carry[2] = {0.f, 0.f};
 #pragma unroll
@@ -331,9 +338,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
 #pragma unroll
     for (int h = 0; h < 7; h++) dSlot[h] = swz(2 * dl + h);
 
-    auto stageD = [&](int g, auto ROTc) {
-        constexpr int ROT = decltype(ROTc)::value;
-#define ACC(k, cc) acc[((k) + 4 * ROT) % 6][cc]
+    auto stageD = [&](int g, int rot) {
         const float4* planeE = sC;
         const float4* planeO = sC + G::XH;
         if (FD == 2) {
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                     for (int b = 0; b < kDownTaps / 2; b++) {
                         const float2 sm = __fadd2_rn(px[2 * cc + b], px[2 * cc + kDownTaps - 1 - b]);
 #pragma unroll
-                        for (int k = 0; k < 6; k++) ACC(k, cc) = ffma2(sm, p.fd2[2 * k + half][b], ACC(k, cc));
+                        for (int i = 0; i < 6; i++) acc[i][cc] = ffma2(sm, p.fdr[rot][i][half][b], acc[i][cc]);
                     }
                 }
             }
@@ -366,9 +371,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                     const int b = q - 2 * cc;               // tap column for output column 2*lane+cc
                     if (b >= 0 && b < kDownTaps) {
 #pragma unroll
-                        for (int k = 0; k < 6; k++) {
-                            ACC(k, cc) = ffma2(pa, p.fd2[2 * k][b], ACC(k, cc));
-                            ACC(k, cc) = ffma2(pb, p.fd2[2 * k + 1][b], ACC(k, cc));
+                        for (int i = 0; i < 6; i++) {
+                            acc[i][cc] = ffma2(pa, p.fdr[rot][i][0][b], acc[i][cc]);
+                            acc[i][cc] = ffma2(pb, p.fdr[rot][i][1][b], acc[i][cc]);
                         }
                     }
                 }
@@ -393,17 +398,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
 #pragma unroll
             for (int cc = 0; cc < 2; cc++)
 #pragma unroll
-                for (int k = 0; k < 6; k++) {
-                    ACC(k, cc) = ffma2(ha[cc], p.fdx[2 * k], ACC(k, cc));
-                    ACC(k, cc) = ffma2(hb[cc], p.fdx[2 * k + 1], ACC(k, cc));
+                for (int i = 0; i < 6; i++) {
+                    acc[i][cc] = ffma2(ha[cc], p.fdvr[rot][i][0], acc[i][cc]);
+                    acc[i][cc] = ffma2(hb[cc], p.fdvr[rot][i][1], acc[i][cc]);
                 }
         }
-        // retire output rows 2g-5 and 2g-4; their two slots become the fresh logical 0 and 1 of the next group
+        // Retire output rows 2g-5 and 2g-4: logical accumulators 5 and 4 = slots (5 + 4*rot) % 6 and (4 + 4*rot) % 6;
+        // the freed slots start the next group as logical 1 and 0.
+        float a0, a1, b0, b1;
+#define SG3_RETIRE(S4, S5)                                                                      \
+        a0 = acc[S5][0].x + carry[0]; a1 = acc[S5][1].x + carry[1];                             \
+        b0 = acc[S4][0].x + acc[S5][0].y; b1 = acc[S4][1].x + acc[S5][1].y;                     \
+        carry[0] = acc[S4][0].y; carry[1] = acc[S4][1].y;                                       \
+        acc[S4][0] = acc[S4][1] = acc[S5][0] = acc[S5][1] = make_float2(0.f, 0.f);
+        if (rot == 0) { SG3_RETIRE(4, 5) } else if (rot == 1) { SG3_RETIRE(2, 3) } else { SG3_RETIRE(0, 1) }
+#undef SG3_RETIRE
         const int oA = 2 * g - 5, oB = 2 * g - 4;
-        const float a0 = ACC(5, 0).x + carry[0], a1 = ACC(5, 1).x + carry[1];
-        const float b0 = ACC(4, 0).x + ACC(5, 0).y, b1 = ACC(4, 1).x + ACC(5, 1).y;
-        carry[0] = ACC(4, 0).y; carry[1] = ACC(4, 1).y;
-        ACC(4, 0) = ACC(4, 1) = ACC(5, 0) = ACC(5, 1) = make_float2(0.f, 0.f);
         const int oxl = 2 * lane;
         if (oxl < tws) {
             const bool two = oxl + 1 < tws;
@@ -418,7 +428,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                 if (two) st_as<T>((T*)((char*)dst + p.ys[3]), b1);
             }
         }
-#undef ACC
     };
 
     // ---- schedule -----------------------------------------------------------------------------------
@@ -434,25 +443,31 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
         pairSlot = pairSlot + 2 >= G::RING ? 0 : pairSlot + 2;
     };
     loadPair(0);
-    int rot = 0;
-    for (int g = 0; g < numGroups; g++) {
-        const int lastRow = (UP == 2 ? 2 * g : g) + 7;       // highest ring row group g reads
-        while (2 * nextPair <= lastRow) producePair();
-        switch (ey) {
-        case 0: stageC(g, std::integral_constant<int, 0>()); break;
-        case 1: stageC(g, std::integral_constant<int, 1>()); break;
-        case 2: if (UP == 4) stageC(g, std::integral_constant<int, (UP == 4 ? 2 : 0)>()); break;
-        default: if (UP == 4) stageC(g, std::integral_constant<int, (UP == 4 ? 3 : 0)>()); break;
+    // EY is a template argument of the whole loop (the polyphase row pattern of stage C is then fixed code);
+    // everything else exists once.
+    auto run = [&](auto EYc) {
+        int rot = 0;
+        for (int g = 0; g < numGroups; g++) {
+            const int lastRow = (UP == 2 ? 2 * g : g) + 7;   // highest ring row group g reads
+            while (2 * nextPair <= lastRow) producePair();
+            stageC(g, EYc);
+            __syncwarp();
+            flushSigns(g);
+            stageD(g, rot);
+            __syncwarp();
+            rot = rot == 2 ? 0 : rot + 1;
+            groupSlot += (UP == 2 ? 2 : 1);
+            groupSlot -= groupSlot >= G::RING ? G::RING : 0;
         }
-        __syncwarp();
-        flushSigns(g);
-        if (rot == 0) stageD(g, std::integral_constant<int, 0>());
-        else if (rot == 1) stageD(g, std::integral_constant<int, 1>());
-        else stageD(g, std::integral_constant<int, 2>());
-        rot = rot == 2 ? 0 : rot + 1;
-        __syncwarp();
-        groupSlot += (UP == 2 ? 2 : 1);
-        groupSlot -= groupSlot >= G::RING ? G::RING : 0;
+    };
+    if (UP == 2) {
+        if (ey == 0) run(std::integral_constant<int, 0>());
+        else run(std::integral_constant<int, 1>());
+    } else {
+        if (ey == 0) run(std::integral_constant<int, 0>());
+        else if (ey == 1) run(std::integral_constant<int, 1>());
+        else if (ey == 2) run(std::integral_constant<int, (UP == 4 ? 2 : 0)>());
+        else run(std::integral_constant<int, (UP == 4 ? 3 : 0)>());
     }
 }
 
