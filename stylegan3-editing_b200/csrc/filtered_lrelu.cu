@@ -5,6 +5,8 @@
 // value in the launch parameters (no setup kernel, no cudaMemcpyToSymbol, no global state -> one launch
 // per call and safe on any stream); tiles are scheduled as a 1-D list of warp strips (no grid-z limit,
 // 64-bit addressing throughout).
+#include <cstring>
+
 #include "flrelu_stream.cuh"
 
 namespace fs = flrelu_stream;
@@ -93,12 +95,14 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
     for (int a = 0; a < fs::kDownTaps; a++)
         for (int b = 0; b < fs::kDownTaps; b++)
             fd2[a][b] = (full && a < fdH && b < fdW) ? d->fd[(d->flip ? a : fdH - 1 - a) * fdW + (d->flip ? b : fdW - 1 - b)] : 0.f;
+    memset(p.fdr, 0, sizeof(p.fdr));
+    memset(p.fdvr, 0, sizeof(p.fdvr));
     for (int rot = 0; rot < 3; rot++)
         for (int i = 0; i < 6; i++) {
             const int k = (i + 2 * rot) % 6;                      // logical accumulator held by slot i at this rotation
             for (int half = 0; half < 2; half++) {
-                p.fdvr[rot][i][half] = p.fdx[2 * k + half];
-                for (int b = 0; b < fs::kDownTaps; b++) p.fdr[rot][i][half][b] = fd2[2 * k + half][b];
+                p.fdvr[rot][half][i] = p.fdx[2 * k + half];
+                for (int b = 0; b < fs::kDownTaps; b++) p.fdr[rot][half][b][i] = fd2[2 * k + half][b];
             }
         }
 

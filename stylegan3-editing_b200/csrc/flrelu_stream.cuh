@@ -81,8 +81,10 @@ struct Params {
     // Down taps as seen by the 6 physical accumulator slots of stage D for each of the 3 rotations (g % 3):
     // slot i holds logical accumulator k = (i + 2*rot) % 6, which pairs with filter rows 2k (half 0) and 2k+1
     // (half 1).  fdr[rot][i][half][b] = FD'[2k + half][b] (dense), fdvr[rot][i][half] = fdx[2k + half] (separable).
-    float fdr[3][6][2][kDownTaps];
-    float fdvr[3][6][2];
+    // Stored with the slot index fastest (padded to 8) so the 6 taps an inner loop consumes are one 128-bit and one
+    // 64-bit uniform load.
+    float fdr[3][2][kDownTaps][8];     // [rot][half][b][slot]
+    float fdvr[3][2][8];               // [rot][half][slot]
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float t, float2 c) { return __ffma2_rn(a, make_float2(t, t), c); }
@@ -248,6 +250,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
         const int xd0 = 2 * (lane + 32 * r) - ex, xd1 = xd0 + 1;
         cSlot0[r] = (xd0 >= 0 && xd0 < G::AW) ? (xd0 & 1) * G::XH + swz(xd0 >> 1) : -1;
         cSlot1[r] = (xd1 >= 0 && xd1 < G::AW) ? (xd1 & 1) * G::XH + swz(xd1 >> 1) : -1;
+        // identity shuffle: makes the value opaque so it stays in a register instead of being recomputed per group
+        cSlot0[r] = __shfl_sync(0xffffffffu, cSlot0[r], lane);
+        cSlot1[r] = __shfl_sync(0xffffffffu, cSlot1[r], lane);
     }
     const long long sPlane = (long long)plane * p.sH;
     auto stageC = [&](int g, auto EYc) {
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     const int dl = min(lane, G::TW / 2 - 1);             // idle lanes read a valid column
     int dSlot[7];                                        // swizzled slots of the 7 pixel pairs a lane reads
 #pragma unroll
-    for (int h = 0; h < 7; h++) dSlot[h] = swz(2 * dl + h);
+    for (int h = 0; h < 7; h++) dSlot[h] = __shfl_sync(0xffffffffu, swz(2 * dl + h), lane);   // opaque, see cSlot
 
     auto stageD = [&](int g, int rot) {
         const float4* planeE = sC;
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                     for (int b = 0; b < kDownTaps / 2; b++) {
                         const float2 sm = __fadd2_rn(px[2 * cc + b], px[2 * cc + kDownTaps - 1 - b]);
 #pragma unroll
-                        for (int i = 0; i < 6; i++) acc[i][cc] = ffma2(sm, p.fdr[rot][i][half][b], acc[i][cc]);
+                        for (int i = 0; i < 6; i++) acc[i][cc] = ffma2(sm, p.fdr[rot][half][b][i], acc[i][cc]);
                     }
                 }
             }
@@ -372,8 +377,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                     if (b >= 0 && b < kDownTaps) {
 #pragma unroll
                         for (int i = 0; i < 6; i++) {
-                            acc[i][cc] = ffma2(pa, p.fdr[rot][i][0][b], acc[i][cc]);
-                            acc[i][cc] = ffma2(pb, p.fdr[rot][i][1][b], acc[i][cc]);
+                            acc[i][cc] = ffma2(pa, p.fdr[rot][0][b][i], acc[i][cc]);
+                            acc[i][cc] = ffma2(pb, p.fdr[rot][1][b][i], acc[i][cc]);
                         }
                     }
                 }
@@ -399,8 +404,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             for (int cc = 0; cc < 2; cc++)
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
-                    acc[i][cc] = ffma2(ha[cc], p.fdvr[rot][i][0], acc[i][cc]);
-                    acc[i][cc] = ffma2(hb[cc], p.fdvr[rot][i][1], acc[i][cc]);
+                    acc[i][cc] = ffma2(ha[cc], p.fdvr[rot][0][i], acc[i][cc]);
+                    acc[i][cc] = ffma2(hb[cc], p.fdvr[rot][1][i], acc[i][cc]);
                 }
         }
         // Retire output rows 2g-5 and 2g-4: logical accumulators 5 and 4 = slots (5 + 4*rot) % 6 and (4 + 4*rot) % 6;
