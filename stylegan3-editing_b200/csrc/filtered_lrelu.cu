@@ -32,8 +32,16 @@ SG3_EXPORT int sg3_filtered_lrelu_shape(int inH, int inW, int up, int down,
     return 0;
 }
 
+int sg3_flrelu_pointwise(const sg3_flrelu_desc* d, float fuScale, float fdScale, cudaStream_t stream);
+
+static bool is_pointwise(int up, int down, int fuW, int fuH, int fdW, int fdH)
+{
+    return up == 1 && down == 1 && fuW == 1 && fuH <= 1 && fdW == 1 && fdH <= 1;
+}
+
 SG3_EXPORT int sg3_filtered_lrelu_supported(int up, int down, int fuW, int fuH, int fdW, int fdH)
 {
+    if (is_pointwise(up, down, fuW, fuH, fdW, fdH)) return 0;
     if (down != 2 || (up != 2 && up != 4)) return SG3_E_NOKERNEL;
     if (fuH != 0 || fuW < 1 || fuW > fs::kTapsPerPhase * up) return SG3_E_NOKERNEL;      // separable up filter only
     if (fdW < 1 || fdW > fs::kDownTaps || fdH > fs::kDownTaps) return SG3_E_NOKERNEL;
@@ -64,6 +72,13 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
     if (rc != 0) return rc;
     if (d->signMode != SG3_SIGNS_NONE && (!d->signs || d->sH < 1 || d->sWb < 1)) return SG3_E_INVALID;
     if (d->signMode == SG3_SIGNS_WRITE && (d->sx & 3)) return SG3_E_NOKERNEL;   // sign bytes must align with strips
+    if (is_pointwise(d->up, d->down, fuW, fuH, fdW, fdH)) {
+        // 1x1 "filters" are scalars (a separable 1-tap filter acts on both axes: squared); padding would change the size
+        if (d->px0 != 0 || d->py0 != 0 || d->outW != d->inW || d->outH != d->inH) return SG3_E_NOKERNEL;
+        const float su = d->fu ? (fuH == 0 ? d->fu[0] * d->fu[0] : d->fu[0]) : 1.0f;
+        const float sd = d->fd ? (fdH == 0 ? d->fd[0] * d->fd[0] : d->fd[0]) : 1.0f;
+        return sg3_flrelu_pointwise(d, su, sd, (cudaStream_t)stream);
+    }
 
     fs::Params p;
     p.x = d->x; p.y = d->y; p.b = d->b; p.s = d->signs;
