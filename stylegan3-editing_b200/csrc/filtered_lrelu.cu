@@ -49,14 +49,29 @@ SG3_EXPORT int sg3_filtered_lrelu_supported(int up, int down, int fuW, int fuH, 
 }
 
 // Kernel instantiations live in flrelu_inst_*.cu (one translation unit per dtype x up factor, built in parallel).
-template <class T, int UP> int flrelu_stream_launch(const fs::Params& p, int fdMode, int signMode, cudaStream_t stream);
+template <class T, int UP, int TMAFLAG> int flrelu_stream_launch(const fs::Params& p, int fdMode, int signMode, cudaStream_t stream);
+
+bool sg3_make_tensor_map(CUtensorMap* m, CUtensorMapDataType type, int rank, const void* base, const uint64_t* dims,
+                         const uint64_t* stridesBytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
 
 namespace {
 
 template <class T>
 int dispatch_shape(const fs::Params& p, int up, int fdMode, int mode, cudaStream_t stream)
 {
-    return up == 2 ? flrelu_stream_launch<T, 2>(p, fdMode, mode, stream) : flrelu_stream_launch<T, 4>(p, fdMode, mode, stream);
+    return up == 2 ? flrelu_stream_launch<T, 2, 0>(p, fdMode, mode, stream) : flrelu_stream_launch<T, 4, 0>(p, fdMode, mode, stream);
+}
+
+// fp32 input with unit pixel stride and 16-byte aligned base / row / channel / sample strides: stage A by TMA.
+bool try_tma_map(fs::Params& p, const sg3_flrelu_desc* d, int up)
+{
+    if (d->dtype != SG3_F32 || d->xStride[3] != 4) return false;
+    if (((uintptr_t)d->x & 15) || (d->xStride[2] & 15) || (d->xStride[1] & 15) || (d->xStride[0] & 15)) return false;
+    if (d->xStride[2] <= 0 || d->xStride[1] <= 0 || d->xStride[0] <= 0) return false;
+    const uint64_t dims[4] = {(uint64_t)d->inW, (uint64_t)d->inH, (uint64_t)d->C, (uint64_t)d->N};
+    const uint64_t strides[3] = {(uint64_t)d->xStride[2], (uint64_t)d->xStride[1], (uint64_t)d->xStride[0]};
+    const uint32_t box[4] = {(uint32_t)(up == 2 ? fs::Geo<2>::TIWP : fs::Geo<4>::TIWP), 2, 1, 1};
+    return sg3_make_tensor_map(&p.mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 }  // namespace
@@ -152,6 +167,9 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
     if ((long long)d->inW * (d->xStride[3] < 0 ? -d->xStride[3] : d->xStride[3]) > 0x7fffffffLL) return SG3_E_NOKERNEL;
 
     cudaStream_t st = (cudaStream_t)stream;
+    if (d->dtype == SG3_F32 && try_tma_map(p, d, up))
+        return up == 2 ? flrelu_stream_launch<float, 2, 1>(p, fdMode, d->signMode, st)
+                       : flrelu_stream_launch<float, 4, 1>(p, fdMode, d->signMode, st);
     if (d->dtype == SG3_F32) return dispatch_shape<float>(p, up, fdMode, d->signMode, st);
     return dispatch_shape<__half>(p, up, fdMode, d->signMode, st);
 }

@@ -1,0 +1,4 @@
+// Instantiates flrelu_stream::kernel<float, 2, *, *, TMA=1> (9 kernels).
+#include "flrelu_launch.cuh"
+
+SG3_FLRELU_INSTANTIATE(float, 2, 1)

@@ -11,7 +11,8 @@
 //    private shared-memory ring, so the ~16 resident warps per SM sit in different stages and the LSU,
 //    FMA and global-load latencies of one warp hide behind the others.
 //  * Per iteration a warp produces one GROUP = 4 activation rows = 2 output rows:
-//      A  global -> registers (prefetched one iteration ahead, raw bits) -> smem, bias added, zero outside
+//      A  TMA bulk-tensor copy of the next 2 input rows into smem (fp32, aligned strides), one pair ahead;
+//         otherwise global -> registers (raw bits, one iteration ahead) -> smem; zero outside the image
 //      B  horizontal polyphase upsample of 2 input rows       (lane = input column)
 //      C  vertical polyphase upsample + gain/lrelu/clamp/signs (lane = 2 adjacent columns)
 //      D  down-by-2 FIR accumulated in registers               (lane = 2 adjacent output columns)
@@ -36,6 +37,7 @@
 // keep the FMA pipe busy; HBM time is ~3-4x smaller than FMA time for config R.
 #pragma once
 
+#include <cuda.h>
 #include <type_traits>
 
 #include "common.cuh"
@@ -56,7 +58,12 @@ template <int UP> struct Geo {
     static constexpr int A_ITEMS = (TIW + 31) / 32;                  // prefetch registers per lane and row (3 / 2)
     static constexpr int RING = UP == 2 ? 8 : 10;                    // live rows of the upsampled ring
     static constexpr int XH = 64;                                    // slots per parity plane (>= AW/2 + 1)
-    static constexpr int SIN_BYTES = ((TIW * 2 * 4 + 15) / 16) * 16;
+    // TMA box width: the box must start on a 16-byte boundary (column multiple of 4), so up to 3 extra columns
+    // are fetched on the left; 16-byte multiple: 76 / 44
+    static constexpr int TIWP = ((TIW + 3 + 3) / 4) * 4;
+    static constexpr int TMA_BUF = ((2 * TIWP * 4 + 127) / 128) * 128;   // one [2 rows][TIWP] landing buffer, 128-byte aligned
+    // stage-A staging: register path = [TIW] float2; TMA path = two landing buffers + two mbarriers
+    static constexpr int SIN_BYTES = 2 * TMA_BUF + 128;
     static constexpr int SB_BYTES = (RING + kDup) * BW * 4;
     static constexpr int SC_BYTES = 2 * XH * 16;
     static constexpr int SS_ROW = 144;                               // sign staging bytes per row (>= AW + 3, mult of 16)
@@ -66,6 +73,7 @@ template <int UP> struct Geo {
 };
 
 struct Params {
+    alignas(64) CUtensorMap mapX;      // 4-D map of x {W, H, C, N}, box {TIWP, 2, 1, 1}; used by the TMA variants only
     const void* x; void* y; const void* b; uint8_t* s;
     int N, C, inH, inW, outH, outW;
     long long xs[4], ys[4], bs;        // byte strides
@@ -86,6 +94,19 @@ struct Params {
     float fdr[3][2][kDownTaps][8];     // [rot][half][b][slot]
     float fdvr[3][2][8];               // [rot][half][slot]
 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
 
 __device__ __forceinline__ float2 ffma2(float2 a, float t, float2 c) { return __ffma2_rn(a, make_float2(t, t), c); }
 
@@ -116,7 +137,10 @@ __device__ __forceinline__ float2 act2(float2 v, const Params& p, unsigned rc0, 
 
 // FD: 0 = separable down filter, 1 = dense 12x12, 2 = dense 12x12 with fd2[a][b] == fd2[a][11-b]
 // (the radial filters): column pairs are pre-added, 6 taps per filter row instead of 12.
-template <class T, int UP, int FD, int MODE>
+// TMA: stage A is a cp.async.bulk.tensor of the [2 rows][TIWP] input box into shared memory (zero fill outside the
+// image comes from the tensor map; the bias enters as the initial value of the stage-B accumulators).  Needs fp32,
+// unit pixel stride and 16-byte aligned row/plane strides; otherwise the register-prefetch path (TMA = false) runs.
+template <class T, int UP, int FD, int MODE, bool TMA>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_constant__ Params p)
 {
     typedef Geo<UP> G;
@@ -128,7 +152,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     if (strip >= p.totalStrips) return;
 
     unsigned char* wsm = smem_raw + warp * G::WARP_BYTES;
-    float2* sIn = (float2*)wsm;                                        // [TIW] (row 2t, row 2t+1)
+    float2* sIn = (float2*)wsm;                                        // register path: [TIW] (row 2t, row 2t+1)
+    uint64_t* sBar = (uint64_t*)(wsm + 2 * G::TMA_BUF);               // TMA path: one mbarrier per landing buffer
     float* sB = (float*)(wsm + G::SIN_BYTES);                          // [RING + kDup][BW]
     float4* sC = (float4*)(wsm + G::SIN_BYTES + G::SB_BYTES);          // [2][XH] rows (0,2,1,3) of one pixel
     unsigned char* sS = wsm + G::SIN_BYTES + G::SB_BYTES + G::SC_BYTES;  // [4][SS_ROW] sign codes, one byte per pixel
@@ -165,6 +190,46 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
         const int jl = lane + 32 * r, j = jBase + jl;
         colOff[r] = (jl < G::TIW && j >= 0 && j < p.inW) ? (int)(j * p.xs[3]) : -1;
     }
+    // TMA path: per-lane bias terms of the stage-B accumulators, hb[r][ph] = bias * sum_k tu[ph][k] * [input column
+    // m + (ph > 0) + k is inside the image]  (the tensor map zero-fills outside columns and rows).
+    float hb[(G::NM / 32) * UP];
+    if (TMA) {
+#pragma unroll
+        for (int r = 0; r < G::NM / 32; r++)
+#pragma unroll
+            for (int ph = 0; ph < UP; ph++) {
+                float acc0 = 0.f;
+#pragma unroll
+                for (int k = 0; k < kTapsPerPhase; k++) {
+                    const int j = jBase + lane + 32 * r + (ph > 0 ? 1 : 0) + k;
+                    if (j >= 0 && j < p.inW) acc0 += p.tu[ph][k];
+                }
+                hb[r * UP + ph] = __shfl_sync(0xffffffffu, acc0 * bias, lane);      // opaque: keep it in a register
+            }
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sBar[0])) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&sBar[1])) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    const int dj = pos_mod(jBase, 4);      // the TMA box starts at column jBase - dj (a multiple of 4, possibly negative)
+    auto tmaIssue = [&](int t) {           // one lane starts the bulk copy of input rows 2t, 2t+1 into buffer t & 1
+        if (lane == 0) {
+            const uint32_t bar = smem_u32(&sBar[t & 1]);
+            const uint32_t dst = smem_u32(wsm + (t & 1) * G::TMA_BUF);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(2 * G::TIWP * 4)) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                ::"r"(dst), "l"((uint64_t)&p.mapX), "r"(bar), "r"(jBase - dj), "r"(iBase + 2 * t), "r"(c), "r"(n) : "memory");
+        }
+    };
+    auto tmaWait = [&](int t) {            // every lane waits until buffer t & 1 holds pair t (bounded: trap, never hang)
+        const uint32_t bar = smem_u32(&sBar[t & 1]);
+        const uint32_t parity = (uint32_t)(t >> 1) & 1u;
+        for (uint32_t spins = 0; !mbar_try_wait(bar, parity); spins++)
+            if (spins > (1u << 24)) __trap();
+    };
     auto loadPair = [&](int t) {
         const int i0 = iBase + 2 * t;
         preValid = 0;
@@ -208,20 +273,30 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
 
     // ---- stage B: horizontal upsample of the pair held in sIn -> ring rows 2t, 2t+1 ----------------
     // Rows landing in the first kDup ring slots are also written behind the ring end.
-    auto stageB = [&]() {
+    auto stageB = [&](int t) {
         float* row0 = sB + pairSlot * G::BW;              // pairSlot == (2t) % RING, kept incrementally (always even)
         float* row1 = row0 + G::BW;
         const bool dup0 = pairSlot < kDup, dup1 = pairSlot + 1 < kDup;
+        const float* tin = (const float*)(wsm + (t & 1) * G::TMA_BUF) + dj;     // TMA landing buffer [2][TIWP], strip column 0
+        float rm0 = 0.f, rm1 = 0.f;                       // row-inside-image masks of the pair (TMA path: scale the bias term)
+        if (TMA) {
+            const int i0 = iBase + 2 * t;
+            rm0 = (i0 >= 0 && i0 < p.inH) ? 1.f : 0.f;
+            rm1 = (i0 + 1 >= 0 && i0 + 1 < p.inH) ? 1.f : 0.f;
+        }
 #pragma unroll
         for (int r = 0; r < G::NM / 32; r++) {
             const int m = lane + 32 * r;
             float2 v[kTapsPerPhase + 1];
 #pragma unroll
-            for (int q = 0; q <= kTapsPerPhase; q++) v[q] = sIn[m + q];
+            for (int q = 0; q <= kTapsPerPhase; q++) {
+                if (TMA) v[q] = make_float2(tin[m + q], tin[G::TIWP + m + q]);
+                else v[q] = sIn[m + q];
+            }
             float2 acc[UP];
 #pragma unroll
             for (int ph = 0; ph < UP; ph++) {
-                acc[ph] = make_float2(0.f, 0.f);
+                acc[ph] = TMA ? make_float2(hb[r * UP + ph] * rm0, hb[r * UP + ph] * rm1) : make_float2(0.f, 0.f);
 #pragma unroll
                 for (int k = 0; k < kTapsPerPhase; k++) acc[ph] = ffma2(v[k + (ph > 0 ? 1 : 0)], p.tu[ph][k], acc[ph]);
             }
@@ -438,16 +513,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     // ---- schedule -----------------------------------------------------------------------------------
     // Group g reads ring rows [2g, 2g+7] (UP=2) or [g, g+7] (UP=4); pairs are produced just in time.
     int nextPair = 0;
-    auto producePair = [&]() {            // pre[] holds pair `nextPair`
-        storePair();
-        __syncwarp();
-        loadPair(nextPair + 1);           // prefetch the following pair while computing
-        stageB();
+    auto producePair = [&]() {            // pair `nextPair` is in flight (TMA) or in pre[] (register path)
+        if (TMA) {
+            tmaWait(nextPair);
+            tmaIssue(nextPair + 1);       // the other buffer was last read by the previous stage B (a __syncwarp ago)
+        } else {
+            storePair();
+            __syncwarp();
+            loadPair(nextPair + 1);       // prefetch the following pair while computing
+        }
+        stageB(nextPair);
         __syncwarp();
         nextPair++;
         pairSlot = pairSlot + 2 >= G::RING ? 0 : pairSlot + 2;
     };
-    loadPair(0);
+    if (TMA) tmaIssue(0); else loadPair(0);
     // EY is a template argument of the whole loop (the polyphase row pattern of stage C is then fixed code);
     // everything else exists once.
     auto run = [&](auto EYc) {
@@ -474,6 +554,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
         else if (ey == 2) run(std::integral_constant<int, (UP == 4 ? 2 : 0)>());
         else run(std::integral_constant<int, (UP == 4 ? 3 : 0)>());
     }
+    if (TMA) tmaWait(nextPair);           // never leave with a bulk copy still writing this warp's shared memory
 }
 
 }  // namespace flrelu_stream

@@ -238,6 +238,23 @@ EncodeTiledFn get_encode()
     return fn;
 }
 
+}  // namespace
+
+// Generic tiled tensor-map encoder shared with the filtered_lrelu TMA path.
+bool sg3_make_tensor_map(CUtensorMap* m, CUtensorMapDataType type, int rank, const void* base, const uint64_t* dims,
+                         const uint64_t* stridesBytes, const uint32_t* box, CUtensorMapSwizzle swizzle)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc || rank < 1 || rank > 5) return false;
+    cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+    for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; i++) gs[i] = stridesBytes[i];
+    return enc(m, type, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+namespace {
+
 bool make_map3(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1Bytes, uint64_t s2Bytes,
                uint32_t b0, uint32_t b1, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B)
 {
