@@ -38,7 +38,7 @@ def parse_args():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
-    ap.add_argument('--batch', type=int, default=8, help='images per GPU per step')
+    ap.add_argument('--batch', type=int, default=32, help='images per GPU per step')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--math', default='tf32', choices=['tf32', 'fp32'], help='modulated_conv2d contraction')
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='time budget of the cpu_baseline sample')
