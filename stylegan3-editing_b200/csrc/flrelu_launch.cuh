@@ -11,7 +11,7 @@ template <class T, int UP, int FD, int MODE, bool TMA>
 int launch_one(const Params& p, cudaStream_t stream)
 {
     auto kern = kernel<T, UP, FD, MODE, TMA>;
-    const int smem = kWarpsPerCta * Geo<UP>::WARP_BYTES;
+    const int smem = kWarpsPerCta * Geo<UP>::warp_bytes(MODE);
     static std::once_flag once;
     static cudaError_t attrErr = cudaSuccess;
     std::call_once(once, [&] { attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });

@@ -68,7 +68,8 @@ template <int UP> struct Geo {
     static constexpr int SC_BYTES = 2 * XH * 16;
     static constexpr int SS_ROW = 144;                               // sign staging bytes per row (>= AW + 3, mult of 16)
     static constexpr int SS_BYTES = 4 * SS_ROW;
-    static constexpr int WARP_BYTES = ((SIN_BYTES + SB_BYTES + SC_BYTES + SS_BYTES + 127) / 128) * 128;
+    // per-warp shared memory; the sign staging area exists only in sign-WRITE kernels (5 instead of 4 CTAs per SM otherwise)
+    static constexpr int warp_bytes(int mode) { return ((SIN_BYTES + SB_BYTES + SC_BYTES + (mode == SG3_SIGNS_WRITE ? SS_BYTES : 0) + 127) / 128) * 128; }
     static_assert(BW == 128 && AW / 2 + 1 <= XH, "strip geometry");
 };
 
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     const long long strip = (long long)blockIdx.x * kWarpsPerCta + warp;
     if (strip >= p.totalStrips) return;
 
-    unsigned char* wsm = smem_raw + warp * G::WARP_BYTES;
+    unsigned char* wsm = smem_raw + warp * G::warp_bytes(MODE);
     float2* sIn = (float2*)wsm;                                        // register path: [TIW] (row 2t, row 2t+1)
     uint64_t* sBar = (uint64_t*)(wsm + 2 * G::TMA_BUF);               // TMA path: one mbarrier per landing buffer
     float* sB = (float*)(wsm + G::SIN_BYTES);                          // [RING + kDup][BW]

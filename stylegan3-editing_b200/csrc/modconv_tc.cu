@@ -14,8 +14,9 @@
 // rows are padded to `ldw` floats by the prologue so that their pitch is 16-byte aligned).
 //
 // Warp roles (192 threads): warps 0-3 epilogue (TMEM lanes 32w..32w+31), warp 4 TMA producer,
-// warp 5 TMEM allocator + MMA issuer.  One output tile per CTA; 2 CTAs per SM overlap one tile's
-// epilogue with the other's loads.  Every mbarrier wait is bounded (trap instead of hang).
+// warp 5 TMEM allocator + MMA issuer.  Persistent: one CTA per SM loops over tiles; the TMA ring runs ahead across
+// tiles and the accumulator is double-buffered in TMEM, so loads, MMAs and the epilogue of consecutive tiles overlap.
+// Every mbarrier wait is bounded (trap instead of hang).
 #include <cuda.h>
 #include <mutex>
 
@@ -25,7 +26,7 @@ namespace {
 
 constexpr int BM = 128;            // pixels per tile (UMMA M)
 constexpr int BK = 32;             // input channels per stage (one 128-byte swizzle row of the K-major operand)
-constexpr int kStages = 4;
+constexpr int kMaxStages = 6;
 constexpr int A_STAGE_BYTES = BM * BK * 4;      // 16 KB: 4 boxes of [32 rows][128 B]
 constexpr int kThreads = 192;
 
@@ -34,9 +35,11 @@ struct TcParams {
     int N, I, O, P;
     int BN;                // out-channels per tile (multiple of 16, <= 256)
     int tmemCols;          // power of two >= max(BN, 32)
+    int accCols;           // TMEM columns per accumulator stage (BN rounded up to 32); two stages are allocated
     int tilesM, tilesN;
     int kTiles;
-    int stages;            // pipeline depth (3 when two CTAs share an SM, else 4)
+    int stages;            // smem pipeline depth (4 for 48 KB stages, 6 for <= 32 KB stages)
+    long long totalTiles;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,30 +123,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA producer runs
+// ahead across tile boundaries (the smem ring never drains), the accumulator is double-buffered in TMEM so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
 __global__ void __launch_bounds__(kThreads, 1)
 modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const TcParams p)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t barFull[kStages], barEmpty[kStages], barAccum;
+    __shared__ __align__(8) uint64_t barFull[kMaxStages], barEmpty[kMaxStages], barAccFull[2], barAccEmpty[2];
     __shared__ uint32_t tmemBase;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bStageBytes = p.BN * BK * 4;
-    const int stageBytes = A_STAGE_BYTES + bStageBytes;
-    // SWIZZLE_128B operands need 1024-byte aligned tiles
-    const uint32_t tiles = (smem_u32(smem) + 1023u) & ~1023u;
-
-    // tile coordinates: n-tile fastest so that CTAs sharing a pixel block run together (L2 reuse of X)
-    const long long t = blockIdx.x;
-    const int tn = (int)(t % p.tilesN);
-    const long long rest = t / p.tilesN;
-    const int tm = (int)(rest % p.tilesM);
-    const int n = (int)(rest / p.tilesM);
-    const int p0 = tm * BM, o0 = tn * p.BN;
+    const int stageBytes = A_STAGE_BYTES + p.BN * BK * 4;
+    const uint32_t tiles = (smem_u32(smem) + 1023u) & ~1023u;        // SWIZZLE_128B operands need 1024-byte aligned tiles
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(smem_u32(&barFull[s]), 1); mbar_init(smem_u32(&barEmpty[s]), 1); }
-        mbar_init(smem_u32(&barAccum), 1);
+        for (int s = 0; s < kMaxStages; s++) { mbar_init(smem_u32(&barFull[s]), 1); mbar_init(smem_u32(&barEmpty[s]), 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(smem_u32(&barAccFull[a]), 1); mbar_init(smem_u32(&barAccEmpty[a]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
@@ -155,19 +156,34 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmemBase;
 
+    // tile -> (sample n, pixel block tm, channel block tn); channel block fastest so that the CTAs working on one
+    // pixel block at the same time share its activation tiles in L2
+    auto decode = [&](long long t, int& n, int& p0, int& o0) {
+        const int tn = (int)(t % p.tilesN);
+        const long long rest = t / p.tilesN;
+        const int tm = (int)(rest % p.tilesM);
+        n = (int)(rest / p.tilesM);
+        p0 = tm * BM;
+        o0 = tn * p.BN;
+    };
+
     if (warp == 4) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
-            for (int kt = 0; kt < p.kTiles; kt++) {
-                const int s = kt % p.stages;
-                const uint32_t round = kt / p.stages;
-                if (kt >= p.stages) mbar_wait(smem_u32(&barEmpty[s]), (round - 1) & 1);
-                const uint32_t full = smem_u32(&barFull[s]);
-                mbar_expect_tx(full, (uint32_t)stageBytes);
-                const uint32_t aDst = tiles + s * stageBytes;
+            uint32_t it = 0;                                          // k-iterations issued so far, across tiles
+            for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x) {
+                int n, p0, o0;
+                decode(t, n, p0, o0);
+                for (int kt = 0; kt < p.kTiles; kt++, it++) {
+                    const uint32_t s = it % p.stages, round = it / p.stages;
+                    if (round > 0) mbar_wait(smem_u32(&barEmpty[s]), (round - 1) & 1);
+                    const uint32_t full = smem_u32(&barFull[s]);
+                    mbar_expect_tx(full, (uint32_t)stageBytes);
+                    const uint32_t aDst = tiles + s * stageBytes;
 #pragma unroll
-                for (int j = 0; j < 4; j++) tma_load_3d(aDst + j * (BK * 128), &mapX, full, p0 + 32 * j, kt * BK, n);
-                tma_load_3d(aDst + A_STAGE_BYTES, &mapW, full, kt * BK, o0, n);
+                    for (int j = 0; j < 4; j++) tma_load_3d(aDst + j * (BK * 128), &mapX, full, p0 + 32 * j, kt * BK, n);
+                    tma_load_3d(aDst + A_STAGE_BYTES, &mapW, full, kt * BK, o0, n);
+                }
             }
         }
     } else if (warp == 5) {
@@ -176,40 +192,57 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, A MN-major, B K-major, N, M=128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
                                    ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int kt = 0; kt < p.kTiles; kt++) {
-                const int s = kt % p.stages;
-                mbar_wait(smem_u32(&barFull[s]), (kt / p.stages) & 1);
+            uint32_t it = 0, tc = 0;                                  // k-iterations / tiles consumed so far
+            for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x, tc++) {
+                const uint32_t as = tc & 1, use = tc >> 1;            // accumulator stage and how often it was used before
+                if (use > 0) mbar_wait(smem_u32(&barAccEmpty[as]), (use - 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t aBase = tiles + s * stageBytes, bBase = aBase + A_STAGE_BYTES;
+                const uint32_t acc = tmem + as * p.accCols;
+                for (int kt = 0; kt < p.kTiles; kt++, it++) {
+                    const uint32_t s = it % p.stages;
+                    mbar_wait(smem_u32(&barFull[s]), (it / p.stages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t aBase = tiles + s * stageBytes, bBase = aBase + A_STAGE_BYTES;
 #pragma unroll
-                for (int ks = 0; ks < BK / 8; ks++) {
-                    // A (fp32, MN-major): 8 k-rows of 128 B per step = two 4-row swizzle atoms 512 B apart (SBO);
-                    // 32-pixel blocks BK*128 B apart (LBO)
-                    const uint64_t da = umma_desc(aBase + ks * 1024, BK * 128, 512, kLayoutSw128Base32);
-                    // B: step 8 tf32 = 32 B inside the 128-byte row; 8-row groups 1024 B apart
-                    const uint64_t db = umma_desc(bBase + ks * 32, 16, 1024);
-                    umma_tf32(tmem, da, db, idesc, (kt > 0 || ks > 0) ? 1u : 0u);
+                    for (int ks = 0; ks < BK / 8; ks++) {
+                        // A (fp32, MN-major): 8 k-rows of 128 B per step = two 4-row swizzle atoms 512 B apart (SBO);
+                        // 32-pixel blocks BK*128 B apart (LBO)
+                        const uint64_t da = umma_desc(aBase + ks * 1024, BK * 128, 512, kLayoutSw128Base32);
+                        // B: step 8 tf32 = 32 B inside the 128-byte row; 8-row groups 1024 B apart
+                        const uint64_t db = umma_desc(bBase + ks * 32, 16, 1024);
+                        umma_tf32(acc, da, db, idesc, (kt > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(&barEmpty[s]));              // frees the smem stage when these MMAs retire
                 }
-                umma_commit(smem_u32(&barEmpty[s]));            // frees the stage when these MMAs retire
+                umma_commit(smem_u32(&barAccFull[as]));               // accumulator of this tile complete
             }
-            umma_commit(smem_u32(&barAccum));                   // accumulator complete
         }
     } else {
-        // ---------------- epilogue: TMEM -> registers -> global ----------------
-        mbar_wait(smem_u32(&barAccum), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int pix = p0 + 32 * warp + lane;
-        float* yn = p.y + ((size_t)n * p.O) * (size_t)p.P;
-        for (int c = 0; c < p.BN; c += 32) {
-            uint32_t r[32];
-            tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c, r);
-            if (pix < p.P) {
+        // ---------------- epilogue: TMEM -> registers -> global (warps 0-3, TMEM lanes 32*warp .. +31) ----------------
+        uint32_t tc = 0;
+        for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x, tc++) {
+            int n, p0, o0;
+            decode(t, n, p0, o0);
+            const uint32_t as = tc & 1;
+            mbar_wait(smem_u32(&barAccFull[as]), (tc >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int pix = p0 + 32 * warp + lane;
+            float* yn = p.y + ((size_t)n * p.O) * (size_t)p.P;
+            for (int c = 0; c < p.BN; c += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + as * p.accCols + (uint32_t)c, r);
+                if (pix < p.P) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const int o = o0 + c + j;
-                    if (c + j < p.BN && o < p.O) yn[(size_t)o * p.P + pix] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; j++) {
+                        const int o = o0 + c + j;
+                        if (c + j < p.BN && o < p.O) yn[(size_t)o * p.P + pix] = __uint_as_float(r[j]);
+                    }
                 }
             }
+            // this warp's TMEM reads are done: hand the accumulator stage back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&barAccEmpty[as]));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -291,18 +324,19 @@ int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I
     p.tilesN = (O + bn - 1) / bn;
     p.tilesM = (int)((P + BM - 1) / BM);
     p.kTiles = (I + BK - 1) / BK;
+    p.accCols = (bn + 31) & ~31;
     int cols = 32;
-    while (cols < bn) cols <<= 1;
+    while (cols < 2 * p.accCols) cols <<= 1;                 // two accumulator stages, power-of-two allocation (<= 512)
     p.tmemCols = cols;
-    const long long ctas = (long long)N * p.tilesM * p.tilesN;
-    if (ctas > 0x7fffffffLL) return SG3_E_TOOLARGE;
+    p.totalTiles = (long long)N * p.tilesM * p.tilesN;
+    const long long ctas = p.totalTiles < sg3_sm_count() ? p.totalTiles : sg3_sm_count();   // persistent: one CTA per SM
 
     alignas(64) CUtensorMap mapX, mapW;
     if (!make_map3(&mapX, x, (uint64_t)P, (uint64_t)I, (uint64_t)N, (uint64_t)P * 4, (uint64_t)P * I * 4, 32, BK,
                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return SG3_E_NOKERNEL;
     if (!make_map3(&mapW, wmod, (uint64_t)ldw, (uint64_t)O, (uint64_t)N, (uint64_t)ldw * 4, (uint64_t)ldw * O * 4, BK, (uint32_t)bn)) return SG3_E_NOKERNEL;
 
-    p.stages = bn > 128 ? 4 : 3;                            // <= 113 KB per CTA keeps two CTAs per SM for narrow tiles
+    p.stages = bn > 128 ? 4 : 6;                            // 4 x 48 KB or 6 x <= 32 KB of operand stages
     const int smemBytes = p.stages * (A_STAGE_BYTES + bn * BK * 4) + 1024;
     static std::once_flag once;
     static cudaError_t attrErr = cudaSuccess;
