@@ -7,9 +7,11 @@
 // 64-bit addressing throughout).
 #include <cstring>
 
+#include "flrelu_bwd_stream.cuh"
 #include "flrelu_stream.cuh"
 
 namespace fs = flrelu_stream;
+namespace fb = flrelu_bwd_stream;
 
 SG3_EXPORT int sg3_filtered_lrelu_shape(int inH, int inW, int up, int down,
                                         int fuW, int fuH, int fdW, int fdH,
@@ -39,9 +41,20 @@ static bool is_pointwise(int up, int down, int fuW, int fuH, int fdW, int fdH)
     return up == 1 && down == 1 && fuW == 1 && fuH <= 1 && fdW == 1 && fdH <= 1;
 }
 
+// Shapes of flrelu_bwd_stream.cuh: up 2 with a dense (<= 12x12) up filter, or up 2 separable with down 4; separable down filter.
+static bool is_dense_up_shape(int up, int down, int fuW, int fuH, int fdW, int fdH)
+{
+    if (up != 2 || (down != 2 && down != 4) || fdH != 0 || fdW < 1 || fdW > 6 * down) return false;
+    if (fuW < 1 || fuW > fb::kUpTaps || fuH > fb::kUpTaps) return false;
+    return fuH != 0 || down == 4;          // separable up / down 2 belongs to the forward kernel
+}
+
+template <class T, int DOWN> int flrelu_bwd_launch(const fb::Params& p, int signMode, cudaStream_t stream);
+
 SG3_EXPORT int sg3_filtered_lrelu_supported(int up, int down, int fuW, int fuH, int fdW, int fdH)
 {
     if (is_pointwise(up, down, fuW, fuH, fdW, fdH)) return 0;
+    if (is_dense_up_shape(up, down, fuW, fuH, fdW, fdH)) return 0;
     if (down != 2 || (up != 2 && up != 4)) return SG3_E_NOKERNEL;
     if (fuH != 0 || fuW < 1 || fuW > fs::kTapsPerPhase * up) return SG3_E_NOKERNEL;      // separable up filter only
     if (fdW < 1 || fdW > fs::kDownTaps || fdH > fs::kDownTaps) return SG3_E_NOKERNEL;
@@ -93,6 +106,50 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
         const float su = d->fu ? (fuH == 0 ? d->fu[0] * d->fu[0] : d->fu[0]) : 1.0f;
         const float sd = d->fd ? (fdH == 0 ? d->fd[0] * d->fd[0] : d->fd[0]) : 1.0f;
         return sg3_flrelu_pointwise(d, su, sd, (cudaStream_t)stream);
+    }
+    if (is_dense_up_shape(d->up, d->down, fuW, fuH, fdW, fdH)) {
+        if (d->signMode == SG3_SIGNS_WRITE) return SG3_E_NOKERNEL;
+        if ((long long)d->inW * (d->xStride[3] < 0 ? -d->xStride[3] : d->xStride[3]) > 0x7fffffffLL) return SG3_E_NOKERNEL;
+        fb::Params q;
+        q.x = d->x; q.y = d->y; q.b = d->b; q.s = d->signs;
+        q.N = d->N; q.C = d->C; q.inH = d->inH; q.inW = d->inW; q.outH = d->outH; q.outW = d->outW;
+        for (int i = 0; i < 4; i++) { q.xs[i] = d->xStride[i]; q.ys[i] = d->yStride[i]; }
+        q.bs = d->bStride;
+        q.px0 = d->px0; q.py0 = d->py0;
+        q.slope = d->slope; q.clamp = d->clamp;
+        q.lreluA = 0.5f * (1.0f + d->slope); q.lreluB = 0.5f * (1.0f - d->slope);
+        q.sH = d->sH; q.sWb = d->sWb; q.sx = d->sx; q.sy = d->sy;
+        // correlation-ordered dense up taps FU'[a][b] (a separable filter is its outer product), scaled by up^2 * gain
+        auto fuAt = [&](int a, int b) -> float {
+            const int fh = fuH ? fuH : fuW;
+            if (a >= fh || b >= fuW) return 0.f;
+            const int sa = d->flip ? a : fh - 1 - a, sb = d->flip ? b : fuW - 1 - b;
+            return fuH ? d->fu[sa * fuW + sb] : d->fu[sa] * d->fu[sb];
+        };
+        for (int py = 0; py < 2; py++)
+            for (int px = 0; px < 2; px++)
+                for (int ka = 0; ka < 6; ka++)
+                    for (int kb = 0; kb < 6; kb++)
+                        q.tu[py][px][ka][kb] = 4.0f * d->gain * fuAt(py + 2 * ka, px + 2 * kb);
+        for (int t = 0; t < 24; t++) q.fd[t] = t < fdW ? (d->fd ? d->fd[d->flip ? t : fdW - 1 - t] : 1.0f) : 0.f;
+        const int tw = d->down == 2 ? fb::Geo<2>::TW : fb::Geo<4>::TW;
+        const long long planes = (long long)d->N * d->C;
+        q.stripsX = (d->outW + tw - 1) / tw;
+        const long long base = planes * q.stripsX;
+        const long long want = (long long)sg3_sm_count() * 16 * 3;
+        int chunks = 1;
+        if (base < want) {
+            chunks = (int)((want + base - 1) / base);
+            const int maxChunks = (d->outH + 31) / 32;
+            if (chunks > maxChunks) chunks = maxChunks;
+            if (chunks < 1) chunks = 1;
+        }
+        q.chunkRows = (d->outH + chunks - 1) / chunks;
+        q.chunksY = (d->outH + q.chunkRows - 1) / q.chunkRows;
+        q.totalStrips = base * q.chunksY;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (d->dtype == SG3_F32) return d->down == 2 ? flrelu_bwd_launch<float, 2>(q, d->signMode, st) : flrelu_bwd_launch<float, 4>(q, d->signMode, st);
+        return d->down == 2 ? flrelu_bwd_launch<__half, 2>(q, d->signMode, st) : flrelu_bwd_launch<__half, 4>(q, d->signMode, st);
     }
 
     fs::Params p;

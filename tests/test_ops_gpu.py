@@ -269,3 +269,71 @@ def test_fused_stream_full_size_properties(ops):
     # one plane against the oracle at full size
     ref = orc.filtered_lrelu(x[:, :1].cpu().numpy(), fu, fd, None, **kw)
     assert rel_err(y1[:, :1].cpu().numpy(), ref) < TOL32
+
+
+BWD_CASES = [
+    # name, up (forward), N, C, in, padding: forward = separable up -> dense radial down 2; backward = dense up 2 -> separable down `up`
+    ('R_same_148', 2, 1, 3, 148, [11, 10, 11, 10]),
+    ('R_up4_84', 4, 1, 2, 84, [-2, -5, -2, -5]),
+    ('R_same_odd', 2, 2, 2, 45, [10, 11, 9, 12]),
+    ('R_up4_odd', 4, 1, 3, 37, [3, 2, 1, 4]),
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('case', BWD_CASES, ids=[c[0] for c in BWD_CASES])
+def test_fused_dense_up_backward(ops, case, dtype):
+    """Backward of the config-R layers runs flrelu_bwd_stream (dense up 2 -> separable down 2 / 4, sign READ):
+    dx, db against the oracle's adjoint, and proof that both directions took a fused kernel."""
+    from oracle import sg3_oracle as orc
+    name, up, N, C, size, pad = case
+    fu, fd = _design(6 * up, True)
+    rng = np.random.RandomState(len(name) * 7)
+    x = (rng.randn(N, C, size, size + 4) * 3).astype(np.float32)
+    b = rng.randn(C).astype(np.float32)
+    if dtype == torch.float16:
+        x, b = x.astype(np.float16).astype(np.float32), b.astype(np.float16).astype(np.float32)
+    kw = dict(up=up, down=2, padding=pad, gain=np.sqrt(2), slope=0.2, clamp=6.0)
+    y_ref, signs = orc.filtered_lrelu(x, fu, fd, b, return_signs=True, **kw)
+    dy = rng.randn(*y_ref.shape).astype(np.float32)
+    if dtype == torch.float16:
+        dy = dy.astype(np.float16).astype(np.float32)
+    kwb = dict(kw)
+    kwb.pop('clamp')
+    dx_ref, db_ref = orc.filtered_lrelu_bwd(dy, signs, x.shape, fu, fd, **kwb)
+    xt, bt = cu(x, True, dtype=dtype), cu(b, True, dtype=dtype)
+    calls = []
+    orig = ops.filtered_lrelu._fused
+
+    def spy(*a, **k):
+        r = orig(*a, **k)
+        calls.append(r is not None)
+        return r
+    ops.filtered_lrelu._fused = spy
+    try:
+        y = ops.filtered_lrelu.filtered_lrelu(xt, cu(fu), cu(fd), bt, **kw)
+        dx, db = torch.autograd.grad(y, [xt, bt], cu(dy, dtype=dtype))
+    finally:
+        ops.filtered_lrelu._fused = orig
+    assert calls == [True, True], calls
+    tol = 5e-5 if dtype == torch.float32 else 4e-3     # fp16: the forward's fp16 rounding moves a few sign decisions
+    assert rel_err(dx.float().cpu().numpy(), dx_ref) < tol
+    assert rel_err(db.float().cpu().numpy(), db_ref) < (5e-5 if dtype == torch.float32 else 2e-2)
+
+
+def test_fused_dense_up_forward_and_sep_down4(ops):
+    """The same kernel family as a forward op: dense up 2 -> separable down 2, and separable up 2 -> down 4."""
+    from oracle import sg3_oracle as orc
+    fu12, fdR = _design(12, True)
+    fu24, _ = _design(24, True)
+    rng = np.random.RandomState(3)
+    x = (rng.randn(2, 3, 70, 66) * 2).astype(np.float32)
+    b = rng.randn(3).astype(np.float32)
+    fl = ops.filtered_lrelu
+    for fu, fd, down, pad in [(fdR, fu12, 2, [10, 11, 10, 11]), (fu12, fu24, 4, [7, 9, 12, 6]), (fdR, fu24, 4, [16, 15, 17, 14])]:
+        kw = dict(up=2, down=down, padding=pad, gain=1.3, slope=0.1, clamp=2.0, flip_filter=True)
+        ref = orc.filtered_lrelu(x, fu, fd, b, **kw)
+        cfg = (2, down) + tuple(pad) + (1.3, 0.1, 2.0, True)
+        res = fl._fused(cu(x), cu(fu), cu(fd), cu(b), None, 0, 0, cfg, False)
+        assert res is not None
+        assert rel_err(res[0].cpu().numpy(), ref) < TOL32
