@@ -203,18 +203,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                 v[q] = hi ? a2.y : a2.x;
             }
             if (MODE == SG3_SIGNS_READ) {
+                // the lane's 4 columns are 8 bits of the two sign bytes covering pixels 4*lane .. 4*lane+7 (byte-aligned base)
                 const int sY = Ys + 4 * g + j + p.sy;
+                const int signX0 = Xs - ex + p.sx;
+                const int byte0 = (signX0 >> 2) + lane;
+                unsigned lo = 0, hi = 0;
                 if (sY >= 0 && sY < p.sH) {
                     const uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
+                    if (byte0 >= 0 && byte0 < p.sWb) lo = __ldg(srow + byte0);
+                    if (byte0 + 1 >= 0 && byte0 + 1 < p.sWb) hi = __ldg(srow + byte0 + 1);
+                }
+                const unsigned bits = (lo | (hi << 8)) >> (2 * (signX0 & 3));
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int sX = Xg + q + p.sx;
-                        if (sX >= 0 && (sX >> 2) < p.sWb) {
-                            const unsigned code = (unsigned)__ldg(srow + (sX >> 2)) >> ((sX & 3) * 2);
-                            if (code & 1u) v[q] *= p.slope;
-                            if (code & 2u) v[q] = 0.f;
-                        }
-                    }
+                for (int q = 0; q < 4; q++) {
+                    const unsigned code = (bits >> (2 * q)) & 3u;
+                    if (code & 1u) v[q] *= p.slope;
+                    if (code & 2u) v[q] = 0.f;
                 }
             } else {
 #pragma unroll

@@ -334,6 +334,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     auto stageC = [&](int g, auto EYc) {
         constexpr int EY = decltype(EYc)::value;
         const float* win = sB + groupSlot * G::BW;       // 8 contiguous window rows (ring + mirrored tail)
+        // Sign READ: per row, lane l fetches the two sign bytes that cover pixels 4l .. 4l+7 of the strip's upsampled
+        // columns (byte-aligned base); any column pair's codes are then 4 bits of one lane's 16-bit window.
+        unsigned signWin[4] = {0u, 0u, 0u, 0u};
+        const int signX0 = Xs - ex + p.sx;               // sign-tensor x of upsampled column 0 of the strip
+        const int signOff = signX0 & 3;                  // pixel offset inside the first byte (arithmetic & also for negatives)
+        if (MODE == SG3_SIGNS_READ) {
+            const int byte0 = (signX0 >> 2) + lane;      // arithmetic shift: floor for negative coordinates
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int sY = Ys + 4 * g + j + p.sy;
+                unsigned lo = 0, hi = 0;
+                if (sY >= 0 && sY < p.sH) {
+                    const uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
+                    if (byte0 >= 0 && byte0 < p.sWb) lo = __ldg(srow + byte0);
+                    if (byte0 + 1 >= 0 && byte0 + 1 < p.sWb) hi = __ldg(srow + byte0 + 1);
+                }
+                signWin[j] = lo | (hi << 8);
+            }
+        }
 #pragma unroll
         for (int r = 0; r < 2; r++) {
             const int xp = 2 * (lane + 32 * r);
@@ -351,14 +370,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
 #pragma unroll
                 for (int k = 0; k < kTapsPerPhase; k++) u = ffma2(w[start + k], p.tv[ph][k], u);
                 unsigned rc0 = 0, rc1 = 0;
-                if (MODE == SG3_SIGNS_READ) {
-                    const int sY = Ys + 4 * g + j + p.sy;
-                    const int sX = Xs - ex + xp + p.sx;
-                    if (sY >= 0 && sY < p.sH) {
-                        const uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
-                        if (sX >= 0 && (sX >> 2) < p.sWb) rc0 = (unsigned)__ldg(srow + (sX >> 2)) >> ((sX & 3) * 2);
-                        if (sX + 1 >= 0 && ((sX + 1) >> 2) < p.sWb) rc1 = (unsigned)__ldg(srow + ((sX + 1) >> 2)) >> (((sX + 1) & 3) * 2);
-                    }
+                if (MODE == SG3_SIGNS_READ) {           // both columns' codes out of the row's sign window (see below)
+                    const int src = min((xp + signOff) >> 2, 31);      // lane 31's window also covers pixels 128..131
+                    const unsigned wbits = __shfl_sync(0xffffffffu, signWin[j], src);
+                    const unsigned four = wbits >> (2 * (xp + signOff - 4 * src));
+                    rc0 = four & 3u;
+                    rc1 = (four >> 2) & 3u;
                 }
                 v[j] = act2<MODE>(u, p, rc0, rc1, code0[j], code1[j]);
             }

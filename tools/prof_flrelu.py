@@ -20,3 +20,18 @@ ev[1].record(); torch.cuda.synchronize()
 ms = ev[0].elapsed_time(ev[1])
 byts = 4 * (x.numel() + y.numel())
 print(f'{sp["name"]} up{sp["up"]} N={N} C={C} {size}->{y.shape[-1]}: {ms:.3f} ms, {byts / ms / 1e6:.1f} GB/s, {y.numel() / ms / 1e6:.1f} Gpix/s out')
+if len(sys.argv) > 3 and sys.argv[3] == 'bwd':
+    xg = x.clone().requires_grad_(True)
+    for it in range(3):
+        y = sg3_b200.filtered_lrelu.filtered_lrelu(xg, fu, fd, b, up=sp['up'], down=sp['down'], padding=sp['padding'], clamp=256)
+        dy = torch.randn_like(y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        (dx,) = torch.autograd.grad(y, xg, dy)
+        e1.record(); torch.cuda.synchronize()
+    print(f'   backward (sign read): {e0.elapsed_time(e1):.3f} ms   forward with sign write: see below')
+    e0.record()
+    y = sg3_b200.filtered_lrelu.filtered_lrelu(xg, fu, fd, b, up=sp['up'], down=sp['down'], padding=sp['padding'], clamp=256)
+    e1.record(); torch.cuda.synchronize()
+    print(f'   forward (sign write): {e0.elapsed_time(e1):.3f} ms')
