@@ -65,9 +65,12 @@ def main():
     tgt = sharding.shard_batch(target, rank, world).to(dev)
 
     losses = []
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for step in range(args.steps):
+    warm = 2                               # untimed: allocator growth (cudaMalloc of GB-sized activations), lazy init
+    t0 = None
+    for step in range(args.steps + warm):
+        if step == warm:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
         bucket.zero()
         img = G.synthesis(ws, noise_mode='const', force_fp32=True)
         # per-rank partial of the global mean loss: sum over own frames / global frame count

@@ -145,7 +145,14 @@ int sg3_upfirdn2d(const void* x, void* y, const float* f,
  * ---------------------------------------------------------------------- */
 int sg3_modconv_weights(const float* w, const float* s, const float* input_gain, int gainMode,
                         float* wmod, float* scratch,
-                        int N, int I, int O, int k, int ldw, int demodulate, int round_tf32, void* stream);
+                        int N, int I, int O, int k, int ldw, int demodulate, int round_tf32, int transpose, void* stream);
+
+/* transpose != 0 (1x1 kernels): wmod is written as [N][I][ldw >= O], the weight operand of the input-gradient GEMM
+ * dX = sg3_modconv_fwd(dY, wmodT, ...) with the roles of I and O swapped.
+ *
+ * sg3_modconv_wgrad (1x1 kernels, TF32 tcgen05, split-K with fp32 atomics): dw[n][o][i] += sum_p dy[n][o][p] * x[n][i][p];
+ * dw [N][O][ldw] must be zeroed by the caller. */
+int sg3_modconv_wgrad(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, void* stream);
 
 int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
                     int N, int I, int O, int H, int W, int k, int pad, int ldw,

@@ -8,6 +8,7 @@
 // fp32 parity; the TF32 tcgen05/TMEM implicit GEMM (mathMode 1) lives in modconv_tc.cu.
 #include "common.cuh"
 
+int sg3_modconv_wgrad_tc(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, cudaStream_t stream);
 int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
                        cudaStream_t stream);
 
@@ -47,7 +48,7 @@ __device__ __forceinline__ float round_tf32(float v)
 __global__ void __launch_bounds__(256) modconv_weights_kernel(
     const float* __restrict__ w, const float* __restrict__ s, const float* __restrict__ gain, int gainMode,
     float* __restrict__ wmod, const float* __restrict__ scratch,
-    int N, int I, int O, int kk, int ldw, int demodulate, int roundTf32)
+    int N, int I, int O, int kk, int ldw, int demodulate, int roundTf32, int transpose)
 {
     __shared__ float red[32];
     const int o = blockIdx.x;
@@ -73,8 +74,11 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
             acc = block_sum(acc, red);
             d = rsqrtf(acc + 1e-8f);
         }
-        float* dst = wmod + ((size_t)n * O + o) * ldw;
-        for (int q = cnt + threadIdx.x; q < ldw; q += blockDim.x) dst[q] = 0.f;      // row padding (TMA pitch)
+        // transpose (1x1 kernels only): wmod is [N][I][ldw >= O], the operand layout of the dgrad GEMM
+        float* dst = transpose ? wmod + (size_t)n * I * ldw + o : wmod + ((size_t)n * O + o) * ldw;
+        const size_t dstStep = transpose ? (size_t)ldw : 1;
+        if (!transpose)
+            for (int q = cnt + threadIdx.x; q < ldw; q += blockDim.x) dst[q] = 0.f;   // row padding (TMA pitch)
         for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
             const int i = q / kk;
             float v = (wo[q] * rw) * (sn[i] * rs);
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
             if (gainMode == 1) v *= gain[0];
             else if (gainMode == 2) v *= gain[i];
             else if (gainMode == 3) v *= gain[(size_t)n * I + i];
-            dst[q] = roundTf32 ? round_tf32(v) : v;
+            dst[q * dstStep] = roundTf32 ? round_tf32(v) : v;
         }
     }
 }
@@ -164,16 +168,17 @@ __global__ void __launch_bounds__(256) modconv_fwd_simt_kernel(
 
 SG3_EXPORT int sg3_modconv_weights(const float* w, const float* s, const float* input_gain, int gainMode,
                                    float* wmod, float* scratch,
-                                   int N, int I, int O, int k, int ldw, int demodulate, int round_tf32_flag, void* stream)
+                                   int N, int I, int O, int k, int ldw, int demodulate, int round_tf32_flag, int transpose, void* stream)
 {
-    if (!w || !s || !wmod || !scratch || N < 1 || I < 1 || O < 1 || k < 1 || ldw < I * k * k) return SG3_E_INVALID;
+    if (!w || !s || !wmod || !scratch || N < 1 || I < 1 || O < 1 || k < 1) return SG3_E_INVALID;
+    if (transpose ? (k != 1 || ldw < O) : (ldw < I * k * k)) return SG3_E_INVALID;
     if (gainMode < 0 || gainMode > 3 || (gainMode && !input_gain)) return SG3_E_INVALID;
     if ((int64_t)N * I > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
     cudaStream_t st = (cudaStream_t)stream;
     if (demodulate) style_norm_kernel<<<1, 1024, 0, st>>>(s, N * I, scratch);
     int gy = N < 8 ? N : 8;
     modconv_weights_kernel<<<dim3((unsigned)O, (unsigned)gy), 256, 0, st>>>(w, s, input_gain, gainMode, wmod, scratch,
-                                                                            N, I, O, k * k, ldw, demodulate, round_tf32_flag);
+                                                                            N, I, O, k * k, ldw, demodulate, round_tf32_flag, transpose);
     return sg3_launch_status(demodulate ? 2 : 1);
 }
 
@@ -195,4 +200,10 @@ SG3_EXPORT int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
     unsigned grid = (unsigned)(total < cap ? total : cap);
     modconv_fwd_simt_kernel<<<grid, 256, 0, st>>>((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, OH, OW, ldw);
     return sg3_launch_status();
+}
+
+SG3_EXPORT int sg3_modconv_wgrad(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, void* stream)
+{
+    if (!dy || !x || !dw || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || ldw < I) return SG3_E_INVALID;
+    return sg3_modconv_wgrad_tc(dy, x, dw, N, I, O, H, W, ldw, (cudaStream_t)stream);
 }

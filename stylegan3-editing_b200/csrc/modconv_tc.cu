@@ -253,6 +253,110 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad of the 1x1 modulated conv:  dW[n][o][i] = sum_p dY[n][o][p] * X[n][i][p]   (per sample; networks_stylegan3.py:59-62
+// differentiated wrt the modulated weights).  D[M = 128 out-channels][N = BN in-channels] += A[M][K] * B[K][N] with both
+// operands K-major (pixels contiguous): A = dY tile, B = X tile, K = pixels, 32 per stage.  The pixel range is split across
+// CTAs (split-K); every CTA adds its partial tile into dW with fp32 atomics (dW is zeroed by the caller).
+struct WgParams {
+    float* dw;             // [N][O][ldw]
+    int N, I, O, P, ldw;
+    int BN, tmemCols;
+    int tilesO, tilesI, splits, kPerSplit;   // k-tiles (32 pixels) per split
+    int kTilesTotal;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+modconv_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX, const WgParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t barFull[kMaxStages], barEmpty[kMaxStages], barAccum;
+    __shared__ uint32_t tmemBase;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int stageBytes = A_STAGE_BYTES + p.BN * BK * 4;
+    const int stages = p.BN > 128 ? 4 : 6;
+    const uint32_t tiles = (smem_u32(smem) + 1023u) & ~1023u;
+
+    long long t = blockIdx.x;
+    const int sp = (int)(t % p.splits); t /= p.splits;
+    const int ti = (int)(t % p.tilesI); t /= p.tilesI;
+    const int to = (int)(t % p.tilesO);
+    const int n = (int)(t / p.tilesO);
+    const int o0 = to * BM, i0 = ti * p.BN;
+    const int kt0 = sp * p.kPerSplit;
+    const int kt1 = min(kt0 + p.kPerSplit, p.kTilesTotal);
+    const int nk = kt1 - kt0;                                // >= 1 by construction
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMaxStages; s++) { mbar_init(smem_u32(&barFull[s]), 1); mbar_init(smem_u32(&barEmpty[s]), 1); }
+        mbar_init(smem_u32(&barAccum), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmemBase)), "r"((uint32_t)p.tmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmemBase;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int it = 0; it < nk; it++) {
+                const int s = it % stages, round = it / stages;
+                if (round > 0) mbar_wait(smem_u32(&barEmpty[s]), (round - 1) & 1);
+                const uint32_t full = smem_u32(&barFull[s]);
+                mbar_expect_tx(full, (uint32_t)stageBytes);
+                const uint32_t aDst = tiles + s * stageBytes;
+                tma_load_3d(aDst, &mapDY, full, (kt0 + it) * BK, o0, n);                    // [128 o][32 px]
+                tma_load_3d(aDst + A_STAGE_BYTES, &mapX, full, (kt0 + it) * BK, i0, n);     // [BN i][32 px]
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            // D=F32, A=B=TF32, both K-major, N = BN, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int it = 0; it < nk; it++) {
+                const int s = it % stages;
+                mbar_wait(smem_u32(&barFull[s]), (it / stages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t aBase = tiles + s * stageBytes, bBase = aBase + A_STAGE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ks++) {
+                    const uint64_t da = umma_desc(aBase + ks * 32, 16, 1024);
+                    const uint64_t db = umma_desc(bBase + ks * 32, 16, 1024);
+                    umma_tf32(tmem, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&barEmpty[s]));
+            }
+            umma_commit(smem_u32(&barAccum));
+        }
+    } else {
+        mbar_wait(smem_u32(&barAccum), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int o = o0 + 32 * warp + lane;
+        float* row = p.dw + ((size_t)n * p.O + (size_t)(o < p.O ? o : 0)) * p.ldw;
+        for (int c = 0; c < p.BN; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c, r);
+            if (o < p.O) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int i = i0 + c + j;
+                    if (c + j < p.BN && i < p.I) atomicAdd(row + i, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmemCols) : "memory");
+    }
+}
+
 // ---- host: tensor maps through the driver entry point (no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -343,5 +447,47 @@ int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I
     std::call_once(once, [] { attrErr = cudaFuncSetAttribute(modconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     if (attrErr != cudaSuccess) return (int)attrErr;
     modconv_tc_kernel<<<(unsigned)ctas, kThreads, smemBytes, stream>>>(mapX, mapW, p);
+    return sg3_launch_status();
+}
+
+// dy [N][O][P], x [N][I][P], dw [N][O][ldw] (zeroed by the caller; ldw >= I).
+int sg3_modconv_wgrad_tc(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, cudaStream_t stream)
+{
+    const long long P = (long long)H * W;
+    if (P % 4 != 0 || P > INT32_MAX) return SG3_E_NOKERNEL;
+    if (((uintptr_t)x & 15) || ((uintptr_t)dy & 15)) return SG3_E_NOKERNEL;
+    WgParams p;
+    p.dw = dw; p.N = N; p.I = I; p.O = O; p.P = (int)P; p.ldw = ldw;
+    const int nt = (I + 255) / 256;
+    int bn = ((I + nt - 1) / nt + 15) & ~15;
+    if (bn < 16) bn = 16;
+    p.BN = bn;
+    p.tilesI = (I + bn - 1) / bn;
+    p.tilesO = (O + BM - 1) / BM;
+    int cols = 32;
+    while (cols < bn) cols <<= 1;
+    p.tmemCols = cols;
+    p.kTilesTotal = (int)((P + BK - 1) / BK);
+    // split the pixel range so that a few waves of CTAs exist; at least 8 k-tiles per CTA
+    const long long baseTiles = (long long)N * p.tilesO * p.tilesI;
+    long long splits = ((long long)sg3_sm_count() * 2 + baseTiles - 1) / baseTiles;
+    const long long maxSplits = (p.kTilesTotal + 7) / 8;
+    if (splits > maxSplits) splits = maxSplits;
+    if (splits < 1) splits = 1;
+    p.kPerSplit = (int)((p.kTilesTotal + splits - 1) / splits);
+    p.splits = (p.kTilesTotal + p.kPerSplit - 1) / p.kPerSplit;
+    const long long ctas = baseTiles * p.splits;
+    if (ctas > 0x7fffffffLL) return SG3_E_TOOLARGE;
+
+    alignas(64) CUtensorMap mapDY, mapX;
+    if (!make_map3(&mapDY, dy, (uint64_t)P, (uint64_t)O, (uint64_t)N, (uint64_t)P * 4, (uint64_t)P * O * 4, BK, BM)) return SG3_E_NOKERNEL;
+    if (!make_map3(&mapX, x, (uint64_t)P, (uint64_t)I, (uint64_t)N, (uint64_t)P * 4, (uint64_t)P * I * 4, BK, (uint32_t)bn)) return SG3_E_NOKERNEL;
+    const int stages = bn > 128 ? 4 : 6;
+    const int smemBytes = stages * (A_STAGE_BYTES + bn * BK * 4) + 1024;
+    static std::once_flag once;
+    static cudaError_t attrErr = cudaSuccess;
+    std::call_once(once, [] { attrErr = cudaFuncSetAttribute(modconv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    if (attrErr != cudaSuccess) return (int)attrErr;
+    modconv_wgrad_kernel<<<(unsigned)ctas, kThreads, smemBytes, stream>>>(mapDY, mapX, p);
     return sg3_launch_status();
 }

@@ -28,8 +28,9 @@ def _math_mode():
     return 'tf32' if torch.backends.cudnn.allow_tf32 else 'fp32'
 
 
-def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False):
-    """[N, O, ldw >= I*k*k] float32 modulated (+demodulated, +input-gain) weights, rows zero padded  (:39-56)."""
+def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, transpose=False):
+    """[N, O, ldw >= I*k*k] float32 modulated (+demodulated, +input-gain) weights, rows zero padded  (:39-56).
+    transpose=True (1x1 only): [N, I, ldw >= O], the weight operand of the input-gradient GEMM."""
     capi.require_cuda(w, 'modulated_conv2d')
     O, I, kh, kw = w.shape
     assert kh == kw
@@ -45,13 +46,18 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False):
             mode, g = 2, g.contiguous()                            # per input channel
         else:
             mode, g = 3, g.expand(N, I).contiguous()               # per (sample, input channel), broadcast like :55
-    ldw = (I * kh * kw + 31) // 32 * 32            # row pitch: 128-byte multiple for the TMA-fed tensor-core path
-    wmod = torch.empty([N, O, ldw], dtype=torch.float32, device=w.device)
+    if transpose:
+        assert kh == 1
+        ldw = (O + 31) // 32 * 32
+        wmod = torch.zeros([N, I, ldw], dtype=torch.float32, device=w.device)      # padding columns must be zero
+    else:
+        ldw = (I * kh * kw + 31) // 32 * 32        # row pitch: 128-byte multiple for the TMA-fed tensor-core path
+        wmod = torch.empty([N, O, ldw], dtype=torch.float32, device=w.device)
     scratch = torch.empty([1], dtype=torch.float32, device=w.device)
     with torch.cuda.device(w.device):
         rc = capi.lib().sg3_modconv_weights(w.data_ptr(), s.data_ptr(), g.data_ptr() if g is not None else None, mode,
                                             wmod.data_ptr(), scratch.data_ptr(), N, I, O, kh, ldw, int(bool(demodulate)),
-                                            int(bool(round_tf32)), capi.stream_ptr(w.device))
+                                            int(bool(round_tf32)), int(bool(transpose)), capi.stream_ptr(w.device))
     capi.check(rc, 'sg3_modconv_weights')
     return wmod
 
@@ -90,9 +96,9 @@ def _reference_formula(x, w, s, demodulate, padding, input_gain):
 
 
 class _ModConv(torch.autograd.Function):
-    """Forward on the sm_100a kernels.  Backward (PTI / fine-tuning) currently differentiates the
-    reference expression with library convolutions (cuDNN dgrad/wgrad); native dgrad/wgrad kernels are
-    the next step and do not change this interface."""
+    """Forward on the sm_100a kernels.  Backward (PTI / fine-tuning): 1x1 kernels with TF32 math run native
+    tcgen05 dgrad / wgrad GEMMs (`_native_backward_1x1`); 3x3 kernels, exact-fp32 mode and higher-order
+    gradients differentiate the reference expression with library convolutions."""
 
     @staticmethod
     def forward(ctx, x, w, s, input_gain, demodulate, padding, math):
@@ -111,6 +117,10 @@ class _ModConv(torch.autograd.Function):
         demodulate, padding, math = ctx.cfg
         need = ctx.needs_input_grad[:3]
         higher_order = torch.is_grad_enabled()
+        if (math == 'tf32' and w.shape[-1] == 1 and padding == 0 and not higher_order
+                and x.dtype == torch.float32 and dy.dtype == torch.float32
+                and (x.shape[2] * x.shape[3]) % 4 == 0):        # TMA needs 16-byte aligned plane pitches
+            return _native_backward_1x1(x, w, s, input_gain, dy, demodulate, need) + (None, None, None, None)
         with torch.enable_grad(), torch.backends.cudnn.flags(allow_tf32=(math == 'tf32')):
             xs = x.detach().requires_grad_(need[0])
             ws = w.detach().requires_grad_(need[1])
@@ -120,6 +130,53 @@ class _ModConv(torch.autograd.Function):
             grads = list(torch.autograd.grad(y, ins, dy, create_graph=higher_order)) if ins else []
         out = [grads.pop(0) if n else None for n in need]
         return out[0], out[1], out[2], None, None, None, None
+
+
+def _native_backward_1x1(x, w, s, input_gain, dy, demodulate, need):
+    """dx, dw, ds of the 1x1 modulated conv on the tcgen05 kernels (TF32): dgrad = the forward GEMM with the
+    transposed modulated weights; wgrad = split-K GEMM over pixels; then the chain rule through the weight
+    prologue (networks_stylegan3.py:39-56) on the small [N, O, I] tensors."""
+    N, I, H, W = x.shape
+    O = w.shape[0]
+    dy = dy.contiguous()
+    xc = x.contiguous()
+    dx = dw = ds = None
+    if need[0]:
+        wT = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, round_tf32=True, transpose=True)
+        dx = conv_forward(dy, wT, I, 1, 0, 'tf32')
+    if need[1] or need[2]:
+        ldw = (I + 31) // 32 * 32
+        dWn = torch.zeros([N, O, ldw], dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = capi.lib().sg3_modconv_wgrad(dy.data_ptr(), xc.data_ptr(), dWn.data_ptr(), N, I, O, H, W, ldw,
+                                              capi.stream_ptr(x.device))
+        capi.check(rc, 'sg3_modconv_wgrad')
+        dW = dWn[:, :, :I]                                             # grad wrt the final per-sample weights [N, O, I]
+        w2 = w.detach().reshape(O, I).float()
+        s2 = s.detach().float()
+        if input_gain is not None:
+            g = input_gain.detach().float()
+            g = g.reshape(1, 1) if g.numel() == 1 else (g.reshape(1, I) if g.ndim == 1 else g.expand(N, I))
+            dW = dW * g.unsqueeze(1)
+        if demodulate:
+            rw = w2.square().mean(dim=1, keepdim=True).rsqrt()          # [O, 1]
+            rs = s2.square().mean().rsqrt()
+            wn, sn = w2 * rw, s2 * rs
+            Wm = wn.unsqueeze(0) * sn.unsqueeze(1)                       # [N, O, I]
+            q = Wm.square().sum(dim=2) + 1e-8                            # [N, O]
+            d = q.rsqrt()
+            dd = (dW * Wm).sum(dim=2)
+            dWm = dW * d.unsqueeze(2) - Wm * (dd * q.pow(-1.5)).unsqueeze(2)
+            dwn = (dWm * sn.unsqueeze(1)).sum(dim=0)                     # [O, I]
+            dsn = (dWm * wn.unsqueeze(0)).sum(dim=1)                     # [N, I]
+            dw = rw * dwn - w2 * rw.pow(3) * (dwn * w2).sum(dim=1, keepdim=True) / I
+            ds = rs * dsn - s2 * rs.pow(3) * (dsn * s2).sum() / (N * I)
+        else:
+            dw = (dW * s2.unsqueeze(1)).sum(dim=0)
+            ds = (dW * w2.unsqueeze(0)).sum(dim=1)
+        dw = dw.reshape(w.shape).to(w.dtype) if need[1] else None
+        ds = ds.to(s.dtype) if need[2] else None
+    return dx, dw, ds
 
 
 def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None, math=None):
