@@ -147,12 +147,20 @@ int sg3_modconv_weights(const float* w, const float* s, const float* input_gain,
                         float* wmod, float* scratch,
                         int N, int I, int O, int k, int ldw, int demodulate, int round_tf32, int transpose, void* stream);
 
-/* transpose != 0 (1x1 kernels): wmod is written as [N][I][ldw >= O], the weight operand of the input-gradient GEMM
- * dX = sg3_modconv_fwd(dY, wmodT, ...) with the roles of I and O swapped.
+/* Weight layouts (`transpose` argument): 0 = [N][O][ldw >= I*k*k] (index i*k*k + tap), read by mathMode 0 and by the
+ * 1x1 tensor-core kernel;  1 (1x1 kernels) = transposed [N][I][ldw >= O], the weight operand of the input-gradient GEMM
+ * dX = sg3_modconv_fwd(dY, wmodT, ...) with the roles of I and O swapped;  2 = tap-major [N][k*k][O][ldw >= I]
+ * (tap = ky*k + kx, i contiguous), the operand sg3_modconv_fwd reads when mathMode = 1 and k > 1.
+ *
+ * sg3_modconv_tc_supported: 0 if sg3_modconv_fwd(mathMode = 1) has a tensor-core kernel for this shape
+ * (k = 1: pad 0, H*W % 4 == 0;  k = 3: pad 0 or 2, W % 4 == 0), SG3_E_NOKERNEL otherwise -- ask before choosing the
+ * weight layout.
  *
  * sg3_modconv_wgrad (1x1 kernels, TF32 tcgen05, split-K with fp32 atomics): dw[n][o][i] += sum_p dy[n][o][p] * x[n][i][p];
  * dw [N][O][ldw] must be zeroed by the caller. */
 int sg3_modconv_wgrad(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, void* stream);
+
+int sg3_modconv_tc_supported(int I, int O, int H, int W, int k, int pad);
 
 int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
                     int N, int I, int O, int H, int W, int k, int pad, int ldw,

@@ -9,6 +9,8 @@
 #include "common.cuh"
 
 int sg3_modconv_wgrad_tc(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, cudaStream_t stream);
+int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw, cudaStream_t stream);
+int sg3_modconv_tc3_supported(int I, int O, int H, int W, int k, int pad);
 int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
                        cudaStream_t stream);
 
@@ -74,10 +76,14 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
             acc = block_sum(acc, red);
             d = rsqrtf(acc + 1e-8f);
         }
-        // transpose (1x1 kernels only): wmod is [N][I][ldw >= O], the operand layout of the dgrad GEMM
-        float* dst = transpose ? wmod + (size_t)n * I * ldw + o : wmod + ((size_t)n * O + o) * ldw;
-        const size_t dstStep = transpose ? (size_t)ldw : 1;
-        if (!transpose)
+        // layout 1 (1x1 kernels only): transposed, wmod is [N][I][ldw >= O], the operand of the dgrad GEMM
+        // layout 2: tap-major, wmod is [N][kk][O][ldw >= I], the operand of the 3x3 tensor-core kernel
+        float* dst = transpose == 1 ? wmod + (size_t)n * I * ldw + o
+                   : transpose == 2 ? wmod + ((size_t)n * kk * O + o) * ldw
+                                    : wmod + ((size_t)n * O + o) * ldw;
+        const size_t dstStep = transpose == 1 ? (size_t)ldw : 1;
+        const size_t tapStep = (size_t)O * ldw;
+        if (transpose == 0)
             for (int q = cnt + threadIdx.x; q < ldw; q += blockDim.x) dst[q] = 0.f;   // row padding (TMA pitch)
         for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
             const int i = q / kk;
@@ -86,7 +92,9 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
             if (gainMode == 1) v *= gain[0];
             else if (gainMode == 2) v *= gain[i];
             else if (gainMode == 3) v *= gain[(size_t)n * I + i];
-            dst[q * dstStep] = roundTf32 ? round_tf32(v) : v;
+            v = roundTf32 ? round_tf32(v) : v;
+            if (transpose == 2) dst[(size_t)(q - i * kk) * tapStep + i] = v;
+            else dst[q * dstStep] = v;
         }
     }
 }
@@ -171,7 +179,8 @@ SG3_EXPORT int sg3_modconv_weights(const float* w, const float* s, const float* 
                                    int N, int I, int O, int k, int ldw, int demodulate, int round_tf32_flag, int transpose, void* stream)
 {
     if (!w || !s || !wmod || !scratch || N < 1 || I < 1 || O < 1 || k < 1) return SG3_E_INVALID;
-    if (transpose ? (k != 1 || ldw < O) : (ldw < I * k * k)) return SG3_E_INVALID;
+    if (transpose < 0 || transpose > 2) return SG3_E_INVALID;
+    if (transpose == 1 ? (k != 1 || ldw < O) : transpose == 2 ? (ldw < I) : (ldw < I * k * k)) return SG3_E_INVALID;
     if (gainMode < 0 || gainMode > 3 || (gainMode && !input_gain)) return SG3_E_INVALID;
     if ((int64_t)N * I > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -186,12 +195,15 @@ SG3_EXPORT int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
                                int N, int I, int O, int H, int W, int k, int pad, int ldw,
                                int mathMode, int dtype, void* stream)
 {
-    if (!x || !wmod || !y || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || k < 1 || pad < 0 || ldw < I * k * k) return SG3_E_INVALID;
+    if (!x || !wmod || !y || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || k < 1 || pad < 0) return SG3_E_INVALID;
+    const bool tapMajor = mathMode == 1 && k > 1;             // the tensor-core kernels for k > 1 read tap-major weights
+    if (ldw < (tapMajor ? I : I * k * k)) return SG3_E_INVALID;
     if (dtype != SG3_F32) return SG3_E_NOKERNEL;
     const int OH = H + 2 * pad - k + 1, OW = W + 2 * pad - k + 1;
     if (OH < 1 || OW < 1) return SG3_E_INVALID;
     if ((int64_t)OH * OW > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
     cudaStream_t st = (cudaStream_t)stream;
+    if (mathMode == 1 && k == 3) return sg3_modconv_fwd_tc3((const float*)x, wmod, (float*)y, N, I, O, H, W, pad, ldw, st);
     if (mathMode == 1) return sg3_modconv_fwd_tc((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, ldw, st);
     if (mathMode != 0) return SG3_E_INVALID;
     const int P = OH * OW;
@@ -200,6 +212,13 @@ SG3_EXPORT int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
     unsigned grid = (unsigned)(total < cap ? total : cap);
     modconv_fwd_simt_kernel<<<grid, 256, 0, st>>>((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, OH, OW, ldw);
     return sg3_launch_status();
+}
+
+SG3_EXPORT int sg3_modconv_tc_supported(int I, int O, int H, int W, int k, int pad)
+{
+    if (I < 1 || O < 1 || H < 1 || W < 1 || k < 1 || pad < 0) return SG3_E_INVALID;
+    if (k == 1) return (pad == 0 && ((int64_t)H * W) % 4 == 0) ? 0 : SG3_E_NOKERNEL;
+    return sg3_modconv_tc3_supported(I, O, H, W, k, pad);
 }
 
 SG3_EXPORT int sg3_modconv_wgrad(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, void* stream)

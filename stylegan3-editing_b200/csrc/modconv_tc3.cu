@@ -1,0 +1,309 @@
+// modconv_tc3.cu -- TF32 tcgen05/TMEM implicit GEMM for the 3x3 modulated conv (StyleGAN3 config T; the grouped cuDNN
+// convolution of networks_stylegan3.py:59-62 with conv_kernel = 3, padding = 2; padding = 0 serves dgrad-style use).
+//
+//   y[n][o][oy][ox] = sum_i sum_ky sum_kx  Wn[ky][kx][o][i] * x[n][i][oy + ky - pad][ox + kx - pad]
+//
+// Activations are NCHW fp32, so the pixel axis is the contiguous one and a one-pixel shift of an operand is neither a
+// legal TMA box start (16-byte granularity) nor a legal UMMA descriptor start.  The shifts are therefore taken on the
+// ACCUMULATOR side:
+//   D[M = 128 out-channels][N = NPX pixels] += A[M][K] * B[K][N]
+//   A = Wn[tap] : K-major  [128 o][32 i]  SWIZZLE_128B, one 16 KB TMA box per (tap, 32-channel chunk)
+//   B = x row   : N-major  [32 i][NPX px] SWIZZLE_128B_ATOM_32B, NPX/32 TMA boxes of [32 i][32 px]; the box start is
+//                 4-pixel aligned, rows/columns outside the image are zero-filled by TMA (that IS the conv padding)
+//   D in TMEM   : lane = out-channel, column = pixel.  The product of input column j with tap kx belongs to output column
+//                 j + 2 - kx, so the MMA of tap kx simply accumulates at a column offset of the TMEM address.
+//                 Measured (tools/tc3_probe.cu): the offset must be EVEN, so kx = 0 and kx = 2 share one accumulator
+//                 (offsets 2 and 0) and kx = 1 gets a second one; the epilogue adds them, one register apart.
+//   ky          : input row oy + ky - pad; a tile holds R output rows and R + 2 input rows per channel chunk in smem,
+//                 every input row feeds up to three output-row accumulators.
+// One X row group therefore serves 9 * R MMAs of K = 32, and the weights of a (tap, chunk) are used for R * (NPX - 4)
+// output pixels.  Epilogue: tcgen05.ld (thread = channel) -> even/odd add -> 32x32 transpose through padded smem ->
+// stores with lanes along x (128-byte lines).
+//
+// Warp roles (192 threads): warps 0-3 epilogue, warp 4 TMA producer (two rings: X row groups, W taps), warp 5 TMEM
+// allocator + MMA issuer.  Persistent over tiles; the accumulator is double-buffered when it fits in 512 columns.
+// Every mbarrier wait is bounded (trap instead of hang).
+#include <cuda.h>
+#include <mutex>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+bool sg3_make_tensor_map(CUtensorMap* m, CUtensorMapDataType type, int rank, const void* base, const uint64_t* dims,
+                         const uint64_t* stridesBytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
+namespace {
+
+constexpr int BK3 = 32;                 // input channels per chunk
+constexpr int W_SLOT_BYTES = 128 * BK3 * 4;   // one tap of one chunk: [128 o][32 i] fp32
+constexpr int kMaxWSlots = 9;
+constexpr int kThreads3 = 192;
+constexpr int STAGE_PITCH = 33;         // transpose staging: [32 channels][33]
+constexpr int kAccPitchAlign = 32;      // accumulator pitch granularity in TMEM columns (tcgen05.ld.x32 start columns)
+
+struct Tc3Params {
+    float* y;
+    int N, I, O, H, W, OH, OW, pad;
+    int NPX, R, CW;            // pixels per MMA (multiple of 32), output rows per tile, accumulator pitch (>= NPX + 4)
+    int S;                     // valid output columns per tile = NPX - 4
+    int xoff, colBase;         // box start = tileX * S - xoff;  output ox = tileX * S + (col - colBase)
+    int accStages, accStageCols, tmemCols;
+    int tilesX, tilesY, tilesO, kChunks;
+    int wSlots, xGroupBytes;
+    long long totalTiles;
+};
+
+__global__ void __launch_bounds__(kThreads3, 1)
+modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const Tc3Params p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    __shared__ __align__(8) uint64_t barWFull[kMaxWSlots], barWEmpty[kMaxWSlots], barXFull[2], barXEmpty[2], barAccFull[2], barAccEmpty[2];
+    __shared__ uint32_t tmemBase;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
+    const uint32_t xRing = base;                                        // 2 groups of (R + 2) rows x NPX px x 32 ch
+    const uint32_t wRing = base + 2u * (uint32_t)p.xGroupBytes;        // wSlots x 16 KB (1024-aligned: xGroupBytes % 4096 == 0)
+    float* stage = reinterpret_cast<float*>(smem + (wRing + (uint32_t)p.wSlots * W_SLOT_BYTES - smem_u32(smem)));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kMaxWSlots; s++) { mbar_init(smem_u32(&barWFull[s]), 1); mbar_init(smem_u32(&barWEmpty[s]), 1); }
+        for (int a = 0; a < 2; a++) {
+            mbar_init(smem_u32(&barXFull[a]), 1); mbar_init(smem_u32(&barXEmpty[a]), 1);
+            mbar_init(smem_u32(&barAccFull[a]), 1); mbar_init(smem_u32(&barAccEmpty[a]), 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmemBase)), "r"((uint32_t)p.tmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmemBase;
+
+    // tile -> (sample, row block, column block, channel block); channel block fastest: the CTAs running together share x in L2
+    auto decode = [&](long long t, int& n, int& oy0, int& tx, int& o0) {
+        const int to = (int)(t % p.tilesO); t /= p.tilesO;
+        tx = (int)(t % p.tilesX); t /= p.tilesX;
+        const int ty = (int)(t % p.tilesY);
+        n = (int)(t / p.tilesY);
+        oy0 = ty * p.R;
+        o0 = to * 128;
+    };
+    const int boxesPerRow = p.NPX >> 5;
+    const uint32_t rowBytes = (uint32_t)p.NPX * 128u;                  // [32 ch][NPX px] of one input row
+
+    if (warp == 4) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            uint32_t xIt = 0, wIt = 0;
+            for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x) {
+                int n, oy0, tx, o0;
+                decode(t, n, oy0, tx, o0);
+                const int xs = tx * p.S - p.xoff;
+                for (int c = 0; c < p.kChunks; c++, xIt++) {
+                    const uint32_t xg = xIt & 1;
+                    if (xIt >= 2) mbar_wait(smem_u32(&barXEmpty[xg]), ((xIt >> 1) - 1) & 1);
+                    const uint32_t xfull = smem_u32(&barXFull[xg]);
+                    mbar_expect_tx(xfull, (uint32_t)p.xGroupBytes);
+                    const uint32_t xDst = xRing + xg * (uint32_t)p.xGroupBytes;
+                    for (int rr = 0; rr < p.R + 2; rr++)
+                        for (int j = 0; j < boxesPerRow; j++)
+                            tma_load_4d(xDst + rr * rowBytes + j * 4096u, &mapX, xfull, xs + 32 * j, oy0 - p.pad + rr, c * BK3, n);
+                    for (int tap = 0; tap < 9; tap++, wIt++) {
+                        const uint32_t ws = wIt % (uint32_t)p.wSlots, round = wIt / (uint32_t)p.wSlots;
+                        if (round > 0) mbar_wait(smem_u32(&barWEmpty[ws]), (round - 1) & 1);
+                        const uint32_t wfull = smem_u32(&barWFull[ws]);
+                        mbar_expect_tx(wfull, (uint32_t)W_SLOT_BYTES);
+                        tma_load_4d(wRing + ws * W_SLOT_BYTES, &mapW, wfull, c * BK3, o0, tap, n);
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0) {
+            // D = F32, A = B = TF32, A K-major (bit 15 = 0), B MN-major (bit 16 = 1), N = NPX, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
+                                   ((uint32_t)(p.NPX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            uint32_t xIt = 0, wIt = 0, tc = 0;
+            for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x, tc++) {
+                const uint32_t as = p.accStages == 2 ? (tc & 1) : 0, use = p.accStages == 2 ? (tc >> 1) : tc;
+                if (use > 0) mbar_wait(smem_u32(&barAccEmpty[as]), (use - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem + as * (uint32_t)p.accStageCols;
+                for (int c = 0; c < p.kChunks; c++, xIt++) {
+                    const uint32_t xg = xIt & 1;
+                    mbar_wait(smem_u32(&barXFull[xg]), (xIt >> 1) & 1);
+                    const uint32_t xBase = xRing + xg * (uint32_t)p.xGroupBytes;
+                    for (int tap = 0; tap < 9; tap++, wIt++) {
+                        const int ky = tap / 3, kx = tap - 3 * ky;
+                        const uint32_t ws = wIt % (uint32_t)p.wSlots;
+                        mbar_wait(smem_u32(&barWFull[ws]), (wIt / (uint32_t)p.wSlots) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t aBase = wRing + ws * W_SLOT_BYTES;
+                        const uint32_t first = (c == 0 && ky == 0 && kx < 2) ? 0u : 1u;    // first touch of an accumulator
+                        for (int oyl = 0; oyl < p.R; oyl++) {
+                            const uint32_t bBase = xBase + (uint32_t)(oyl + ky) * rowBytes;
+                            const uint32_t d = acc + (uint32_t)((2 * oyl + (kx & 1)) * p.CW + (kx == 0 ? 2 : 0));
+#pragma unroll
+                            for (int ks = 0; ks < BK3 / 8; ks++) {
+                                const uint64_t da = umma_desc(aBase + ks * 32, 16, 1024);
+                                const uint64_t db = umma_desc(bBase + ks * 1024, BK3 * 128, 512, kLayoutSw128Base32);
+                                umma_tf32(d, da, db, idesc, ks > 0 ? 1u : first);
+                            }
+                        }
+                        umma_commit(smem_u32(&barWEmpty[ws]));
+                    }
+                    umma_commit(smem_u32(&barXEmpty[xg]));
+                }
+                umma_commit(smem_u32(&barAccFull[as]));
+            }
+        }
+    } else {
+        // ---------------- epilogue: TMEM -> registers -> transpose in smem -> global (warps 0-3) ----------------
+        float* st = stage + warp * (32 * STAGE_PITCH);
+        uint32_t tc = 0;
+        for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x, tc++) {
+            int n, oy0, tx, o0;
+            decode(t, n, oy0, tx, o0);
+            const uint32_t as = p.accStages == 2 ? (tc & 1) : 0, use = p.accStages == 2 ? (tc >> 1) : tc;
+            mbar_wait(smem_u32(&barAccFull[as]), use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem + ((uint32_t)(32 * warp) << 16) + as * (uint32_t)p.accStageCols;
+            const int oBase = o0 + 32 * warp;
+            const int colEnd = p.colBase + p.S;
+            for (int oyl = 0; oyl < p.R; oyl++) {
+                const int oy = oy0 + oyl;
+                if (oy >= p.OH) break;
+                float carry = 0.f;
+                for (int c0 = 0; c0 < colEnd; c0 += 32) {
+                    uint32_t e[32], o[32];
+                    tmem_ld32(acc + (uint32_t)((2 * oyl) * p.CW + c0), e);
+                    tmem_ld32(acc + (uint32_t)((2 * oyl + 1) * p.CW + c0), o);
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const float prev = j == 0 ? carry : __uint_as_float(o[j - 1]);
+                        st[lane * STAGE_PITCH + j] = __uint_as_float(e[j]) + prev;
+                    }
+                    carry = __uint_as_float(o[31]);
+                    __syncwarp();
+                    const int col = c0 + lane;
+                    const int ox = tx * p.S + col - p.colBase;
+                    const bool okx = col >= p.colBase && col < colEnd && ox < p.OW;
+                    float* yrow = p.y + (((size_t)n * p.O + oBase) * p.OH + oy) * (size_t)p.OW + ox;
+                    const size_t chStep = (size_t)p.OH * p.OW;
+#pragma unroll 8
+                    for (int ch = 0; ch < 32; ch++)
+                        if (okx && oBase + ch < p.O) yrow[ch * chStep] = st[ch * STAGE_PITCH + lane];
+                    __syncwarp();
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&barAccEmpty[as]));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmemCols) : "memory");
+    }
+}
+
+constexpr int kSmemLimit3 = 224 * 1024;       // + 2 KB of static barriers stays under the 227 KB per-CTA limit
+
+// Pick (NPX, R, accumulator stages, W slots) for a layer: minimise an estimate of the per-layer time
+// max(MMA clocks, operand bytes / 40 B/clk) over the tile shapes that fit TMEM (512 columns) and shared memory.
+bool plan_tc3(Tc3Params& p)
+{
+    double best = 1e300;
+    bool found = false;
+    const int wantStages = p.kChunks <= 4 ? 2 : 1;        // short K loops: overlap the epilogue with the next tile
+    for (int pass = 0; pass < 2 && !found; pass++) {
+        const int accStages = pass == 0 ? wantStages : 1;
+        for (int npx = 64; npx <= 224; npx += 32) {
+            for (int r = 1; r <= 4; r++) {
+                const int cw = (npx + 4 + kAccPitchAlign - 1) / kAccPitchAlign * kAccPitchAlign, stageCols = 2 * r * cw;
+                // the last 32-column epilogue load of the last accumulator must stay inside the allocation
+                const int need = (accStages - 1) * stageCols + (2 * r - 1) * cw + ((cw + 31) & ~31);
+                if (need > 512) continue;
+                const int xGroup = (r + 2) * npx * 128;
+                int wSlots = (kSmemLimit3 - 1024 - 4 * 32 * STAGE_PITCH * 4 - 2 * xGroup) / W_SLOT_BYTES;
+                if (wSlots > kMaxWSlots) wSlots = kMaxWSlots;
+                if (wSlots < 3) continue;
+                const int s = npx - 4;
+                const long long tiles = (long long)((p.OW + s - 1) / s) * ((p.OH + r - 1) / r);
+                const double mma = 18.0 * r * npx;
+                const double load = (9.0 * (p.O < 128 ? p.O : 128) * 128 + (double)xGroup) / 40.0;
+                const double cost = (double)tiles * (mma > load ? mma : load);
+                if (cost < best) {
+                    best = cost; found = true;
+                    p.NPX = npx; p.R = r; p.CW = cw; p.S = s; p.accStages = accStages; p.accStageCols = stageCols;
+                    p.wSlots = wSlots; p.xGroupBytes = xGroup;
+                    int cols = 32;
+                    while (cols < need) cols <<= 1;
+                    p.tmemCols = cols;
+                }
+            }
+        }
+    }
+    return found;
+}
+
+}  // namespace
+
+// 0 when the tensor-core path takes this shape (the caller then prepares the weights tap-major), SG3_E_NOKERNEL otherwise.
+int sg3_modconv_tc3_supported(int I, int O, int H, int W, int k, int pad)
+{
+    if (k != 3 || (pad != 0 && pad != 2)) return SG3_E_NOKERNEL;
+    if (W % 4 != 0 || H + 2 * pad - 2 < 1 || W + 2 * pad - 2 < 1) return SG3_E_NOKERNEL;      // TMA: 16-byte row pitch
+    (void)I; (void)O;
+    return 0;
+}
+
+// x [N][I][H][W]; wtap [N][9][O][ldw] (tap = ky * 3 + kx, i contiguous, ldw % 4 == 0, ldw >= I); y [N][O][OH][OW].
+int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw,
+                        cudaStream_t stream)
+{
+    if (sg3_modconv_tc3_supported(I, O, H, W, 3, pad) != 0) return SG3_E_NOKERNEL;
+    if (ldw % 4 != 0 || ldw < I) return SG3_E_NOKERNEL;
+    if (((uintptr_t)x & 15) || ((uintptr_t)wtap & 15)) return SG3_E_NOKERNEL;
+    Tc3Params p;
+    p.y = y; p.N = N; p.I = I; p.O = O; p.H = H; p.W = W; p.pad = pad;
+    p.OH = H + 2 * pad - 2; p.OW = W + 2 * pad - 2;
+    p.kChunks = (I + BK3 - 1) / BK3;
+    p.xoff = pad == 2 ? 4 : 0;
+    p.colBase = pad == 2 ? 4 : 2;
+    if (!plan_tc3(p)) return SG3_E_NOKERNEL;
+    p.tilesX = (p.OW + p.S - 1) / p.S;
+    p.tilesY = (p.OH + p.R - 1) / p.R;
+    p.tilesO = (O + 127) / 128;
+    p.totalTiles = (long long)N * p.tilesY * p.tilesX * p.tilesO;
+    const long long ctas = p.totalTiles < sg3_sm_count() ? p.totalTiles : sg3_sm_count();
+
+    alignas(64) CUtensorMap mapX, mapW;
+    {
+        const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)I, (uint64_t)N};
+        const uint64_t strides[3] = {(uint64_t)W * 4, (uint64_t)W * H * 4, (uint64_t)W * H * I * 4};
+        const uint32_t box[4] = {32, 1, BK3, 1};
+        if (!sg3_make_tensor_map(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+            return SG3_E_NOKERNEL;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)I, (uint64_t)O, 9, (uint64_t)N};
+        const uint64_t strides[3] = {(uint64_t)ldw * 4, (uint64_t)ldw * O * 4, (uint64_t)ldw * O * 9 * 4};
+        const uint32_t box[4] = {BK3, 128, 1, 1};
+        if (!sg3_make_tensor_map(&mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, wtap, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+            return SG3_E_NOKERNEL;
+    }
+    const int smemBytes = 2 * p.xGroupBytes + p.wSlots * W_SLOT_BYTES + 4 * 32 * STAGE_PITCH * 4 + 1024;
+    static std::once_flag once;
+    static cudaError_t attrErr = cudaSuccess;
+    std::call_once(once, [] { attrErr = cudaFuncSetAttribute(modconv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3); });
+    if (attrErr != cudaSuccess) return (int)attrErr;
+    modconv_tc3_kernel<<<(unsigned)ctas, kThreads3, smemBytes, stream>>>(mapX, mapW, p);
+    return sg3_launch_status();
+}

@@ -28,9 +28,10 @@ def _math_mode():
     return 'tf32' if torch.backends.cudnn.allow_tf32 else 'fp32'
 
 
-def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, transpose=False):
+def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, transpose=False, tap_major=False):
     """[N, O, ldw >= I*k*k] float32 modulated (+demodulated, +input-gain) weights, rows zero padded  (:39-56).
-    transpose=True (1x1 only): [N, I, ldw >= O], the weight operand of the input-gradient GEMM."""
+    transpose=True (1x1 only): [N, I, ldw >= O], the weight operand of the input-gradient GEMM.
+    tap_major=True: [N, k*k, O, ldw >= I], the operand of the 3x3 tensor-core kernel."""
     capi.require_cuda(w, 'modulated_conv2d')
     O, I, kh, kw = w.shape
     assert kh == kw
@@ -46,7 +47,12 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, tr
             mode, g = 2, g.contiguous()                            # per input channel
         else:
             mode, g = 3, g.expand(N, I).contiguous()               # per (sample, input channel), broadcast like :55
-    if transpose:
+    layout = 1 if transpose else (2 if tap_major else 0)
+    if tap_major:
+        assert not transpose
+        ldw = (I + 31) // 32 * 32
+        wmod = torch.empty([N, kh * kw, O, ldw], dtype=torch.float32, device=w.device)
+    elif transpose:
         assert kh == 1
         ldw = (O + 31) // 32 * 32
         wmod = torch.zeros([N, I, ldw], dtype=torch.float32, device=w.device)      # padding columns must be zero
@@ -57,7 +63,7 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, tr
     with torch.cuda.device(w.device):
         rc = capi.lib().sg3_modconv_weights(w.data_ptr(), s.data_ptr(), g.data_ptr() if g is not None else None, mode,
                                             wmod.data_ptr(), scratch.data_ptr(), N, I, O, kh, ldw, int(bool(demodulate)),
-                                            int(bool(round_tf32)), int(bool(transpose)), capi.stream_ptr(w.device))
+                                            int(bool(round_tf32)), layout, capi.stream_ptr(w.device))
     capi.check(rc, 'sg3_modconv_weights')
     return wmod
 
@@ -68,14 +74,16 @@ def conv_forward(x, wmod, O, k, padding, math):
     OH, OW = H + 2 * padding - k + 1, W + 2 * padding - k + 1
     y = torch.empty([N, O, OH, OW], dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        ldw = wmod.shape[2]
+        ldw = wmod.shape[-1]
         rc = capi.lib().sg3_modconv_fwd(x.data_ptr(), wmod.data_ptr(), y.data_ptr(), N, I, O, H, W, k, padding, ldw,
                                         1 if math == 'tf32' else 0, capi.SG3_F32, capi.stream_ptr(x.device))
-        if rc == capi.SG3_E_NOKERNEL and math == 'tf32':       # shapes the tensor-core kernel does not cover yet (3x3)
-            rc = capi.lib().sg3_modconv_fwd(x.data_ptr(), wmod.data_ptr(), y.data_ptr(), N, I, O, H, W, k, padding, ldw,
-                                            0, capi.SG3_F32, capi.stream_ptr(x.device))
     capi.check(rc, 'sg3_modconv_fwd')
     return y
+
+
+def tc_supported(I, O, H, W, k, padding):
+    """True when sg3_modconv_fwd has a tensor-core kernel for this shape (decides math mode and weight layout)."""
+    return capi.lib().sg3_modconv_tc_supported(I, O, H, W, k, padding) == 0
 
 
 def _reference_formula(x, w, s, demodulate, padding, input_gain):
@@ -105,7 +113,10 @@ class _ModConv(torch.autograd.Function):
         O, I, k, _ = w.shape
         xin = x.contiguous()
         x32 = xin if xin.dtype == torch.float32 else xin.float()
-        wmod = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, round_tf32=(math == 'tf32'))
+        if math == 'tf32' and not tc_supported(I, O, x32.shape[2], x32.shape[3], k, padding):
+            math = 'fp32'                  # shapes without a tensor-core kernel run the exact SIMT contraction
+        wmod = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, round_tf32=(math == 'tf32'),
+                               tap_major=(math == 'tf32' and k > 1))
         y = conv_forward(x32, wmod, O, k, padding, math)
         ctx.save_for_backward(x, w, s, input_gain)
         ctx.cfg = (demodulate, padding, math)

@@ -205,3 +205,62 @@ def test_modconv_tc_vs_oracle(pkg, shape):
                                     capi.stream_ptr(xt.device))
     assert rc == 0
     assert rel_err(y2.cpu().numpy(), ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# 3x3 TF32 tcgen05/TMEM contraction (modconv_tc3.cu, config T), called through the C ABI.
+
+TC3_CASES = [
+    # N, I, O, H, W, pad
+    (1, 32, 16, 8, 8, 2),          # one tile, one chunk, O << 128
+    (1, 32, 128, 36, 36, 2),       # T-1024 L0 map size, full 128-lane tile
+    (2, 64, 64, 20, 52, 2),        # two chunks, two samples, non-square
+    (1, 81, 51, 40, 148, 2),       # ragged I and O (T-1024 L11 channel counts), several column tiles
+    (1, 512, 323, 16, 24, 2),      # 16 chunks, three channel tiles (ragged last)
+    (1, 40, 200, 12, 276, 2),      # wide rows: several column tiles per row
+    (2, 48, 32, 18, 20, 0),        # padding 0 ('valid'), the dgrad form
+    (1, 128, 81, 30, 532, 2),      # short K loop -> double-buffered accumulators, 532-wide rows
+]
+
+
+@pytest.mark.parametrize('shape', TC3_CASES, ids=['x'.join(map(str, s)) for s in TC3_CASES])
+def test_modconv_tc3_vs_oracle(pkg, shape):
+    """3x3 tensor-core contraction vs the CPU oracle; TF32 tolerance (stated separately from fp32 parity):
+    max |err| <= 2e-3 * max |ref|.  The exact SIMT kernel on the same weights must agree to fp32 rounding."""
+    from oracle import sg3_oracle as orc
+    from sg3_b200 import capi
+    N, I, O, H, W, pad = shape
+    rng = np.random.RandomState(I + O + W)
+    x = rng.randn(N, I, H, W).astype(np.float32)
+    wm = (rng.randn(N, O, I, 3, 3) / np.sqrt(9 * I)).astype(np.float32)
+    assert capi.lib().sg3_modconv_tc_supported(I, O, H, W, 3, pad) == 0
+    ldw = (I + 31) // 32 * 32
+    wtap = np.zeros((N, 9, O, ldw), np.float32)                        # tap-major operand layout
+    wtap[:, :, :, :I] = wm.reshape(N, O, I, 9).transpose(0, 3, 1, 2)
+    OH, OW = H + 2 * pad - 2, W + 2 * pad - 2
+    xt, wt = cu(x), cu(wtap)
+    y = torch.full((N, O, OH, OW), float('nan'), device='cuda')
+    rc = capi.lib().sg3_modconv_fwd(xt.data_ptr(), wt.data_ptr(), y.data_ptr(), N, I, O, H, W, 3, pad, ldw, 1, capi.SG3_F32,
+                                    capi.stream_ptr(xt.device))
+    assert rc == 0, 'tensor-core path must take 3x3 convolutions with padding 0 / 2'
+    torch.cuda.synchronize()
+    ref = orc.conv2d(x, wm, padding=pad)
+    assert rel_err(y.cpu().numpy(), ref) < 2e-3
+    ld0 = (9 * I + 31) // 32 * 32
+    w0 = np.zeros((N, O, ld0), np.float32)
+    w0[:, :, :9 * I] = wm.reshape(N, O, 9 * I)
+    y2 = torch.empty_like(y)
+    w0t = cu(w0)
+    rc = capi.lib().sg3_modconv_fwd(xt.data_ptr(), w0t.data_ptr(), y2.data_ptr(), N, I, O, H, W, 3, pad, ld0, 0, capi.SG3_F32,
+                                    capi.stream_ptr(xt.device))
+    assert rc == 0
+    assert rel_err(y2.cpu().numpy(), ref) < 1e-5
+
+
+def test_modconv_tap_major_weights(pkg):
+    """The tap-major prologue layout holds the same numbers as the standard layout."""
+    rng = np.random.RandomState(5)
+    w, s = rng.randn(37, 19, 3, 3).astype(np.float32), rng.randn(3, 19).astype(np.float32)
+    a = pkg.modulated_conv.modconv_weights(cu(w), cu(s), True, torch.tensor(0.7).cuda())[:, :, :19 * 9].reshape(3, 37, 19, 9)
+    b = pkg.modulated_conv.modconv_weights(cu(w), cu(s), True, torch.tensor(0.7).cuda(), tap_major=True)[:, :, :, :19]
+    assert torch.equal(a.permute(0, 3, 1, 2), b)
