@@ -53,7 +53,9 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     __shared__ __align__(8) uint64_t barFull[kMaxStages], barEmpty[kMaxStages], barAccFull[2], barAccEmpty[2];
     __shared__ uint32_t tmemBase;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the role dispatch is then provably warp-uniform and the producer / MMA loops run on the
+    // uniform datapath (see tc_common.cuh, "warp-uniform issue")
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int stageBytes = A_STAGE_BYTES + p.BN * BK * 4;
     const uint32_t tiles = (smem_u32(smem) + 1023u) & ~1023u;        // SWIZZLE_128B operands need 1024-byte aligned tiles
 
@@ -69,7 +71,7 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmemBase;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmemBase, 0);
 
     // tile -> (sample n, pixel block tm, channel block tn); channel block fastest so that the CTAs working on one
     // pixel block at the same time share its activation tiles in L2
@@ -83,54 +85,46 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     };
 
     if (warp == 4) {
-        // ---------------- TMA producer ----------------
-        if (lane == 0) {
-            uint32_t it = 0;                                          // k-iterations issued so far, across tiles
-            for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x) {
-                int n, p0, o0;
-                decode(t, n, p0, o0);
-                for (int kt = 0; kt < p.kTiles; kt++, it++) {
-                    const uint32_t s = it % p.stages, round = it / p.stages;
-                    if (round > 0) mbar_wait(smem_u32(&barEmpty[s]), (round - 1) & 1);
-                    const uint32_t full = smem_u32(&barFull[s]);
-                    mbar_expect_tx(full, (uint32_t)stageBytes);
-                    const uint32_t aDst = tiles + s * stageBytes;
+        // ---------------- TMA producer (whole warp, elected lane issues) ----------------
+        uint32_t it = 0;                                          // k-iterations issued so far, across tiles
+        for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x) {
+            int n, p0, o0;
+            decode(t, n, p0, o0);
+            for (int kt = 0; kt < p.kTiles; kt++, it++) {
+                const uint32_t s = it % p.stages, round = it / p.stages;
+                if (round > 0) mbar_wait(smem_u32(&barEmpty[s]), (round - 1) & 1);
+                const uint32_t full = smem_u32(&barFull[s]);
+                mbar_expect_tx_elect(full, (uint32_t)stageBytes);
+                const uint32_t aDst = tiles + s * stageBytes;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) tma_load_3d(aDst + j * (BK * 128), &mapX, full, p0 + 32 * j, kt * BK, n);
-                    tma_load_3d(aDst + A_STAGE_BYTES, &mapW, full, kt * BK, o0, n);
-                }
+                for (int j = 0; j < 4; j++) tma_load_3d_elect(aDst + j * (BK * 128), &mapX, full, p0 + 32 * j, kt * BK, n);
+                tma_load_3d_elect(aDst + A_STAGE_BYTES, &mapW, full, kt * BK, o0, n);
             }
         }
     } else if (warp == 5) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, A MN-major, B K-major, N, M=128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
-                                   ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            uint32_t it = 0, tc = 0;                                  // k-iterations / tiles consumed so far
-            for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x, tc++) {
-                const uint32_t as = tc & 1, use = tc >> 1;            // accumulator stage and how often it was used before
-                if (use > 0) mbar_wait(smem_u32(&barAccEmpty[as]), (use - 1) & 1);
+        // ---------------- MMA issuer (whole warp, elected lane issues) ----------------
+        // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, A MN-major, B K-major, N, M=128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
+                               ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // A (fp32, MN-major): 8 k-rows of 128 B per step = two 4-row swizzle atoms 512 B apart (SBO), 32-pixel blocks
+        // BK*128 B apart (LBO), K step 1024 B;  B (K-major): K step 32 B inside the 128-byte row, 8-row groups 1024 B apart
+        const uint64_t dA = umma_desc(tiles, BK * 128, 512, kLayoutSw128Base32), dB = umma_desc(tiles + A_STAGE_BYTES, 16, 1024);
+        const uint32_t aLo0 = (uint32_t)dA, aHi = (uint32_t)(dA >> 32), bLo0 = (uint32_t)dB, bHi = (uint32_t)(dB >> 32);
+        const uint32_t stageStep = (uint32_t)stageBytes >> 4;
+        uint32_t it = 0, tc = 0;                                  // k-iterations / tiles consumed so far
+        for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x, tc++) {
+            const uint32_t as = tc & 1, use = tc >> 1;            // accumulator stage and how often it was used before
+            if (use > 0) mbar_wait(smem_u32(&barAccEmpty[as]), (use - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem + as * p.accCols;
+            for (int kt = 0; kt < p.kTiles; kt++, it++) {
+                const uint32_t s = it % p.stages;
+                mbar_wait(smem_u32(&barFull[s]), (it / p.stages) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc = tmem + as * p.accCols;
-                for (int kt = 0; kt < p.kTiles; kt++, it++) {
-                    const uint32_t s = it % p.stages;
-                    mbar_wait(smem_u32(&barFull[s]), (it / p.stages) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t aBase = tiles + s * stageBytes, bBase = aBase + A_STAGE_BYTES;
-#pragma unroll
-                    for (int ks = 0; ks < BK / 8; ks++) {
-                        // A (fp32, MN-major): 8 k-rows of 128 B per step = two 4-row swizzle atoms 512 B apart (SBO);
-                        // 32-pixel blocks BK*128 B apart (LBO)
-                        const uint64_t da = umma_desc(aBase + ks * 1024, BK * 128, 512, kLayoutSw128Base32);
-                        // B: step 8 tf32 = 32 B inside the 128-byte row; 8-row groups 1024 B apart
-                        const uint64_t db = umma_desc(bBase + ks * 32, 16, 1024);
-                        umma_tf32(acc, da, db, idesc, (kt > 0 || ks > 0) ? 1u : 0u);
-                    }
-                    umma_commit(smem_u32(&barEmpty[s]));              // frees the smem stage when these MMAs retire
-                }
-                umma_commit(smem_u32(&barAccFull[as]));               // accumulator of this tile complete
+                umma_tf32_x4<64, 2>(acc, aLo0 + s * stageStep, aHi, bLo0 + s * stageStep, bHi, idesc, kt > 0 ? 1u : 0u);
+                umma_commit_elect(smem_u32(&barEmpty[s]));        // frees the smem stage when these MMAs retire
             }
+            umma_commit_elect(smem_u32(&barAccFull[as]));         // accumulator of this tile complete
         }
     } else {
         // ---------------- epilogue: TMEM -> registers -> global (warps 0-3, TMEM lanes 32*warp .. +31) ----------------
@@ -187,7 +181,7 @@ modconv_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_con
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t barFull[kMaxStages], barEmpty[kMaxStages], barAccum;
     __shared__ uint32_t tmemBase;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int stageBytes = A_STAGE_BYTES + p.BN * BK * 4;
     const int stages = p.BN > 128 ? 4 : 6;
     const uint32_t tiles = (smem_u32(smem) + 1023u) & ~1023u;
@@ -214,39 +208,32 @@ modconv_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_con
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmemBase;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmemBase, 0);
 
     if (warp == 4) {
-        if (lane == 0) {
-            for (int it = 0; it < nk; it++) {
-                const int s = it % stages, round = it / stages;
-                if (round > 0) mbar_wait(smem_u32(&barEmpty[s]), (round - 1) & 1);
-                const uint32_t full = smem_u32(&barFull[s]);
-                mbar_expect_tx(full, (uint32_t)stageBytes);
-                const uint32_t aDst = tiles + s * stageBytes;
-                tma_load_3d(aDst, &mapDY, full, (kt0 + it) * BK, o0, n);                    // [128 o][32 px]
-                tma_load_3d(aDst + A_STAGE_BYTES, &mapX, full, (kt0 + it) * BK, i0, n);     // [BN i][32 px]
-            }
+        for (int it = 0; it < nk; it++) {
+            const int s = it % stages, round = it / stages;
+            if (round > 0) mbar_wait(smem_u32(&barEmpty[s]), (round - 1) & 1);
+            const uint32_t full = smem_u32(&barFull[s]);
+            mbar_expect_tx_elect(full, (uint32_t)stageBytes);
+            const uint32_t aDst = tiles + s * stageBytes;
+            tma_load_3d_elect(aDst, &mapDY, full, (kt0 + it) * BK, o0, n);                    // [128 o][32 px]
+            tma_load_3d_elect(aDst + A_STAGE_BYTES, &mapX, full, (kt0 + it) * BK, i0, n);     // [BN i][32 px]
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            // D=F32, A=B=TF32, both K-major, N = BN, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int it = 0; it < nk; it++) {
-                const int s = it % stages;
-                mbar_wait(smem_u32(&barFull[s]), (it / stages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t aBase = tiles + s * stageBytes, bBase = aBase + A_STAGE_BYTES;
-#pragma unroll
-                for (int ks = 0; ks < BK / 8; ks++) {
-                    const uint64_t da = umma_desc(aBase + ks * 32, 16, 1024);
-                    const uint64_t db = umma_desc(bBase + ks * 32, 16, 1024);
-                    umma_tf32(tmem, da, db, idesc, (it > 0 || ks > 0) ? 1u : 0u);
-                }
-                umma_commit(smem_u32(&barEmpty[s]));
-            }
-            umma_commit(smem_u32(&barAccum));
+        // D=F32, A=B=TF32, both K-major, N = BN, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        const uint64_t dA = umma_desc(tiles, 16, 1024), dB = umma_desc(tiles + A_STAGE_BYTES, 16, 1024);
+        const uint32_t aLo0 = (uint32_t)dA, aHi = (uint32_t)(dA >> 32), bLo0 = (uint32_t)dB, bHi = (uint32_t)(dB >> 32);
+        const uint32_t stageStep = (uint32_t)stageBytes >> 4;
+        for (int it = 0; it < nk; it++) {
+            const int s = it % stages;
+            mbar_wait(smem_u32(&barFull[s]), (it / stages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_tf32_x4<2, 2>(tmem, aLo0 + s * stageStep, aHi, bLo0 + s * stageStep, bHi, idesc, it > 0 ? 1u : 0u);
+            umma_commit_elect(smem_u32(&barEmpty[s]));
         }
+        umma_commit_elect(smem_u32(&barAccum));
     } else {
         mbar_wait(smem_u32(&barAccum), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -59,7 +59,9 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t barWFull[kMaxWSlots], barWEmpty[kMaxWSlots], barXFull[2], barXEmpty[2], barAccFull[2], barAccEmpty[2];
     __shared__ uint32_t tmemBase;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: the compiler then knows the role dispatch is warp-uniform and keeps the producer / MMA
+    // loop state in uniform registers (no R2UR traffic in front of every UTMALDG / UTCHMMA)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
     const uint32_t xRing = base;                                        // 2 groups of (R + 2) rows x NPX px x 32 ch
     const uint32_t wRing = base + 2u * (uint32_t)p.xGroupBytes;        // wSlots x 16 KB (1024-aligned: xGroupBytes % 4096 == 0)
@@ -80,7 +82,7 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem = tmemBase;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmemBase, 0);
 
     // tile -> (sample, row block, column block, channel block); channel block fastest: the CTAs running together share x in L2
     auto decode = [&](long long t, int& n, int& oy0, int& tx, int& o0) {
@@ -95,71 +97,69 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     const uint32_t rowBytes = (uint32_t)p.NPX * 128u;                  // [32 ch][NPX px] of one input row
 
     if (warp == 4) {
-        // ---------------- TMA producer ----------------
-        if (lane == 0) {
-            uint32_t xIt = 0, wIt = 0;
-            for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x) {
-                int n, oy0, tx, o0;
-                decode(t, n, oy0, tx, o0);
-                const int xs = tx * p.S - p.xoff;
-                for (int c = 0; c < p.kChunks; c++, xIt++) {
-                    const uint32_t xg = xIt & 1;
-                    if (xIt >= 2) mbar_wait(smem_u32(&barXEmpty[xg]), ((xIt >> 1) - 1) & 1);
-                    const uint32_t xfull = smem_u32(&barXFull[xg]);
-                    mbar_expect_tx(xfull, (uint32_t)p.xGroupBytes);
-                    const uint32_t xDst = xRing + xg * (uint32_t)p.xGroupBytes;
-                    for (int rr = 0; rr < p.R + 2; rr++)
-                        for (int j = 0; j < boxesPerRow; j++)
-                            tma_load_4d(xDst + rr * rowBytes + j * 4096u, &mapX, xfull, xs + 32 * j, oy0 - p.pad + rr, c * BK3, n);
-                    for (int tap = 0; tap < 9; tap++, wIt++) {
-                        const uint32_t ws = wIt % (uint32_t)p.wSlots, round = wIt / (uint32_t)p.wSlots;
-                        if (round > 0) mbar_wait(smem_u32(&barWEmpty[ws]), (round - 1) & 1);
-                        const uint32_t wfull = smem_u32(&barWFull[ws]);
-                        mbar_expect_tx(wfull, (uint32_t)W_SLOT_BYTES);
-                        tma_load_4d(wRing + ws * W_SLOT_BYTES, &mapW, wfull, c * BK3, o0, tap, n);
-                    }
+        // ---------------- TMA producer: the whole warp runs the loop, one elected lane issues ----------------
+        uint32_t xIt = 0, wIt = 0;
+        for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x) {
+            int n, oy0, tx, o0;
+            decode(t, n, oy0, tx, o0);
+            const int xs = tx * p.S - p.xoff;
+            for (int c = 0; c < p.kChunks; c++, xIt++) {
+                const uint32_t xg = xIt & 1;
+                if (xIt >= 2) mbar_wait(smem_u32(&barXEmpty[xg]), ((xIt >> 1) - 1) & 1);
+                const uint32_t xfull = smem_u32(&barXFull[xg]);
+                mbar_expect_tx_elect(xfull, (uint32_t)p.xGroupBytes);
+                const uint32_t xDst = xRing + xg * (uint32_t)p.xGroupBytes;
+                for (int rr = 0; rr < p.R + 2; rr++)
+                    for (int j = 0; j < boxesPerRow; j++)
+                        tma_load_4d_elect(xDst + rr * rowBytes + j * 4096u, &mapX, xfull, xs + 32 * j, oy0 - p.pad + rr, c * BK3, n);
+                for (int tap = 0; tap < 9; tap++, wIt++) {
+                    const uint32_t ws = wIt % (uint32_t)p.wSlots, round = wIt / (uint32_t)p.wSlots;
+                    if (round > 0) mbar_wait(smem_u32(&barWEmpty[ws]), (round - 1) & 1);
+                    const uint32_t wfull = smem_u32(&barWFull[ws]);
+                    mbar_expect_tx_elect(wfull, (uint32_t)W_SLOT_BYTES);
+                    tma_load_4d_elect(wRing + ws * W_SLOT_BYTES, &mapW, wfull, c * BK3, o0, tap, n);
                 }
             }
         }
     } else if (warp == 5) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
-            // D = F32, A = B = TF32, A K-major (bit 15 = 0), B MN-major (bit 16 = 1), N = NPX, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
-                                   ((uint32_t)(p.NPX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            uint32_t xIt = 0, wIt = 0, tc = 0;
-            for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x, tc++) {
-                const uint32_t as = p.accStages == 2 ? (tc & 1) : 0, use = p.accStages == 2 ? (tc >> 1) : tc;
-                if (use > 0) mbar_wait(smem_u32(&barAccEmpty[as]), (use - 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc = tmem + as * (uint32_t)p.accStageCols;
-                for (int c = 0; c < p.kChunks; c++, xIt++) {
-                    const uint32_t xg = xIt & 1;
-                    mbar_wait(smem_u32(&barXFull[xg]), (xIt >> 1) & 1);
-                    const uint32_t xBase = xRing + xg * (uint32_t)p.xGroupBytes;
-                    for (int tap = 0; tap < 9; tap++, wIt++) {
-                        const int ky = tap / 3, kx = tap - 3 * ky;
-                        const uint32_t ws = wIt % (uint32_t)p.wSlots;
-                        mbar_wait(smem_u32(&barWFull[ws]), (wIt / (uint32_t)p.wSlots) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t aBase = wRing + ws * W_SLOT_BYTES;
-                        const uint32_t first = (c == 0 && ky == 0 && kx < 2) ? 0u : 1u;    // first touch of an accumulator
-                        for (int oyl = 0; oyl < p.R; oyl++) {
-                            const uint32_t bBase = xBase + (uint32_t)(oyl + ky) * rowBytes;
-                            const uint32_t d = acc + (uint32_t)((2 * oyl + (kx & 1)) * p.CW + (kx == 0 ? 2 : 0));
+        // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues (tc_common.cuh) ----------------
+        // D = F32, A = B = TF32, A K-major (bit 15 = 0), B MN-major (bit 16 = 1), N = NPX, M = 128
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
+                               ((uint32_t)(p.NPX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t dA = umma_desc(wRing, 16, 1024), dB = umma_desc(xRing, BK3 * 128, 512, kLayoutSw128Base32);
+        const uint32_t aLo0 = (uint32_t)dA, aHi = (uint32_t)(dA >> 32), bLo0 = (uint32_t)dB, bHi = (uint32_t)(dB >> 32);
+        const uint32_t rowStep = rowBytes >> 4, groupStep = (uint32_t)p.xGroupBytes >> 4;
+        uint32_t xIt = 0, wIt = 0, tc = 0;
+        for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x, tc++) {
+            const uint32_t as = p.accStages == 2 ? (tc & 1) : 0, use = p.accStages == 2 ? (tc >> 1) : tc;
+            if (use > 0) mbar_wait(smem_u32(&barAccEmpty[as]), (use - 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t acc = tmem + as * (uint32_t)p.accStageCols;
+            for (int c = 0; c < p.kChunks; c++, xIt++) {
+                const uint32_t xg = xIt & 1;
+                mbar_wait(smem_u32(&barXFull[xg]), (xIt >> 1) & 1);
+                const uint32_t bLoG = bLo0 + xg * groupStep;
+                uint32_t ws = wIt % (uint32_t)p.wSlots, wPhase = (wIt / (uint32_t)p.wSlots) & 1;
+#pragma unroll 1
+                for (int ky = 0; ky < 3; ky++) {
 #pragma unroll
-                            for (int ks = 0; ks < BK3 / 8; ks++) {
-                                const uint64_t da = umma_desc(aBase + ks * 32, 16, 1024);
-                                const uint64_t db = umma_desc(bBase + ks * 1024, BK3 * 128, 512, kLayoutSw128Base32);
-                                umma_tf32(d, da, db, idesc, ks > 0 ? 1u : first);
-                            }
-                        }
-                        umma_commit(smem_u32(&barWEmpty[ws]));
+                    for (int kx = 0; kx < 3; kx++) {
+                        mbar_wait(smem_u32(&barWFull[ws]), wPhase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t aLo = aLo0 + ws * (W_SLOT_BYTES >> 4);
+                        const uint32_t first = (c == 0 && ky == 0 && kx < 2) ? 0u : 1u;     // first touch of an accumulator
+                        const uint32_t dOff = (uint32_t)((kx & 1) * p.CW + (kx == 0 ? 2 : 0));
+                        for (int oyl = 0; oyl < p.R; oyl++)
+                            umma_tf32_x4<2, 64>(acc + dOff + (uint32_t)(2 * oyl * p.CW), aLo, aHi,
+                                                bLoG + (uint32_t)(oyl + ky) * rowStep, bHi, idesc, first);
+                        umma_commit_elect(smem_u32(&barWEmpty[ws]));
+                        if (++ws == (uint32_t)p.wSlots) { ws = 0; wPhase ^= 1; }
                     }
-                    umma_commit(smem_u32(&barXEmpty[xg]));
                 }
-                umma_commit(smem_u32(&barAccFull[as]));
+                wIt += 9;
+                umma_commit_elect(smem_u32(&barXEmpty[xg]));
             }
+            umma_commit_elect(smem_u32(&barAccFull[as]));
         }
     } else {
         // ---------------- epilogue: TMEM -> registers -> transpose in smem -> global (warps 0-3) ----------------

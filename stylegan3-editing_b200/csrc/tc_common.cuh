@@ -99,4 +99,67 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// ---- warp-uniform issue -------------------------------------------------------------------------------------------
+// Measured (tools/tc_mma_bench.cu): when tcgen05.mma sits in a single-thread branch (`if (lane == 0)`), ptxas wraps every
+// UTCHMMA in an ELECT/branch waterfall to move its operands into uniform registers and one MMA costs ~140 clk of issue
+// time -- more than the 64..128 clk the tensor core needs for N = 128..256.  The helpers below are called by ALL lanes of
+// the (converged) MMA warp; elect.sync picks the issuing lane, the operands stay in uniform registers and four MMAs go
+// out back to back (N = 64: 48 clk, N = 96: 56 clk, N >= 128: N/2 clk per MMA, the tensor-core floor).
+//
+// Descriptors are passed as 32-bit halves: hi = SBO | version | layout (constant per operand kind), lo = LBO | start >> 4;
+// a K step only adds to the start field (AS / BS in 16-byte units: 2 for a K-major SWIZZLE_128B operand, 64 for the
+// 32-bit MN-major one).
+template <int AS, int BS>
+__device__ __forceinline__ void umma_tf32_x4(uint32_t d, uint32_t aLo, uint32_t aHi, uint32_t bLo, uint32_t bHi, uint32_t idesc,
+                                             uint32_t accumulateFirst)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, %5, %5;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+        "add.u32 al, %1, %7;\n\tadd.u32 bl, %3, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, t;\n\t"
+        "add.u32 al, %1, %9;\n\tadd.u32 bl, %3, %10;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, t;\n\t"
+        "add.u32 al, %1, %11;\n\tadd.u32 bl, %3, %12;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, t;\n\t}"
+        ::"r"(d), "r"(aLo), "r"(aHi), "r"(bLo), "r"(bHi), "r"(idesc), "r"(accumulateFirst),
+          "n"(AS), "n"(BS), "n"(2 * AS), "n"(2 * BS), "n"(3 * AS), "n"(3 * BS) : "memory");
+}
+
+// tcgen05.commit from the elected lane of a converged warp.
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+
+// TMA issue from the elected lane of a converged warp (same reason: no ELECT waterfall around UTMALDG).
+__device__ __forceinline__ void mbar_expect_tx_elect(uint32_t bar, uint32_t bytes)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_3d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d_elect(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\telect.sync _|q, 0xffffffff;\n\t"
+        "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 }  // namespace
