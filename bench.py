@@ -30,7 +30,10 @@ if ROOT not in sys.path:
 
 R1024 = dict(z_dim=512, c_dim=0, w_dim=512, img_resolution=1024, img_channels=3,
              channel_base=65536, channel_max=1024, conv_kernel=1, use_radial_filters=True)
+T1024 = dict(z_dim=512, c_dim=0, w_dim=512, img_resolution=1024, img_channels=3,
+             channel_base=32768, channel_max=512, conv_kernel=3, use_radial_filters=False)
 METRIC = 'StyleGAN3-R 1024^2 G-forward images/sec'
+CFG_NAME = 'R'          # --config T switches R1024 / METRIC to the config-T generator (BASELINE.json configs[1])
 
 
 def parse_args():
@@ -43,7 +46,15 @@ def parse_args():
     ap.add_argument('--math', default='tf32', choices=['tf32', 'fp32'], help='modulated_conv2d contraction')
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='time budget of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    return ap.parse_args()
+    ap.add_argument('--config', default='R', choices=['R', 'T'],
+                    help='R: StyleGAN3-R 1024^2 (the metric BASELINE.json is quoted on, default); T: StyleGAN3-T 1024^2 (configs[1])')
+    args = ap.parse_args()
+    if args.config == 'T':
+        global METRIC, CFG_NAME
+        R1024.clear(); R1024.update(T1024)
+        METRIC = 'StyleGAN3-T 1024^2 G-forward images/sec'
+        CFG_NAME = 'T'
+    return args
 
 
 # --------------------------------------------------------------------------------------------------
@@ -106,7 +117,7 @@ def cpu_sample(seconds, threads=None):
     dt = time.perf_counter() - t0
     frac = done / total
     return dict(value=frac / dt, unit='images/s', cores=cores, kind='port',
-                sample=f'1 image, StyleGAN3-R 1024^2 synthesis layers L0..L{nl - 1} of 15 on the CPU oracle '
+                sample=f'1 image, StyleGAN3-{CFG_NAME} 1024^2 synthesis layers L0..L{nl - 1} of 15 on the CPU oracle '
                        f'({100 * frac:.1f}% of per-image FLOPs, {dt:.1f} s); images/s extrapolated by FLOP share')
 
 
@@ -126,7 +137,7 @@ def run_reference(args):
     out = dict(metric=METRIC, value=v, unit='images/s', impl='reference', n_gpus=args.gpus, steps=args.steps,
                warmup=args.warmup, ms_per_step=1e3 / v if v > 0 else None, higher_is_better=True, scaling='weak',
                vs_baseline=None, dtype='f32', data='synthetic',
-               config=dict(workload='StyleGAN3-R 1024^2 synthesis forward, random-init, fp32 (force_fp32)',
+               config=dict(workload=f'StyleGAN3-{CFG_NAME} 1024^2 synthesis forward, random-init, fp32 (force_fp32)',
                            note='reference CPU algorithm (impl=ref composition) via the oracle port; bounded sample per step'),
                cpu_baseline=info, e2e=dict(value=v, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(out))
@@ -295,7 +306,7 @@ def run_ours(args):
         metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
         dtype='f32' if args.math == 'fp32' else 'f32 (tf32 tensor-core conv)', data='synthetic',
-        config=dict(workload='StyleGAN3-R 1024^2 synthesis forward (BASELINE.json configs[2]), random-init seed 0, '
+        config=dict(workload=f'StyleGAN3-{CFG_NAME} 1024^2 synthesis forward (BASELINE.json configs[{2 if CFG_NAME == "R" else 1}]), random-init seed 0, '
                              'force_fp32, noise_mode=const', per_gpu_batch=B, global_batch=world * B,
                     parallelism=f'batch-sharded x{world}, no collective', conv_math=args.math,
                     l2='activations of every layer exceed the 126 MB L2 (inputs larger than L2, no flush needed)'),
@@ -304,7 +315,8 @@ def run_ours(args):
                  h2d_bytes_per_step=int(ws_host.numel() * 4), d2h_bytes_per_step=int(img_host.numel() * 4)),
         gpu_launches=int(launches),
         roofline=dict(bound='hbm', achieved=achieved, peak=hbm_peak, unit='GB/s', frac=achieved / hbm_peak,
-                      traffic=None, kernel='filtered_lrelu (15 calls per step, all timed with CUDA events)',
+                      traffic=None, traffic_note='ncu --set full of the L11 launch (profiles/r01_flrelu_L11_ncu.md): dram read+write = 0.98x the algorithmic bytes',
+                      kernel='filtered_lrelu (15 calls per step, all timed with CUDA events)',
                       launches_timed=n_calls, ms_per_step=fl_ms / args.steps,
                       peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s (of fallback)',
                       fp32_pipe=dict(achieved_tfma=fma_rate, peak_tfma=fp32_peak_tfma, frac=fma_rate / fp32_peak_tfma,

@@ -35,10 +35,9 @@ bool sg3_make_tensor_map(CUtensorMap* m, CUtensorMapDataType type, int rank, con
 namespace {
 
 constexpr int BK3 = 32;                 // input channels per chunk
-constexpr int W_SLOT_BYTES = 128 * BK3 * 4;   // one tap of one chunk: [128 o][32 i] fp32
-constexpr int kMaxWSlots = 9;
+constexpr int kMaxWSlots = 36;          // W ring slots; one slot = one tap of one chunk: [wRows <= 128 o][32 i] fp32
 constexpr int kThreads3 = 192;
-constexpr int STAGE_PITCH = 33;         // transpose staging: [32 channels][33]
+constexpr int STAGE_PITCH = 36;         // transpose staging: [32 channels][36] (16-byte rows: float4 writes, conflict-free)
 constexpr int kAccPitchAlign = 32;      // accumulator pitch granularity in TMEM columns (tcgen05.ld.x32 start columns)
 
 struct Tc3Params {
@@ -50,6 +49,8 @@ struct Tc3Params {
     int accStages, accStageCols, tmemCols;
     int tilesX, tilesY, tilesO, kChunks;
     int wSlots, xGroupBytes;
+    int wRows, wSlotBytes;     // rows of a W slot (min(128, ceil8(O))) and its size
+    int resident;              // the ring holds every (chunk, tap) of the layer: W is reloaded only when (n, o-tile) changes
     long long totalTiles;
 };
 
@@ -65,7 +66,7 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
     const uint32_t xRing = base;                                        // 2 groups of (R + 2) rows x NPX px x 32 ch
     const uint32_t wRing = base + 2u * (uint32_t)p.xGroupBytes;        // wSlots x 16 KB (1024-aligned: xGroupBytes % 4096 == 0)
-    float* stage = reinterpret_cast<float*>(smem + (wRing + (uint32_t)p.wSlots * W_SLOT_BYTES - smem_u32(smem)));
+    float* stage = reinterpret_cast<float*>(smem + (wRing + (uint32_t)(p.wSlots * p.wSlotBytes) - smem_u32(smem)));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxWSlots; s++) { mbar_init(smem_u32(&barWFull[s]), 1); mbar_init(smem_u32(&barWEmpty[s]), 1); }
@@ -99,10 +100,13 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     if (warp == 4) {
         // ---------------- TMA producer: the whole warp runs the loop, one elected lane issues ----------------
         uint32_t xIt = 0, wIt = 0;
+        int wN = -1, wO = -1;                                     // (sample, channel block) whose weights sit in a resident ring
         for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x) {
             int n, oy0, tx, o0;
             decode(t, n, oy0, tx, o0);
             const int xs = tx * p.S - p.xoff;
+            const bool reuseW = p.resident && n == wN && o0 == wO;
+            wN = n; wO = o0;
             for (int c = 0; c < p.kChunks; c++, xIt++) {
                 const uint32_t xg = xIt & 1;
                 if (xIt >= 2) mbar_wait(smem_u32(&barXEmpty[xg]), ((xIt >> 1) - 1) & 1);
@@ -116,8 +120,8 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                     const uint32_t ws = wIt % (uint32_t)p.wSlots, round = wIt / (uint32_t)p.wSlots;
                     if (round > 0) mbar_wait(smem_u32(&barWEmpty[ws]), (round - 1) & 1);
                     const uint32_t wfull = smem_u32(&barWFull[ws]);
-                    mbar_expect_tx_elect(wfull, (uint32_t)W_SLOT_BYTES);
-                    tma_load_4d_elect(wRing + ws * W_SLOT_BYTES, &mapW, wfull, c * BK3, o0, tap, n);
+                    mbar_expect_tx_elect(wfull, reuseW ? 0u : (uint32_t)p.wSlotBytes);    // resident: hand the slot over as is
+                    if (!reuseW) tma_load_4d_elect(wRing + ws * (uint32_t)p.wSlotBytes, &mapW, wfull, c * BK3, o0, tap, n);
                 }
             }
         }
@@ -146,7 +150,7 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                     for (int kx = 0; kx < 3; kx++) {
                         mbar_wait(smem_u32(&barWFull[ws]), wPhase);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t aLo = aLo0 + ws * (W_SLOT_BYTES >> 4);
+                        const uint32_t aLo = aLo0 + ws * ((uint32_t)p.wSlotBytes >> 4);
                         const uint32_t first = (c == 0 && ky == 0 && kx < 2) ? 0u : 1u;     // first touch of an accumulator
                         const uint32_t dOff = (uint32_t)((kx & 1) * p.CW + (kx == 0 ? 2 : 0));
                         for (int oyl = 0; oyl < p.R; oyl++)
@@ -163,6 +167,9 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
         }
     } else {
         // ---------------- epilogue: TMEM -> registers -> transpose in smem -> global (warps 0-3) ----------------
+        // A warp can only read its own 32 TMEM lanes (= 32 channels), but once a 32-column block is staged in shared memory
+        // any warp can store it: the four warps share the channel rows of every block, so narrow layers (O = 32: one
+        // warp owns all the channels) still store with 128 threads.
         float* st = stage + warp * (32 * STAGE_PITCH);
         uint32_t tc = 0;
         for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x, tc++) {
@@ -172,32 +179,43 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             mbar_wait(smem_u32(&barAccFull[as]), use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc = tmem + ((uint32_t)(32 * warp) << 16) + as * (uint32_t)p.accStageCols;
-            const int oBase = o0 + 32 * warp;
+            const int nrows = min(128, p.O - o0);                 // valid channels (TMEM lanes) of this tile
+            const bool mine = 32 * warp < nrows;
             const int colEnd = p.colBase + p.S;
+            const size_t chStep = (size_t)p.OH * p.OW;
             for (int oyl = 0; oyl < p.R; oyl++) {
                 const int oy = oy0 + oyl;
                 if (oy >= p.OH) break;
                 float carry = 0.f;
                 for (int c0 = 0; c0 < colEnd; c0 += 32) {
-                    uint32_t e[32], o[32];
-                    tmem_ld32(acc + (uint32_t)((2 * oyl) * p.CW + c0), e);
-                    tmem_ld32(acc + (uint32_t)((2 * oyl + 1) * p.CW + c0), o);
+                    if (mine) {
+                        uint32_t e[32], o[32];
+                        tmem_ld32(acc + (uint32_t)((2 * oyl) * p.CW + c0), e);
+                        tmem_ld32(acc + (uint32_t)((2 * oyl + 1) * p.CW + c0), o);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float prev = j == 0 ? carry : __uint_as_float(o[j - 1]);
-                        st[lane * STAGE_PITCH + j] = __uint_as_float(e[j]) + prev;
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 v;
+                            v.x = __uint_as_float(e[j]) + (j == 0 ? carry : __uint_as_float(o[j - 1]));
+                            v.y = __uint_as_float(e[j + 1]) + __uint_as_float(o[j]);
+                            v.z = __uint_as_float(e[j + 2]) + __uint_as_float(o[j + 1]);
+                            v.w = __uint_as_float(e[j + 3]) + __uint_as_float(o[j + 2]);
+                            *reinterpret_cast<float4*>(st + lane * STAGE_PITCH + j) = v;
+                        }
+                        carry = __uint_as_float(o[31]);
                     }
-                    carry = __uint_as_float(o[31]);
-                    __syncwarp();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");          // block staged by its owners
                     const int col = c0 + lane;
                     const int ox = tx * p.S + col - p.colBase;
-                    const bool okx = col >= p.colBase && col < colEnd && ox < p.OW;
-                    float* yrow = p.y + (((size_t)n * p.O + oBase) * p.OH + oy) * (size_t)p.OW + ox;
-                    const size_t chStep = (size_t)p.OH * p.OW;
-#pragma unroll 8
-                    for (int ch = 0; ch < 32; ch++)
-                        if (okx && oBase + ch < p.O) yrow[ch * chStep] = st[ch * STAGE_PITCH + lane];
-                    __syncwarp();
+                    if (col >= p.colBase && col < colEnd && ox < p.OW) {
+                        float* yp = p.y + (((size_t)n * p.O + o0 + warp) * p.OH + oy) * (size_t)p.OW + ox;
+                        const float* sp = stage + warp * STAGE_PITCH + lane;
+                        for (int r = warp; r < nrows; r += 4) {
+                            *yp = *sp;
+                            yp += 4 * chStep;
+                            sp += 4 * STAGE_PITCH;
+                        }
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");          // block stored: the staging buffer is free again
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -231,18 +249,20 @@ bool plan_tc3(Tc3Params& p)
                 const int need = (accStages - 1) * stageCols + (2 * r - 1) * cw + ((cw + 31) & ~31);
                 if (need > 512) continue;
                 const int xGroup = (r + 2) * npx * 128;
-                int wSlots = (kSmemLimit3 - 1024 - 4 * 32 * STAGE_PITCH * 4 - 2 * xGroup) / W_SLOT_BYTES;
+                int wSlots = (kSmemLimit3 - 1024 - 4 * 32 * STAGE_PITCH * 4 - 2 * xGroup) / p.wSlotBytes;
                 if (wSlots > kMaxWSlots) wSlots = kMaxWSlots;
                 if (wSlots < 3) continue;
+                const bool resident = wSlots >= 9 * p.kChunks;
+                if (resident) wSlots = 9 * p.kChunks;
                 const int s = npx - 4;
                 const long long tiles = (long long)((p.OW + s - 1) / s) * ((p.OH + r - 1) / r);
                 const double mma = 18.0 * r * npx;
-                const double load = (9.0 * (p.O < 128 ? p.O : 128) * 128 + (double)xGroup) / 40.0;
+                const double load = ((resident ? 0.0 : 9.0 * p.wSlotBytes) + (double)xGroup) / 40.0;
                 const double cost = (double)tiles * (mma > load ? mma : load);
                 if (cost < best) {
                     best = cost; found = true;
                     p.NPX = npx; p.R = r; p.CW = cw; p.S = s; p.accStages = accStages; p.accStageCols = stageCols;
-                    p.wSlots = wSlots; p.xGroupBytes = xGroup;
+                    p.wSlots = wSlots; p.xGroupBytes = xGroup; p.resident = resident ? 1 : 0;
                     int cols = 32;
                     while (cols < need) cols <<= 1;
                     p.tmemCols = cols;
@@ -277,6 +297,8 @@ int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int 
     p.kChunks = (I + BK3 - 1) / BK3;
     p.xoff = pad == 2 ? 4 : 0;
     p.colBase = pad == 2 ? 4 : 2;
+    p.wRows = O >= 128 ? 128 : (O + 7) & ~7;
+    p.wSlotBytes = p.wRows * BK3 * 4;
     if (!plan_tc3(p)) return SG3_E_NOKERNEL;
     p.tilesX = (p.OW + p.S - 1) / p.S;
     p.tilesY = (p.OH + p.R - 1) / p.R;
@@ -295,11 +317,11 @@ int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int 
     {
         const uint64_t dims[4] = {(uint64_t)I, (uint64_t)O, 9, (uint64_t)N};
         const uint64_t strides[3] = {(uint64_t)ldw * 4, (uint64_t)ldw * O * 4, (uint64_t)ldw * O * 9 * 4};
-        const uint32_t box[4] = {BK3, 128, 1, 1};
+        const uint32_t box[4] = {BK3, (uint32_t)p.wRows, 1, 1};
         if (!sg3_make_tensor_map(&mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, wtap, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
             return SG3_E_NOKERNEL;
     }
-    const int smemBytes = 2 * p.xGroupBytes + p.wSlots * W_SLOT_BYTES + 4 * 32 * STAGE_PITCH * 4 + 1024;
+    const int smemBytes = 2 * p.xGroupBytes + p.wSlots * p.wSlotBytes + 4 * 32 * STAGE_PITCH * 4 + 1024;
     static std::once_flag once;
     static cudaError_t attrErr = cudaSuccess;
     std::call_once(once, [] { attrErr = cudaFuncSetAttribute(modconv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3); });

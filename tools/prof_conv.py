@@ -7,12 +7,14 @@ from sg3_b200 import capi
 from oracle import sg3_oracle as orc
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 CFG = sys.argv[2] if len(sys.argv) > 2 else 'R'
+ONLY = sys.argv[3] if len(sys.argv) > 3 else None
 if CFG == 'R':
     _, specs = orc.layer_specs(1024, channel_base=65536, channel_max=1024, conv_kernel=1, use_radial_filters=True)
 else:
     _, specs = orc.layer_specs(1024, channel_base=32768, channel_max=512, conv_kernel=3, use_radial_filters=False)
 tot = 0; tot_ideal = 0
 for sp in specs:
+    if ONLY and not sp['name'].startswith(ONLY + '_'): continue
     I, O, H = sp['in_channels'], sp['out_channels'], sp['in_size']
     k = sp.get('conv_kernel', 1)
     if not sp.get('is_torgb', False) and CFG == 'T': k = 3
