@@ -13,6 +13,7 @@ struct BiasActParams {
     const void* x; const void* b; const void* xref; const void* yref; const void* dy; void* y;
     int64_t sizeX; int32_t sizeB; int64_t stepB;
     int grad; float alpha, gain, clamp;
+    int biasMode;      // 0: none; 1: one bias per 16-byte packet, 32-bit index math; 2: per element, 32-bit; 3: per element, 64-bit
 };
 
 template <class S> struct ActConst {
@@ -89,7 +90,8 @@ __device__ __forceinline__ S bias_act_one(S x, S b, S xref, S yref, S dy, int gr
     S y;
     if (grad == 0) {
         y = Act<A, S>::f(x + b, alpha) * gain;
-        if (clamp >= 0) y = (y > -clamp && y < clamp) ? y : (y >= 0 ? clamp : -clamp);
+        // same results as (y > -c && y < c) ? y : (y >= 0 ? c : -c), including NaN -> -c, in two min/max instructions
+        if (clamp >= 0) y = min(max(y, -clamp), clamp);
         return y;
     }
     S xr = xref + b;
@@ -132,10 +134,16 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActParams p)
             if (yref) yr[0] = yref[base];
             if (dy)   ds[0] = dy[base];
         }
+        // Bias index (i / stepB) % sizeB: the 64-bit divisions of the general form cost more than the memory traffic of
+        // the whole packet, so the common layouts take a cheaper route (NCHW with H*W a multiple of the packet: one
+        // 32-bit division per packet).
+        S bvec = (S)0;
+        if (p.biasMode == 1) bvec = ld_as<T>(b + ((uint32_t)base / (uint32_t)p.stepB) % (uint32_t)p.sizeB);
 #pragma unroll
         for (int j = 0; j < VN; j++) {
-            S bv = (S)0;
-            if (b) bv = ld_as<T>(b + ((base + j) / p.stepB) % p.sizeB);
+            S bv = bvec;
+            if (p.biasMode == 2) bv = ld_as<T>(b + (((uint32_t)base + j) / (uint32_t)p.stepB) % (uint32_t)p.sizeB);
+            else if (p.biasMode == 3) bv = ld_as<T>(b + ((base + j) / p.stepB) % p.sizeB);
             S r = bias_act_one<A, S>(ld_as<T>(xs + j), bv, xref ? ld_as<T>(xr + j) : (S)0, yref ? ld_as<T>(yr + j) : (S)0,
                                      dy ? ld_as<T>(ds + j) : (S)1, p.grad, alpha, gain, clamp);
             st_as<T>(out + j, r);
@@ -161,8 +169,13 @@ int launch_bias_act(const BiasActParams& p, cudaStream_t stream)
     const int64_t cap = (int64_t)sg3_sm_count() * 16;    // 16 CTAs of 256 threads per SM, grid-stride beyond that
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (vec) bias_act_kernel<T, A, true><<<(unsigned)blocks, threads, 0, stream>>>(p);
-    else     bias_act_kernel<T, A, false><<<(unsigned)blocks, threads, 0, stream>>>(p);
+    BiasActParams q = p;
+    const bool small = p.sizeX <= 0xffffffffLL && p.stepB <= 0xffffffffLL;
+    if (!p.b) q.biasMode = 0;
+    else if (small && vec && p.stepB % VN == 0) q.biasMode = 1;
+    else q.biasMode = small ? 2 : 3;
+    if (vec) bias_act_kernel<T, A, true><<<(unsigned)blocks, threads, 0, stream>>>(q);
+    else     bias_act_kernel<T, A, false><<<(unsigned)blocks, threads, 0, stream>>>(q);
     return sg3_launch_status();
 }
 
