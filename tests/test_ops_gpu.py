@@ -337,3 +337,40 @@ def test_fused_dense_up_forward_and_sep_down4(ops):
         res = fl._fused(cu(x), cu(fu), cu(fd), cu(b), None, 0, 0, cfg, False)
         assert res is not None
         assert rel_err(res[0].cpu().numpy(), ref) < TOL32
+
+
+# ---------------------------------------------------------------------------------------------
+# upfirdn2d fast paths (1-D polyphase kernels, small dense filters) vs the CPU oracle.
+
+UPFIRDN_FAST = [
+    # name, taps (1-D -> separable two-pass; 2-D -> dense), up, down, padding, flip, shape
+    ('sep12_up2', 12, 2, 1, [11, 10, 11, 10], False, (2, 3, 37, 45)),
+    ('sep24_up4', 24, 4, 1, [-2, -5, -2, -5], False, (1, 4, 29, 33)),
+    ('sep12_down2', 12, 1, 2, 0, False, (2, 3, 70, 86)),
+    ('sep24_down4', 24, 1, 4, [3, 1, 2, 0], True, (1, 2, 90, 101)),
+    ('sep8_same', 8, 1, 1, [4, 3, 4, 3], True, (2, 2, 33, 65)),
+    ('sep12_up2_crop', 12, 2, 1, [-3, 7, 5, -4], False, (1, 2, 40, 40)),
+    ('dense4_filter', (4, 4), 1, 1, [2, 1, 2, 1], False, (2, 3, 50, 67)),
+    ('dense4_up2', (4, 4), 2, 1, [2, 1, 2, 1], False, (2, 3, 31, 35)),
+    ('dense4_down2', (4, 4), 1, 2, [1, 1, 1, 1], True, (2, 3, 64, 70)),
+    ('dense3x4_up4', (3, 4), 4, 1, [5, 2, 3, 1], False, (1, 2, 17, 19)),
+    ('dense8_up2', (8, 8), 2, 1, [4, 3, 4, 3], False, (1, 2, 21, 23)),
+]
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.float16])
+@pytest.mark.parametrize('case', UPFIRDN_FAST, ids=[c[0] for c in UPFIRDN_FAST])
+def test_upfirdn2d_fast_paths(ops, case, dtype):
+    from oracle import sg3_oracle as orc
+    name, taps, up, down, padding, flip, shape = case
+    rng = np.random.RandomState(len(name))
+    f = rng.randn(*((taps,) if isinstance(taps, int) else taps)).astype(np.float32)
+    x = rng.randn(*shape).astype(np.float32)
+    if dtype == torch.float16:
+        x = x.astype(np.float16).astype(np.float32)
+    before = ops.capi.lib().sg3_launch_count()
+    y = ops.upfirdn2d.upfirdn2d(cu(x).to(dtype), cu(f), up=up, down=down, padding=padding, flip_filter=flip, gain=up * up)
+    assert ops.capi.lib().sg3_launch_count() - before == (2 if isinstance(taps, int) else 1)
+    ref = orc.upfirdn2d(x, f, up=up, down=down, padding=padding, flip_filter=flip, gain=up * up)
+    assert y.shape == ref.shape
+    assert rel_err(y.float().cpu().numpy(), ref) < (TOL32 if dtype == torch.float32 else 2e-3)
