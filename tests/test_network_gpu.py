@@ -264,3 +264,18 @@ def test_modconv_tap_major_weights(pkg):
     a = pkg.modulated_conv.modconv_weights(cu(w), cu(s), True, torch.tensor(0.7).cuda())[:, :, :19 * 9].reshape(3, 37, 19, 9)
     b = pkg.modulated_conv.modconv_weights(cu(w), cu(s), True, torch.tensor(0.7).cuda(), tap_major=True)[:, :, :, :19]
     assert torch.equal(a.permute(0, 3, 1, 2), b)
+
+
+def test_host_pipeline_matches_direct_call(pkg):
+    """sharding.HostPipeline (pinned host in/out, copies overlapped with the next forward) returns the same images."""
+    from sg3_b200 import sharding
+    G, g = _build(pkg, 'tinyR')
+    ws = cu(g.z['tinyR/ws'])
+    ref = G.synthesis(ws, noise_mode='const', force_fp32=True).cpu()
+    ws_host = ws.cpu().pin_memory()
+    outs = [torch.empty_like(ref).pin_memory() for _ in range(2)]
+    pipe = sharding.HostPipeline(G, 'cuda')
+    for i in range(5):
+        pipe.submit(ws_host, outs[i & 1])
+    pipe.finish()
+    assert torch.equal(outs[0], ref) and torch.equal(outs[1], ref)
