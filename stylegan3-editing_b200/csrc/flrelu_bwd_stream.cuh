@@ -268,6 +268,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     };
 
     // ---- stage H: horizontal down filter of the finished rows, store ----
+    // store address of the first row retired by group g (down 2: row 2g-5, column 2*lane; down 4: row g-5, column lane)
+    char* outRow = yPlane + (long long)(oy0 - 5) * p.ys[2] + (long long)(ox0 + (DOWN == 2 ? 2 * lane : lane)) * p.ys[3];
     auto stageH = [&](int g) {
         if (DOWN == 2) {
             const int oA = 2 * g - 5, oB = 2 * g - 4;
@@ -283,24 +285,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             if (oxl < tws) {
                 const bool two = oxl + 1 < tws;
                 if (oA >= 0 && oA < chs) {
-                    T* dst = (T*)(yPlane + (long long)(oy0 + oA) * p.ys[2] + (long long)(ox0 + oxl) * p.ys[3]);
-                    st_as<T>(dst, h0.x);
-                    if (two) st_as<T>((T*)((char*)dst + p.ys[3]), h1.x);
+                    st_as<T>((T*)outRow, h0.x);
+                    if (two) st_as<T>((T*)(outRow + p.ys[3]), h1.x);
                 }
                 if (oB >= 0 && oB < chs) {
-                    T* dst = (T*)(yPlane + (long long)(oy0 + oB) * p.ys[2] + (long long)(ox0 + oxl) * p.ys[3]);
-                    st_as<T>(dst, h0.y);
-                    if (two) st_as<T>((T*)((char*)dst + p.ys[3]), h1.y);
+                    st_as<T>((T*)(outRow + p.ys[2]), h0.y);
+                    if (two) st_as<T>((T*)(outRow + p.ys[2] + p.ys[3]), h1.y);
                 }
             }
+            outRow += 2 * p.ys[2];
         } else {
             const int o = g - 5;
             const int base = min(4 * lane, kBW - 24);
             float h = 0.f;
 #pragma unroll
             for (int q = 0; q < 24; q++) h = fmaf(sV[base + q].x, p.fd[q], h);
-            if (lane < tws && o >= 0 && o < chs)
-                st_as<T>((T*)(yPlane + (long long)(oy0 + o) * p.ys[2] + (long long)(ox0 + lane) * p.ys[3]), h);
+            if (lane < tws && o >= 0 && o < chs) st_as<T>((T*)outRow, h);
+            outRow += p.ys[2];
         }
     };
 

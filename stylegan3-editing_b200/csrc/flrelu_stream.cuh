@@ -436,6 +436,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
 #pragma unroll
     for (int h = 0; h < 7; h++) dSlot[h] = __shfl_sync(0xffffffffu, swz(2 * dl + h), lane);   // opaque, see cSlot
 
+    // store address of output row 2g-5 (the first row retired by group g), column 2*lane of this strip
+    char* outRow = yPlane + (long long)(oy0 - 5) * p.ys[2] + (long long)(ox0 + 2 * lane) * p.ys[3];
     auto stageD = [&](int g, int rot) {
         const float4* planeE = sC;
         const float4* planeO = sC + G::XH;
@@ -516,16 +518,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
         if (oxl < tws) {
             const bool two = oxl + 1 < tws;
             if (oA >= 0 && oA < chs) {
-                T* dst = (T*)(yPlane + (long long)(oy0 + oA) * p.ys[2] + (long long)(ox0 + oxl) * p.ys[3]);
-                st_as<T>(dst, a0);
-                if (two) st_as<T>((T*)((char*)dst + p.ys[3]), a1);
+                st_as<T>((T*)outRow, a0);
+                if (two) st_as<T>((T*)(outRow + p.ys[3]), a1);
             }
             if (oB >= 0 && oB < chs) {
-                T* dst = (T*)(yPlane + (long long)(oy0 + oB) * p.ys[2] + (long long)(ox0 + oxl) * p.ys[3]);
-                st_as<T>(dst, b0);
-                if (two) st_as<T>((T*)((char*)dst + p.ys[3]), b1);
+                st_as<T>((T*)(outRow + p.ys[2]), b0);
+                if (two) st_as<T>((T*)(outRow + p.ys[2] + p.ys[3]), b1);
             }
         }
+        outRow += 2 * p.ys[2];             // the lane's store address walks down two output rows per group
     };
 
     // ---- schedule -----------------------------------------------------------------------------------
