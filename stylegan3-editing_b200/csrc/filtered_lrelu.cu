@@ -107,6 +107,9 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
         const float sd = d->fd ? (fdH == 0 ? d->fd[0] * d->fd[0] : d->fd[0]) : 1.0f;
         return sg3_flrelu_pointwise(d, su, sd, (cudaStream_t)stream);
     }
+    // The stream kernels fold the gain into the up-filter taps and evaluate lrelu(v) as max(v, slope * v): that needs a
+    // positive gain and a slope in [0, 1] (every StyleGAN3 layer: sqrt(2), 0.2).  Anything else takes the generic composition.
+    if (d->signMode != SG3_SIGNS_READ && (!(d->gain > 0.f) || !(d->slope >= 0.f && d->slope <= 1.f))) return SG3_E_NOKERNEL;
     if (is_dense_up_shape(d->up, d->down, fuW, fuH, fdW, fdH)) {
         if (d->signMode == SG3_SIGNS_WRITE) return SG3_E_NOKERNEL;
         if ((long long)d->inW * (d->xStride[3] < 0 ? -d->xStride[3] : d->xStride[3]) > 0x7fffffffLL) return SG3_E_NOKERNEL;

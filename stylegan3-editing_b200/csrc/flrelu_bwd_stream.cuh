@@ -223,8 +223,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
-                    const float rr = fmaf(fabsf(v[q]), p.lreluB, v[q] * p.lreluA);
-                    v[q] = fminf(fmaxf(rr, -p.clamp), p.clamp);
+                    float rr;                       // lrelu + lower clamp in one 3-input max (slope in [0, 1], host-checked)
+                    asm("max.f32 %0, %1, %2, %3;" : "=f"(rr) : "f"(v[q]), "f"(v[q] * p.slope), "f"(-p.clamp));
+                    v[q] = fminf(rr, p.clamp);
                 }
             }
             rowv[j][0] = make_float2(v[0], v[1]);

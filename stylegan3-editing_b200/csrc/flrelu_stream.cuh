@@ -114,7 +114,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float t, float2 c) { return __
 __device__ __forceinline__ int swz(int xh) { return xh ^ ((xh >> 3) & 1); }
 
 // leaky ReLU + clamp of two values that already carry the gain; 2-bit sign codes in WRITE mode.
-//   NONE : v*a + |v|*b (one packed FMUL2 + FFMA with |.| source modifier), then clamp by two FMNMX
+//   NONE : max3(v, slope*v, -clamp) then min(., clamp): one packed FMUL2, one FMNMX3 and one FMNMX per value
 //   WRITE: same value, plus code = clamped ? 2 : negative ? 1 : 0
 //   READ : backward pass: scale by {1, slope, 0} according to the stored code, no clamp
 template <int MODE>
@@ -127,13 +127,18 @@ __device__ __forceinline__ float2 act2(float2 v, const Params& p, unsigned rc0, 
         if (rc1 & 2u) v.y = 0.f;
         return v;
     }
-    const float2 va = __fmul2_rn(v, make_float2(p.lreluA, p.lreluA));
-    const float r0 = fmaf(fabsf(v.x), p.lreluB, va.x), r1 = fmaf(fabsf(v.y), p.lreluB, va.y);
+    // lrelu(v) = max(v, slope * v) for 0 <= slope <= 1 (checked on the host); the lower clamp rides in the same 3-input max
+    const float2 sv = __fmul2_rn(v, make_float2(p.slope, p.slope));
     if (MODE == SG3_SIGNS_WRITE) {
+        const float r0 = fmaxf(v.x, sv.x), r1 = fmaxf(v.y, sv.y);
         wc0 = (fabsf(r0) > p.clamp) ? 2u : ((v.x < 0.f) ? 1u : 0u);
         wc1 = (fabsf(r1) > p.clamp) ? 2u : ((v.y < 0.f) ? 1u : 0u);
+        return make_float2(fminf(fmaxf(r0, -p.clamp), p.clamp), fminf(fmaxf(r1, -p.clamp), p.clamp));
     }
-    return make_float2(fminf(fmaxf(r0, -p.clamp), p.clamp), fminf(fmaxf(r1, -p.clamp), p.clamp));
+    float r0, r1;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r0) : "f"(v.x), "f"(sv.x), "f"(-p.clamp));
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r1) : "f"(v.y), "f"(sv.y), "f"(-p.clamp));
+    return make_float2(fminf(r0, p.clamp), fminf(r1, p.clamp));
 }
 
 // FD: 0 = separable down filter, 1 = dense 12x12, 2 = dense 12x12 with fd2[a][b] == fd2[a][11-b]
