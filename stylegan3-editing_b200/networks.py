@@ -132,16 +132,26 @@ class SynthesisInput(torch.nn.Module):
         freqs = freqs @ m[:, :2, :2]
         # Attenuate frequencies pushed beyond the band limit by the user transform.
         amps = (1 - (freqs.norm(dim=2) - self.bandwidth) / (self.sampling_rate / 2 - self.bandwidth)).clamp(0, 1)
-        theta = torch.eye(2, 3, device=device)
-        theta[0, 0] = 0.5 * self.size[0] / self.sampling_rate
-        theta[1, 1] = 0.5 * self.size[1] / self.sampling_rate
-        grid = torch.nn.functional.affine_grid(theta.unsqueeze(0), [1, 1, self.size[1], self.size[0]], align_corners=False)
+        grid = self._sampling_grid(device)
         x = (grid.unsqueeze(3) @ freqs.permute(0, 2, 1).unsqueeze(1).unsqueeze(2)).squeeze(3)     # [n, h, w, c]
         x = torch.sin((x + phases.unsqueeze(1).unsqueeze(2)) * (np.pi * 2)) * amps.unsqueeze(1).unsqueeze(2)
         x = x @ (self.weight / np.sqrt(self.channels)).t()
         x = x.permute(0, 3, 1, 2)
         _shape_is(x, [n, self.channels, int(self.size[1]), int(self.size[0])])
         return x
+
+    def _sampling_grid(self, device):
+        """The constant sampling grid of :236-239 (depends on size and sampling rate only).  Built once per device with
+        host-side scalars, so the forward itself contains no host-to-device copy and can be captured in a CUDA graph."""
+        g = getattr(self, '_grid_cache', None)
+        if g is None or g.device != device:
+            theta = torch.eye(2, 3)
+            theta[0, 0] = 0.5 * self.size[0] / self.sampling_rate
+            theta[1, 1] = 0.5 * self.size[1] / self.sampling_rate
+            g = torch.nn.functional.affine_grid(theta.unsqueeze(0).to(device), [1, 1, int(self.size[1]), int(self.size[0])],
+                                                align_corners=False)
+            self._grid_cache = g
+        return g
 
     def extra_repr(self):
         return (f'w_dim={self.w_dim:d}, channels={self.channels:d}, size={list(self.size)},\n'
@@ -325,3 +335,37 @@ class Generator(torch.nn.Module):
     def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False, **synthesis_kwargs):
         ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff, update_emas=update_emas)
         return self.synthesis(ws, update_emas=update_emas, **synthesis_kwargs)
+
+
+class GraphedSynthesis:
+    """CUDA-graph replay of `SynthesisNetwork.forward` for one (batch, dtype) signature.
+
+    A forward of the 1024^2 generator is ~300 kernel launches of which only ~45 are heavy; at batch 1-8 (ReStyle inversion,
+    PTI, video frames) the Python / launch overhead of the ~250 small ones is comparable to the GPU time (SURVEY.md 8f,
+    rank 2).  This wrapper captures one eager forward into a `torch.cuda.CUDAGraph` -- every sg3_b200 kernel launches on
+    the capturing stream, taps and TMA tensor maps travel in the launch parameters, nothing synchronises with the host --
+    and replays it: `img = graphed(ws)` copies `ws` into the static input and returns the static output (valid until the
+    next call).  Inference only (`torch.no_grad`); the generator's weights are read at replay time, so in-place weight
+    updates (PTI) are seen, but `input.transform` must be updated in place as well.
+    """
+
+    def __init__(self, synthesis, ws_example, **layer_kwargs):
+        self.synthesis = synthesis
+        self.kw = dict(noise_mode='const', force_fp32=True)
+        self.kw.update(layer_kwargs)
+        self.ws = ws_example.detach().clone()
+        side = torch.cuda.Stream(self.ws.device)
+        side.wait_stream(torch.cuda.current_stream(self.ws.device))
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(2):                                  # warm-up: filter tap caches, allocator pools, lazy inits
+                self.synthesis(self.ws, **self.kw)
+        torch.cuda.current_stream(self.ws.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.img = self.synthesis(self.ws, **self.kw)
+
+    def __call__(self, ws):
+        assert ws.shape == self.ws.shape and ws.dtype == self.ws.dtype
+        self.ws.copy_(ws, non_blocking=True)
+        self.graph.replay()
+        return self.img

@@ -279,3 +279,15 @@ def test_host_pipeline_matches_direct_call(pkg):
         pipe.submit(ws_host, outs[i & 1])
     pipe.finish()
     assert torch.equal(outs[0], ref) and torch.equal(outs[1], ref)
+
+
+def test_graphed_synthesis_matches_eager(pkg):
+    """networks.GraphedSynthesis: CUDA-graph replay of the synthesis forward returns the eager images, also for new latents."""
+    G, g = _build(pkg, 'tinyT')
+    ws = cu(g.z['tinyT/ws'])
+    gs = pkg.networks.GraphedSynthesis(G.synthesis, ws)
+    ref = G.synthesis(ws, noise_mode='const', force_fp32=True)
+    assert torch.equal(gs(ws), ref)
+    ws2 = ws.flip(0) * 0.9
+    ref2 = G.synthesis(ws2, noise_mode='const', force_fp32=True)
+    assert torch.equal(gs(ws2), ref2)
