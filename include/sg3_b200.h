@@ -135,13 +135,15 @@ int sg3_upfirdn2d(const void* x, void* y, const float* f,
  *   wmod[n][o][i][kh][kw] = w*rsqrt(mean w^2) * s*rsqrt(mean s^2) * rsqrt(sum(.)^2+1e-8) * input_gain
  * w [O][I][k][k] f32, s [N][I] f32, input_gain: NULL, or f32 with gainMode 1 = scalar,
  * 2 = [I], 3 = [N][I].  wmod is f32 [N][O][ldw] with row pitch ldw >= I*k*k floats (zero padded;
- * the tensor-core path needs ldw % 4 == 0); if round_tf32 != 0 each value is
- * rounded to the nearest TF32 so the tensor-core contraction sees unbiased operands.
+ * the tensor-core path needs ldw % 4 == 0); round_tf32 = 1: each value is rounded to the nearest TF32 so the
+ * tensor-core contraction sees unbiased operands; round_tf32 = 2: wmod is written as float16 [N][O][ldw] (ldw % 8 == 0),
+ * the weight operand of the fp16 tensor-core contraction (what the reference's w.to(x.dtype) produces for fp16 layers).
  * scratch: >= 4 bytes of device memory (batch-global style norm).
  *
  * sg3_modconv_fwd: y[n][o][p] = sum_{i,tap} wmod[n][o][i][tap] * x[n][i][p + tap - pad]
  * x [N][I][H][W] contiguous, y [N][O][H+2pad-k+1][W+2pad-k+1] contiguous, dtype f32.
  * mathMode 0: FP32 SIMT (exact fp32 accumulate);  1: TF32 tcgen05 implicit GEMM.
+ * dtype f16 (mathMode 1, k = 1, H*W % 8 == 0): x, y and wmod are float16, kind::f16 MMAs with fp32 accumulation.
  * ---------------------------------------------------------------------- */
 int sg3_modconv_weights(const float* w, const float* s, const float* input_gain, int gainMode,
                         float* wmod, float* scratch,

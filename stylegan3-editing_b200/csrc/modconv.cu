@@ -11,6 +11,7 @@
 int sg3_modconv_wgrad_tc(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, cudaStream_t stream);
 int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw, cudaStream_t stream);
 int sg3_modconv_tc3_supported(int I, int O, int H, int W, int k, int pad);
+int sg3_modconv_fwd_tc_f16(const void* x, const void* wmod, void* y, int N, int I, int O, int H, int W, int k, int pad, int ldw, cudaStream_t stream);
 int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
                        cudaStream_t stream);
 
@@ -83,8 +84,11 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
                                     : wmod + ((size_t)n * O + o) * ldw;
         const size_t dstStep = transpose == 1 ? (size_t)ldw : 1;
         const size_t tapStep = (size_t)O * ldw;
-        if (transpose == 0)
+        __half* dstH = reinterpret_cast<__half*>(wmod) + ((size_t)n * O + o) * ldw;       // fp16 operand form (layout 0 only)
+        if (transpose == 0 && roundTf32 != 2)
             for (int q = cnt + threadIdx.x; q < ldw; q += blockDim.x) dst[q] = 0.f;   // row padding (TMA pitch)
+        if (roundTf32 == 2)
+            for (int q = cnt + threadIdx.x; q < ldw; q += blockDim.x) dstH[q] = __float2half_rn(0.f);
         for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
             const int i = q / kk;
             float v = (wo[q] * rw) * (sn[i] * rs);
@@ -92,6 +96,7 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
             if (gainMode == 1) v *= gain[0];
             else if (gainMode == 2) v *= gain[i];
             else if (gainMode == 3) v *= gain[(size_t)n * I + i];
+            if (roundTf32 == 2) { dstH[q] = __float2half_rn(v); continue; }       // what the reference's w.to(x.dtype) does (:61)
             v = roundTf32 ? round_tf32(v) : v;
             if (transpose == 2) dst[(size_t)(q - i * kk) * tapStep + i] = v;
             else dst[q * dstStep] = v;
@@ -179,7 +184,8 @@ SG3_EXPORT int sg3_modconv_weights(const float* w, const float* s, const float* 
                                    int N, int I, int O, int k, int ldw, int demodulate, int round_tf32_flag, int transpose, void* stream)
 {
     if (!w || !s || !wmod || !scratch || N < 1 || I < 1 || O < 1 || k < 1) return SG3_E_INVALID;
-    if (transpose < 0 || transpose > 2) return SG3_E_INVALID;
+    if (transpose < 0 || transpose > 2 || round_tf32_flag < 0 || round_tf32_flag > 2) return SG3_E_INVALID;
+    if (round_tf32_flag == 2 && transpose != 0) return SG3_E_INVALID;
     if (transpose == 1 ? (k != 1 || ldw < O) : transpose == 2 ? (ldw < I) : (ldw < I * k * k)) return SG3_E_INVALID;
     if (gainMode < 0 || gainMode > 3 || (gainMode && !input_gain)) return SG3_E_INVALID;
     if ((int64_t)N * I > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
@@ -198,6 +204,8 @@ SG3_EXPORT int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
     if (!x || !wmod || !y || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || k < 1 || pad < 0) return SG3_E_INVALID;
     const bool tapMajor = mathMode == 1 && k > 1;             // the tensor-core kernels for k > 1 read tap-major weights
     if (ldw < (tapMajor ? I : I * k * k)) return SG3_E_INVALID;
+    if (dtype == SG3_F16)        // fp16 activations and fp16 weights (prologue format 2): tensor cores only, 1x1 kernels
+        return mathMode == 1 ? sg3_modconv_fwd_tc_f16(x, wmod, y, N, I, O, H, W, k, pad, ldw, (cudaStream_t)stream) : SG3_E_NOKERNEL;
     if (dtype != SG3_F32) return SG3_E_NOKERNEL;
     const int OH = H + 2 * pad - k + 1, OW = W + 2 * pad - k + 1;
     if (OH < 1 || OW < 1) return SG3_E_INVALID;

@@ -19,6 +19,7 @@
 // Every mbarrier wait is bounded (trap instead of hang).
 #include <cuda.h>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -32,7 +33,7 @@ constexpr int A_STAGE_BYTES = BM * BK * 4;      // 16 KB: 4 boxes of [32 rows][1
 constexpr int kThreads = 192;
 
 struct TcParams {
-    float* y;
+    void* y;               // float (HALF = false) or __half (HALF = true)
     int N, I, O, P;
     int BN;                // out-channels per tile (multiple of 16, <= 256)
     int tmemCols;          // power of two >= max(BN, 32)
@@ -46,9 +47,14 @@ struct TcParams {
 // Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA producer runs
 // ahead across tile boundaries (the smem ring never drains), the accumulator is double-buffered in TMEM so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
+// HALF: fp16 activations / weights / output with kind::f16 MMAs.  Same stage bytes (a stage is 64 input channels of
+// 2 bytes instead of 32 of 4): A = X^T is MN-major in the standard SWIZZLE_128B form (two TMA boxes [64 k][64 px] per
+// stage, 8-k atoms 1024 B apart, 64-pixel blocks one box apart), B = Wn K-major as before; K = 16 per instruction.
+template <bool HALF>
 __global__ void __launch_bounds__(kThreads, 1)
 modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const TcParams p)
 {
+    constexpr int KST = HALF ? 64 : 32;            // input channels per stage
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t barFull[kMaxStages], barEmpty[kMaxStages], barAccFull[2], barAccEmpty[2];
     __shared__ uint32_t tmemBase;
@@ -96,19 +102,28 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 const uint32_t full = smem_u32(&barFull[s]);
                 mbar_expect_tx_elect(full, (uint32_t)stageBytes);
                 const uint32_t aDst = tiles + s * stageBytes;
+                if (HALF) {
 #pragma unroll
-                for (int j = 0; j < 4; j++) tma_load_3d_elect(aDst + j * (BK * 128), &mapX, full, p0 + 32 * j, kt * BK, n);
-                tma_load_3d_elect(aDst + A_STAGE_BYTES, &mapW, full, kt * BK, o0, n);
+                    for (int j = 0; j < 2; j++) tma_load_3d_elect(aDst + j * (KST * 128), &mapX, full, p0 + 64 * j, kt * KST, n);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) tma_load_3d_elect(aDst + j * (BK * 128), &mapX, full, p0 + 32 * j, kt * BK, n);
+                }
+                tma_load_3d_elect(aDst + A_STAGE_BYTES, &mapW, full, kt * KST, o0, n);
             }
         }
     } else if (warp == 5) {
         // ---------------- MMA issuer (whole warp, elected lane issues) ----------------
         // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, A MN-major, B K-major, N, M=128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) |
+        // (HALF: A = B = F16 -> format fields 0)
+        const uint32_t idesc = (1u << 4) | (HALF ? 0u : (2u << 7) | (2u << 10)) | (1u << 15) | (0u << 16) |
                                ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
         // A (fp32, MN-major): 8 k-rows of 128 B per step = two 4-row swizzle atoms 512 B apart (SBO), 32-pixel blocks
         // BK*128 B apart (LBO), K step 1024 B;  B (K-major): K step 32 B inside the 128-byte row, 8-row groups 1024 B apart
-        const uint64_t dA = umma_desc(tiles, BK * 128, 512, kLayoutSw128Base32), dB = umma_desc(tiles + A_STAGE_BYTES, 16, 1024);
+        // A (fp16, MN-major): 16 k-rows per step = two 8-row atoms 1024 B apart (SBO), 64-pixel blocks KST*128 B apart (LBO)
+        const uint64_t dA = HALF ? umma_desc(tiles, KST * 128, 1024)
+                                 : umma_desc(tiles, BK * 128, 512, kLayoutSw128Base32);
+        const uint64_t dB = umma_desc(tiles + A_STAGE_BYTES, 16, 1024);
         const uint32_t aLo0 = (uint32_t)dA, aHi = (uint32_t)(dA >> 32), bLo0 = (uint32_t)dB, bHi = (uint32_t)(dB >> 32);
         const uint32_t stageStep = (uint32_t)stageBytes >> 4;
         uint32_t it = 0, tc = 0;                                  // k-iterations / tiles consumed so far
@@ -121,7 +136,8 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 const uint32_t s = it % p.stages;
                 mbar_wait(smem_u32(&barFull[s]), (it / p.stages) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                umma_tf32_x4<64, 2>(acc, aLo0 + s * stageStep, aHi, bLo0 + s * stageStep, bHi, idesc, kt > 0 ? 1u : 0u);
+                if (HALF) umma_f16_x4<128, 2>(acc, aLo0 + s * stageStep, aHi, bLo0 + s * stageStep, bHi, idesc, kt > 0 ? 1u : 0u);
+                else umma_tf32_x4<64, 2>(acc, aLo0 + s * stageStep, aHi, bLo0 + s * stageStep, bHi, idesc, kt > 0 ? 1u : 0u);
                 umma_commit_elect(smem_u32(&barEmpty[s]));        // frees the smem stage when these MMAs retire
             }
             umma_commit_elect(smem_u32(&barAccFull[as]));         // accumulator of this tile complete
@@ -136,7 +152,8 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             mbar_wait(smem_u32(&barAccFull[as]), (tc >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int pix = p0 + 32 * warp + lane;
-            float* yn = p.y + ((size_t)n * p.O) * (size_t)p.P;
+            typedef typename std::conditional<HALF, __half, float>::type OutT;
+            OutT* yn = (OutT*)p.y + ((size_t)n * p.O) * (size_t)p.P;
             for (int c = 0; c < p.BN; c += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + as * p.accCols + (uint32_t)c, r);
@@ -144,7 +161,7 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const int o = o0 + c + j;
-                        if (c + j < p.BN && o < p.O) yn[(size_t)o * p.P + pix] = __uint_as_float(r[j]);
+                        if (c + j < p.BN && o < p.O) st_as<OutT>(yn + (size_t)o * p.P + pix, __uint_as_float(r[j]));
                     }
                 }
             }
@@ -310,13 +327,16 @@ bool make_map3(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint6
 
 }  // namespace
 
-// x [N][I][P], wmod [N][O][ldw] (ldw % 4 == 0, zero beyond I), y [N][O][P]; k must be 1.
-int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
-                       cudaStream_t stream)
+namespace {
+
+// x [N][I][P], wmod [N][O][ldw] (zero beyond I), y [N][O][P]; k must be 1.  HALF: all three are fp16.
+template <bool HALF>
+int launch_fwd_tc(const void* x, const void* wmod, void* y, int N, int I, int O, int H, int W, int k, int pad, int ldw, cudaStream_t stream)
 {
     if (k != 1 || pad != 0) return SG3_E_NOKERNEL;
+    const int esz = HALF ? 2 : 4, kst = HALF ? 64 : 32;
     const long long P = (long long)H * W;
-    if (P % 4 != 0 || ldw % 4 != 0 || ldw < I) return SG3_E_NOKERNEL;        // TMA needs 16-byte global strides
+    if ((P * esz) % 16 != 0 || (ldw * esz) % 16 != 0 || ldw < I) return SG3_E_NOKERNEL;        // TMA needs 16-byte global strides
     if (((uintptr_t)x & 15) || ((uintptr_t)wmod & 15)) return SG3_E_NOKERNEL;
     if (P > INT32_MAX) return SG3_E_TOOLARGE;
 
@@ -329,7 +349,7 @@ int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I
     p.BN = bn;
     p.tilesN = (O + bn - 1) / bn;
     p.tilesM = (int)((P + BM - 1) / BM);
-    p.kTiles = (I + BK - 1) / BK;
+    p.kTiles = (I + kst - 1) / kst;
     p.accCols = (bn + 31) & ~31;
     int cols = 32;
     while (cols < 2 * p.accCols) cols <<= 1;                 // two accumulator stages, power-of-two allocation (<= 512)
@@ -338,18 +358,45 @@ int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I
     const long long ctas = p.totalTiles < sg3_sm_count() ? p.totalTiles : sg3_sm_count();   // persistent: one CTA per SM
 
     alignas(64) CUtensorMap mapX, mapW;
-    if (!make_map3(&mapX, x, (uint64_t)P, (uint64_t)I, (uint64_t)N, (uint64_t)P * 4, (uint64_t)P * I * 4, 32, BK,
-                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return SG3_E_NOKERNEL;
-    if (!make_map3(&mapW, wmod, (uint64_t)ldw, (uint64_t)O, (uint64_t)N, (uint64_t)ldw * 4, (uint64_t)ldw * O * 4, BK, (uint32_t)bn)) return SG3_E_NOKERNEL;
-
+    const CUtensorMapDataType dt = HALF ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    {
+        const uint64_t dims[3] = {(uint64_t)P, (uint64_t)I, (uint64_t)N};
+        const uint64_t strides[2] = {(uint64_t)P * esz, (uint64_t)P * I * esz};
+        const uint32_t box[3] = {HALF ? 64u : 32u, (uint32_t)kst, 1};
+        if (!sg3_make_tensor_map(&mapX, dt, 3, x, dims, strides, box, HALF ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+            return SG3_E_NOKERNEL;
+    }
+    {
+        const uint64_t dims[3] = {(uint64_t)ldw, (uint64_t)O, (uint64_t)N};
+        const uint64_t strides[2] = {(uint64_t)ldw * esz, (uint64_t)ldw * O * esz};
+        const uint32_t box[3] = {(uint32_t)kst, (uint32_t)bn, 1};
+        if (!sg3_make_tensor_map(&mapW, dt, 3, wmod, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return SG3_E_NOKERNEL;
+    }
     p.stages = bn > 128 ? 4 : 6;                            // 4 x 48 KB or 6 x <= 32 KB of operand stages
     const int smemBytes = p.stages * (A_STAGE_BYTES + bn * BK * 4) + 1024;
     static std::once_flag once;
     static cudaError_t attrErr = cudaSuccess;
-    std::call_once(once, [] { attrErr = cudaFuncSetAttribute(modconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    std::call_once(once, [] {
+        attrErr = cudaFuncSetAttribute(modconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (attrErr == cudaSuccess) attrErr = cudaFuncSetAttribute(modconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
     if (attrErr != cudaSuccess) return (int)attrErr;
-    modconv_tc_kernel<<<(unsigned)ctas, kThreads, smemBytes, stream>>>(mapX, mapW, p);
+    modconv_tc_kernel<HALF><<<(unsigned)ctas, kThreads, smemBytes, stream>>>(mapX, mapW, p);
     return sg3_launch_status();
+}
+
+}  // namespace
+
+int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
+                       cudaStream_t stream)
+{
+    return launch_fwd_tc<false>(x, wmod, y, N, I, O, H, W, k, pad, ldw, stream);
+}
+
+int sg3_modconv_fwd_tc_f16(const void* x, const void* wmod, void* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
+                           cudaStream_t stream)
+{
+    return launch_fwd_tc<true>(x, wmod, y, N, I, O, H, W, k, pad, ldw, stream);
 }
 
 // dy [N][O][P], x [N][I][P], dw [N][O][ldw] (zeroed by the caller; ldw >= I).

@@ -130,6 +130,28 @@ __device__ __forceinline__ void umma_tf32_x4(uint32_t d, uint32_t aLo, uint32_t 
           "n"(AS), "n"(BS), "n"(2 * AS), "n"(2 * BS), "n"(3 * AS), "n"(3 * BS) : "memory");
 }
 
+// Same for kind::f16 (fp16 operands, fp32 accumulate; K = 16 per instruction).
+template <int AS, int BS>
+__device__ __forceinline__ void umma_f16_x4(uint32_t d, uint32_t aLo, uint32_t aHi, uint32_t bLo, uint32_t bHi, uint32_t idesc,
+                                            uint32_t accumulateFirst)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q, t;\n\t.reg .b64 da, db;\n\t.reg .b32 al, bl;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "setp.eq.u32 t, %5, %5;\n\t"
+        "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "add.u32 al, %1, %7;\n\tadd.u32 bl, %3, %8;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+        "add.u32 al, %1, %9;\n\tadd.u32 bl, %3, %10;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t"
+        "add.u32 al, %1, %11;\n\tadd.u32 bl, %3, %12;\n\tmov.b64 da, {al, %2};\n\tmov.b64 db, {bl, %4};\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, t;\n\t}"
+        ::"r"(d), "r"(aLo), "r"(aHi), "r"(bLo), "r"(bHi), "r"(idesc), "r"(accumulateFirst),
+          "n"(AS), "n"(BS), "n"(2 * AS), "n"(2 * BS), "n"(3 * AS), "n"(3 * BS) : "memory");
+}
+
 // tcgen05.commit from the elected lane of a converged warp.
 __device__ __forceinline__ void umma_commit_elect(uint32_t bar)
 {

@@ -28,10 +28,11 @@ def _math_mode():
     return 'tf32' if torch.backends.cudnn.allow_tf32 else 'fp32'
 
 
-def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, transpose=False, tap_major=False):
+def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, transpose=False, tap_major=False, half=False):
     """[N, O, ldw >= I*k*k] float32 modulated (+demodulated, +input-gain) weights, rows zero padded  (:39-56).
     transpose=True (1x1 only): [N, I, ldw >= O], the weight operand of the input-gradient GEMM.
-    tap_major=True: [N, k*k, O, ldw >= I], the operand of the 3x3 tensor-core kernel."""
+    tap_major=True: [N, k*k, O, ldw >= I], the operand of the 3x3 tensor-core kernel.
+    half=True: float16 [N, O, ldw] (what `w.to(x.dtype)` of :61 produces for fp16 layers), operand of the fp16 tensor-core kernel."""
     capi.require_cuda(w, 'modulated_conv2d')
     O, I, kh, kw = w.shape
     assert kh == kw
@@ -48,7 +49,11 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, tr
         else:
             mode, g = 3, g.expand(N, I).contiguous()               # per (sample, input channel), broadcast like :55
     layout = 1 if transpose else (2 if tap_major else 0)
-    if tap_major:
+    if half:
+        assert not transpose and not tap_major
+        ldw = (I * kh * kw + 63) // 64 * 64
+        wmod = torch.empty([N, O, ldw], dtype=torch.float16, device=w.device)
+    elif tap_major:
         assert not transpose
         ldw = (I + 31) // 32 * 32
         wmod = torch.empty([N, kh * kw, O, ldw], dtype=torch.float32, device=w.device)
@@ -63,20 +68,20 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, tr
     with torch.cuda.device(w.device):
         rc = capi.lib().sg3_modconv_weights(w.data_ptr(), s.data_ptr(), g.data_ptr() if g is not None else None, mode,
                                             wmod.data_ptr(), scratch.data_ptr(), N, I, O, kh, ldw, int(bool(demodulate)),
-                                            int(bool(round_tf32)), layout, capi.stream_ptr(w.device))
+                                            2 if half else int(bool(round_tf32)), layout, capi.stream_ptr(w.device))
     capi.check(rc, 'sg3_modconv_weights')
     return wmod
 
 
 def conv_forward(x, wmod, O, k, padding, math):
-    """y[n,o] = sum_i wmod[n,o,i] (*) x[n,i] with zero padding; x float32 contiguous."""
+    """y[n,o] = sum_i wmod[n,o,i] (*) x[n,i] with zero padding; x float32 (or float16 with float16 weights) contiguous."""
     N, I, H, W = x.shape
     OH, OW = H + 2 * padding - k + 1, W + 2 * padding - k + 1
-    y = torch.empty([N, O, OH, OW], dtype=torch.float32, device=x.device)
+    y = torch.empty([N, O, OH, OW], dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
         ldw = wmod.shape[-1]
         rc = capi.lib().sg3_modconv_fwd(x.data_ptr(), wmod.data_ptr(), y.data_ptr(), N, I, O, H, W, k, padding, ldw,
-                                        1 if math == 'tf32' else 0, capi.SG3_F32, capi.stream_ptr(x.device))
+                                        1 if math == 'tf32' else 0, capi.dtype_code(x.dtype), capi.stream_ptr(x.device))
     capi.check(rc, 'sg3_modconv_fwd')
     return y
 
@@ -112,6 +117,15 @@ class _ModConv(torch.autograd.Function):
     def forward(ctx, x, w, s, input_gain, demodulate, padding, math):
         O, I, k, _ = w.shape
         xin = x.contiguous()
+        if (xin.dtype == torch.float16 and math == 'tf32' and k == 1 and padding == 0
+                and (xin.shape[2] * xin.shape[3]) % 8 == 0):
+            # fp16 layer (reference :61 casts the weights to fp16 and runs an fp16 cuDNN conv): fp16 tensor-core kernel,
+            # no up / down casts of the activations
+            wmod = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, half=True)
+            y = conv_forward(xin, wmod, O, k, padding, 'tf32')
+            ctx.save_for_backward(x, w, s, input_gain)
+            ctx.cfg = (demodulate, padding, math)
+            return y
         x32 = xin if xin.dtype == torch.float32 else xin.float()
         if math == 'tf32' and not tc_supported(I, O, x32.shape[2], x32.shape[3], k, padding):
             math = 'fp32'                  # shapes without a tensor-core kernel run the exact SIMT contraction

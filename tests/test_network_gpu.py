@@ -291,3 +291,38 @@ def test_graphed_synthesis_matches_eager(pkg):
     ws2 = ws.flip(0) * 0.9
     ref2 = G.synthesis(ws2, noise_mode='const', force_fp32=True)
     assert torch.equal(gs(ws2), ref2)
+
+
+@pytest.mark.parametrize('shape', TC_CASES, ids=['x'.join(map(str, s)) for s in TC_CASES])
+def test_modconv_tc_f16_vs_oracle(pkg, shape):
+    """fp16 tensor-core contraction (fp16 activations and weights, fp32 accumulate, fp16 store) vs the oracle on the same
+    fp16-rounded operands; tolerance 2e-3 of max |ref| (fp16 output rounding)."""
+    from oracle import sg3_oracle as orc
+    from sg3_b200 import capi
+    N, I, O, H, W = shape
+    if (H * W) % 8:
+        pytest.skip('fp16 TMA needs 16-byte plane pitch')
+    rng = np.random.RandomState(I + O)
+    x = rng.randn(N, I, H, W).astype(np.float16)
+    wm = (rng.randn(N, O, I) / np.sqrt(I)).astype(np.float16)
+    ldw = (I + 63) // 64 * 64
+    wpad = np.zeros((N, O, ldw), np.float16)
+    wpad[:, :, :I] = wm
+    xt, wt = cu(x), cu(wpad)
+    y = torch.empty(N, O, H, W, device='cuda', dtype=torch.float16)
+    rc = capi.lib().sg3_modconv_fwd(xt.data_ptr(), wt.data_ptr(), y.data_ptr(), N, I, O, H, W, 1, 0, ldw, 1, capi.SG3_F16,
+                                    capi.stream_ptr(xt.device))
+    assert rc == 0
+    torch.cuda.synchronize()
+    ref = orc.conv2d(x.astype(np.float32), wm.astype(np.float32).reshape(N, O, I, 1, 1), padding=0)
+    assert rel_err(y.float().cpu().numpy(), ref) < 2e-3
+
+
+def test_modconv_half_weights(pkg):
+    """The fp16 prologue output equals the fp32 prologue output rounded to fp16."""
+    rng = np.random.RandomState(6)
+    w, s = rng.randn(37, 70, 1, 1).astype(np.float32), rng.randn(3, 70).astype(np.float32)
+    a = pkg.modulated_conv.modconv_weights(cu(w), cu(s), True, torch.tensor(0.7).cuda())[:, :, :70]
+    b = pkg.modulated_conv.modconv_weights(cu(w), cu(s), True, torch.tensor(0.7).cuda(), half=True)
+    assert b.dtype == torch.float16 and b.shape[2] == 128
+    assert torch.equal(a.half(), b[:, :, :70]) and float(b[:, :, 70:].abs().max()) == 0.0
