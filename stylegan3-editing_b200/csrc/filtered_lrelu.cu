@@ -120,7 +120,6 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
         q.bs = d->bStride;
         q.px0 = d->px0; q.py0 = d->py0;
         q.slope = d->slope; q.clamp = d->clamp;
-        q.lreluA = 0.5f * (1.0f + d->slope); q.lreluB = 0.5f * (1.0f - d->slope);
         q.sH = d->sH; q.sWb = d->sWb; q.sx = d->sx; q.sy = d->sy;
         // correlation-ordered dense up taps FU'[a][b] (a separable filter is its outer product), scaled by up^2 * gain
         auto fuAt = [&](int a, int b) -> float {
@@ -176,8 +175,6 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
             p.tu[ph][k] = v;
             p.tv[ph][k] = v * d->gain;
         }
-    p.lreluA = 0.5f * (1.0f + d->slope);
-    p.lreluB = 0.5f * (1.0f - d->slope);
     const bool full = fdH != 0 && d->fd != nullptr;
     float fd2[fs::kDownTaps][fs::kDownTaps];
     for (int b = 0; b < fs::kDownTaps; b++)

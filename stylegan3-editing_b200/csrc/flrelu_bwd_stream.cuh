@@ -50,7 +50,6 @@ struct Params {
     long long xs[4], ys[4], bs;
     int px0, py0;
     float slope, clamp;
-    float lreluA, lreluB;
     int sH, sWb, sx, sy;
     int stripsX, chunksY, chunkRows;
     long long totalStrips;

@@ -85,7 +85,6 @@ struct Params {
     long long totalStrips;
     float tu[4][kTapsPerPhase];        // tu[p][k]: up taps of phase p, pre-scaled by UP (horizontal pass)
     float tv[4][kTapsPerPhase];        // vertical pass: tu * gain (the activation gain rides on the taps)
-    float lreluA, lreluB;              // lrelu(v) = v*lreluA + |v|*lreluB = v*(1+slope)/2 + |v|*(1-slope)/2
     float fdx[kDownTaps];              // separable down taps (correlation order), horizontal pass; unused when dense
     // Down taps as seen by the 6 physical accumulator slots of stage D for each of the 3 rotations (g % 3):
     // slot i holds logical accumulator k = (i + 2*rot) % 6, which pairs with filter rows 2k (half 0) and 2k+1
