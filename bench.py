@@ -304,6 +304,17 @@ def run_ours(args):
     fp32_peak_tfma = 148 * 128 * 1.965e9 / 1e12          # 37.2 TFMA/s at max SM clock
     fma_rate = fma_per_img * B * args.steps / (fl_ms * 1e-3) / 1e12 if fl_ms > 0 else 0.0
 
+    # measured DRAM traffic of the filtered_lrelu launches (ncu dram__bytes_read.sum + dram__bytes_write.sum, committed capture),
+    # scaled from the profiled batch to this step's batch; compare with `algorithmic_bytes`
+    traffic, traffic_note = None, 'no ncu traffic capture for this config'
+    try:
+        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_flrelu_traffic.json')))
+        if tr.get('config') == CFG_NAME:
+            traffic = tr['dram_bytes_per_image'] * B
+            traffic_note = 'bytes per step = ncu dram read+write per image (profiles/r01_flrelu_traffic.json, batch 2 capture) x per-GPU batch'
+    except Exception:
+        pass
+
     value = world * B * args.steps / (ms_total * 1e-3)
     out = dict(
         metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
@@ -318,7 +329,7 @@ def run_ours(args):
                  h2d_bytes_per_step=int(ws_host.numel() * 4), d2h_bytes_per_step=int(img_host[0].numel() * 4)),
         gpu_launches=int(launches),
         roofline=dict(bound='hbm', achieved=achieved, peak=hbm_peak, unit='GB/s', frac=achieved / hbm_peak,
-                      traffic=None, traffic_note='ncu --set full of the L11 launch (profiles/r01_flrelu_L11_ncu.md): dram read+write = 0.98x the algorithmic bytes',
+                      traffic=traffic, algorithmic_bytes=fl_bytes / args.steps, traffic_note=traffic_note,
                       kernel='filtered_lrelu (15 calls per step, all timed with CUDA events)',
                       launches_timed=n_calls, ms_per_step=fl_ms / args.steps,
                       peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s (of fallback)',
