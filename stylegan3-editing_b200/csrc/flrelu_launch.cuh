@@ -14,7 +14,11 @@ int launch_one(const Params& p, cudaStream_t stream)
     const int smem = kWarpsPerCta * Geo<UP>::warp_bytes(MODE);
     static std::once_flag once;
     static cudaError_t attrErr = cudaSuccess;
-    std::call_once(once, [&] { attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    std::call_once(once, [&] {
+        attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        // all of the SM's shared memory: five 44.5 KB CTAs (UP = 2) only fit with the maximum carve-out
+        if (attrErr == cudaSuccess) attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    });
     if (attrErr != cudaSuccess) return (int)attrErr;
     const long long ctas = (p.totalStrips + kWarpsPerCta - 1) / kWarpsPerCta;
     if (ctas > 0x7fffffffLL) return SG3_E_TOOLARGE;

@@ -146,7 +146,7 @@ __device__ __forceinline__ float2 act2(float2 v, const Params& p, unsigned rc0, 
 // image comes from the tensor map; the bias enters as the initial value of the stage-B accumulators).  Needs fp32,
 // unit pixel stride and 16-byte aligned row/plane strides; otherwise the register-prefetch path (TMA = false) runs.
 template <class T, int UP, int FD, int MODE, bool TMA>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_constant__ Params p)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(const __grid_constant__ Params p)
 {
     typedef Geo<UP> G;
     extern __shared__ __align__(128) unsigned char smem_raw[];
