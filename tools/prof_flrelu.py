@@ -1,4 +1,4 @@
-"""One filtered_lrelu launch at a BASELINE-size layer, for ncu: python tools/prof_flrelu.py [L11|L10|L12] [N]"""
+"""One filtered_lrelu launch at a BASELINE-size layer, for ncu: python tools/prof_flrelu.py [L11|L10|TL12|all|Tall] [N] [bwd]  (T prefix = config T)"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -6,9 +6,19 @@ import sg3_b200
 from oracle import sg3_oracle as orc
 which = sys.argv[1] if len(sys.argv) > 1 else 'L11'
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-_, specs = orc.layer_specs(1024, channel_base=65536, channel_max=1024, conv_kernel=1, use_radial_filters=True)
+cfgT = which.startswith('T')
+if cfgT:
+    which = which[1:]
+    _, specs = orc.layer_specs(1024, channel_base=32768, channel_max=512, conv_kernel=3, use_radial_filters=False)
+else:
+    _, specs = orc.layer_specs(1024, channel_base=65536, channel_max=1024, conv_kernel=1, use_radial_filters=True)
+if which == 'all':
+    import subprocess
+    for i in range(len(specs) - 1):
+        subprocess.run([sys.executable, __file__, ('T' if cfgT else '') + f'L{i}', str(N)])
+    sys.exit(0)
 sp = specs[int(which[1:])]
-C, size = sp['out_channels'], sp['in_size']
+C, size = sp['out_channels'], sp['in_size'] + sp['conv_kernel'] - 1
 x = torch.randn(N, C, size, size, device='cuda') * 2
 b = torch.randn(C, device='cuda')
 fu = torch.from_numpy(sp['up_filter']).cuda(); fd = torch.from_numpy(sp['down_filter']).cuda()
