@@ -237,36 +237,38 @@ constexpr int kSmemLimit3 = 224 * 1024;       // + 2 KB of static barriers stays
 // max(MMA clocks, operand bytes / 40 B/clk) over the tile shapes that fit TMEM (512 columns) and shared memory.
 bool plan_tc3(Tc3Params& p)
 {
+    // Per-tile time model fitted on B200 (tools/run_tc3_sweep.sh): a fixed 1700 clk of pipeline hand-over, the K loop
+    // (tensor core or operand stream, whichever is slower) and -- the accumulator is single-buffered -- the serial
+    // epilogue at ~530 clk per 32-column block.  Double-buffered accumulators only fit tiles of <= 96 pixels and
+    // measured slower than one large tile for every StyleGAN3-T layer, so they are not planned.
     double best = 1e300;
     bool found = false;
-    const int wantStages = p.kChunks <= 4 ? 2 : 1;        // short K loops: overlap the epilogue with the next tile
-    for (int pass = 0; pass < 2 && !found; pass++) {
-        const int accStages = pass == 0 ? wantStages : 1;
-        for (int npx = 64; npx <= 224; npx += 32) {
-            for (int r = 1; r <= 4; r++) {
-                const int cw = (npx + 4 + kAccPitchAlign - 1) / kAccPitchAlign * kAccPitchAlign, stageCols = 2 * r * cw;
-                // the last 32-column epilogue load of the last accumulator must stay inside the allocation
-                const int need = (accStages - 1) * stageCols + (2 * r - 1) * cw + ((cw + 31) & ~31);
-                if (need > 512) continue;
-                const int xGroup = (r + 2) * npx * 128;
-                int wSlots = (kSmemLimit3 - 1024 - 4 * 32 * STAGE_PITCH * 4 - 2 * xGroup) / p.wSlotBytes;
-                if (wSlots > kMaxWSlots) wSlots = kMaxWSlots;
-                if (wSlots < 3) continue;
-                const bool resident = wSlots >= 9 * p.kChunks;
-                if (resident) wSlots = 9 * p.kChunks;
-                const int s = npx - 4;
-                const long long tiles = (long long)((p.OW + s - 1) / s) * ((p.OH + r - 1) / r);
-                const double mma = 18.0 * r * npx;
-                const double load = ((resident ? 0.0 : 9.0 * p.wSlotBytes) + (double)xGroup) / 40.0;
-                const double cost = (double)tiles * (mma > load ? mma : load);
-                if (cost < best) {
-                    best = cost; found = true;
-                    p.NPX = npx; p.R = r; p.CW = cw; p.S = s; p.accStages = accStages; p.accStageCols = stageCols;
-                    p.wSlots = wSlots; p.xGroupBytes = xGroup; p.resident = resident ? 1 : 0;
-                    int cols = 32;
-                    while (cols < need) cols <<= 1;
-                    p.tmemCols = cols;
-                }
+    for (int npx = 64; npx <= 224; npx += 32) {
+        for (int r = 1; r <= 4; r++) {
+            const int cw = (npx + 4 + kAccPitchAlign - 1) / kAccPitchAlign * kAccPitchAlign, stageCols = 2 * r * cw;
+            // the last 32-column epilogue load of the last accumulator must stay inside the allocation
+            const int need = (2 * r - 1) * cw + ((cw + 31) & ~31);
+            if (need > 512) continue;
+            const int xGroup = (r + 2) * npx * 128;
+            int wSlots = (kSmemLimit3 - 1024 - 4 * 32 * STAGE_PITCH * 4 - 2 * xGroup) / p.wSlotBytes;
+            if (wSlots > kMaxWSlots) wSlots = kMaxWSlots;
+            if (wSlots < 3) continue;
+            const bool resident = wSlots >= 9 * p.kChunks;
+            if (resident) wSlots = 9 * p.kChunks;
+            const int s = npx - 4;
+            const long long tiles = (long long)((p.OW + s - 1) / s) * ((p.OH + r - 1) / r);
+            const double perMma = npx / 2.0 > 32.0 + npx / 4.0 ? npx / 2.0 : 32.0 + npx / 4.0;       // tools/tc_mma_bench.cu
+            const double mma = 36.0 * r * perMma;
+            const double load = ((resident ? 0.0 : 9.0 * p.wSlotBytes) + (double)xGroup) / 40.0;
+            const double epi = 530.0 * r * ((p.colBase + s + 31) / 32);
+            const double cost = (double)tiles * (1700.0 + p.kChunks * (mma > load ? mma : load) + epi);
+            if (cost < best) {
+                best = cost; found = true;
+                p.NPX = npx; p.R = r; p.CW = cw; p.S = s; p.accStages = 1; p.accStageCols = stageCols;
+                p.wSlots = wSlots; p.xGroupBytes = xGroup; p.resident = resident ? 1 : 0;
+                int cols = 32;
+                while (cols < need) cols <<= 1;
+                p.tmemCols = cols;
             }
         }
     }
