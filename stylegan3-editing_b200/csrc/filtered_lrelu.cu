@@ -64,8 +64,6 @@ SG3_EXPORT int sg3_filtered_lrelu_supported(int up, int down, int fuW, int fuH, 
 // Kernel instantiations live in flrelu_inst_*.cu (one translation unit per dtype x up factor, built in parallel).
 template <class T, int UP, int TMAFLAG> int flrelu_stream_launch(const fs::Params& p, int fdMode, int signMode, cudaStream_t stream);
 
-bool sg3_make_tensor_map(CUtensorMap* m, CUtensorMapDataType type, int rank, const void* base, const uint64_t* dims,
-                         const uint64_t* stridesBytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
 
 namespace {
 

@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "tensor_map.h"
 
 namespace {
 

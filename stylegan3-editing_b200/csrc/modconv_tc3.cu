@@ -27,10 +27,9 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "tensor_map.h"
 #include "tc_common.cuh"
 
-bool sg3_make_tensor_map(CUtensorMap* m, CUtensorMapDataType type, int rank, const void* base, const uint64_t* dims,
-                         const uint64_t* stridesBytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
 
 namespace {
 
