@@ -9,6 +9,7 @@
 
 #include "flrelu_bwd_stream.cuh"
 #include "flrelu_stream.cuh"
+#include "tensor_map.h"
 
 namespace fs = flrelu_stream;
 namespace fb = flrelu_bwd_stream;
