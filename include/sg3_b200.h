@@ -76,6 +76,10 @@ typedef struct sg3_flrelu_desc {
     int32_t sx, sy;                              /* sign offset added to upsampled coords */
     int32_t dtype;                               /* SG3_F32 / SG3_F16 */
     int32_t reserved;
+    float*  ysum;                                /* optional f32 [C]: the kernel ADDS sum_{n,h,w} y[n][c][h][w] (fp32 atomics;
+                                                    zero it first).  In the backward pass y = dx and this is the bias gradient
+                                                    (filtered_lrelu.py:268 computes dx.sum([0,2,3]) in a second pass).  NULL = off;
+                                                    ignored by the pointwise (1x1 filter) kernel: returns SG3_E_NOKERNEL there. */
 } sg3_flrelu_desc;
 
 /* Output and sign-tensor geometry (filtered_lrelu.cpp:69-93).  Any out pointer may be NULL. */

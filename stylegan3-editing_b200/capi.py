@@ -32,6 +32,7 @@ class FlreluDesc(ctypes.Structure):
         ('flip', ctypes.c_int32), ('signMode', ctypes.c_int32),
         ('sH', ctypes.c_int32), ('sWb', ctypes.c_int32), ('sx', ctypes.c_int32), ('sy', ctypes.c_int32),
         ('dtype', ctypes.c_int32), ('reserved', ctypes.c_int32),
+        ('ysum', ctypes.c_void_p),
     ]
 
 

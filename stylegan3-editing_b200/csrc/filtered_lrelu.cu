@@ -99,6 +99,8 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
     if (rc != 0) return rc;
     if (d->signMode != SG3_SIGNS_NONE && (!d->signs || d->sH < 1 || d->sWb < 1)) return SG3_E_INVALID;
     if (d->signMode == SG3_SIGNS_WRITE && (d->sx & 3)) return SG3_E_NOKERNEL;   // sign bytes must align with strips
+    // the channel sum of the outputs is produced by the sign-READ (backward) stream kernels only
+    if (d->ysum && (d->signMode != SG3_SIGNS_READ || is_pointwise(d->up, d->down, fuW, fuH, fdW, fdH))) return SG3_E_NOKERNEL;
     if (is_pointwise(d->up, d->down, fuW, fuH, fdW, fdH)) {
         // 1x1 "filters" are scalars (a separable 1-tap filter acts on both axes: squared); padding would change the size
         if (d->px0 != 0 || d->py0 != 0 || d->outW != d->inW || d->outH != d->inH) return SG3_E_NOKERNEL;
@@ -113,7 +115,7 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
         if (d->signMode == SG3_SIGNS_WRITE) return SG3_E_NOKERNEL;
         if ((long long)d->inW * (d->xStride[3] < 0 ? -d->xStride[3] : d->xStride[3]) > 0x7fffffffLL) return SG3_E_NOKERNEL;
         fb::Params q;
-        q.x = d->x; q.y = d->y; q.b = d->b; q.s = d->signs;
+        q.x = d->x; q.y = d->y; q.b = d->b; q.s = d->signs; q.ysum = d->ysum;
         q.N = d->N; q.C = d->C; q.inH = d->inH; q.inW = d->inW; q.outH = d->outH; q.outW = d->outW;
         for (int i = 0; i < 4; i++) { q.xs[i] = d->xStride[i]; q.ys[i] = d->yStride[i]; }
         q.bs = d->bStride;
@@ -154,7 +156,7 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
     }
 
     fs::Params p;
-    p.x = d->x; p.y = d->y; p.b = d->b; p.s = d->signs;
+    p.x = d->x; p.y = d->y; p.b = d->b; p.s = d->signs; p.ysum = d->ysum;
     p.N = d->N; p.C = d->C; p.inH = d->inH; p.inW = d->inW; p.outH = d->outH; p.outW = d->outW;
     for (int i = 0; i < 4; i++) { p.xs[i] = d->xStride[i]; p.ys[i] = d->yStride[i]; }
     p.bs = d->bStride;

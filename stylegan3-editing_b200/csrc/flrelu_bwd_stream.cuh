@@ -46,6 +46,7 @@ template <int DOWN> struct Geo {
 
 struct Params {
     const void* x; void* y; const void* b; const uint8_t* s;
+    float* ysum;                       // optional [C]: += sum of the outputs of channel c (the bias gradient)
     int N, C, inH, inW, outH, outW;
     long long xs[4], ys[4], bs;
     int px0, py0;
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     // ---- stage H: horizontal down filter of the finished rows, store ----
     // store address of the first row retired by group g (down 2: row 2g-5, column 2*lane; down 4: row g-5, column lane)
     char* outRow = yPlane + (long long)(oy0 - 5) * p.ys[2] + (long long)(ox0 + (DOWN == 2 ? 2 * lane : lane)) * p.ys[3];
+    float ySum = 0.f;                   // sum of the outputs this lane stored
     auto stageH = [&](int g) {
         if (DOWN == 2) {
             const int oA = 2 * g - 5, oB = 2 * g - 4;
@@ -287,10 +289,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                 if (oA >= 0 && oA < chs) {
                     st_as<T>((T*)outRow, h0.x);
                     if (two) st_as<T>((T*)(outRow + p.ys[3]), h1.x);
+                    ySum += two ? h0.x + h1.x : h0.x;
                 }
                 if (oB >= 0 && oB < chs) {
                     st_as<T>((T*)(outRow + p.ys[2]), h0.y);
                     if (two) st_as<T>((T*)(outRow + p.ys[2] + p.ys[3]), h1.y);
+                    ySum += two ? h0.y + h1.y : h0.y;
                 }
             }
             outRow += 2 * p.ys[2];
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             float h = 0.f;
 #pragma unroll
             for (int q = 0; q < 24; q++) h = fmaf(sV[base + q].x, p.fd[q], h);
-            if (lane < tws && o >= 0 && o < chs) st_as<T>((T*)outRow, h);
+            if (lane < tws && o >= 0 && o < chs) { st_as<T>((T*)outRow, h); ySum += h; }
             outRow += p.ys[2];
         }
     };
@@ -325,6 +329,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     };
     if (ey == 0) run(std::integral_constant<int, 0>());
     else run(std::integral_constant<int, 1>());
+    if (p.ysum) {                                   // bias gradient: one fp32 atomic per strip
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ySum += __shfl_xor_sync(0xffffffffu, ySum, o);
+        if (lane == 0) atomicAdd(p.ysum + c, ySum);
+    }
 }
 
 }  // namespace flrelu_bwd_stream

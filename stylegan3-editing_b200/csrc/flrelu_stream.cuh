@@ -76,6 +76,7 @@ template <int UP> struct Geo {
 struct Params {
     alignas(64) CUtensorMap mapX;      // 4-D map of x {W, H, C, N}, box {TIWP, 2, 1, 1}; used by the TMA variants only
     const void* x; void* y; const void* b; uint8_t* s;
+    float* ysum;                       // optional [C]: += sum of the outputs of channel c (bias gradient of the backward pass)
     int N, C, inH, inW, outH, outW;
     long long xs[4], ys[4], bs;        // byte strides
     int px0, py0;
@@ -442,6 +443,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
 
     // store address of output row 2g-5 (the first row retired by group g), column 2*lane of this strip
     char* outRow = yPlane + (long long)(oy0 - 5) * p.ys[2] + (long long)(ox0 + 2 * lane) * p.ys[3];
+    float ySum = 0.f;                   // sum of the outputs this lane stored (sign-READ kernels = backward pass only)
     auto stageD = [&](int g, int rot) {
         const float4* planeE = sC;
         const float4* planeO = sC + G::XH;
@@ -524,10 +526,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
             if (oA >= 0 && oA < chs) {
                 st_as<T>((T*)outRow, a0);
                 if (two) st_as<T>((T*)(outRow + p.ys[3]), a1);
+                if (MODE == SG3_SIGNS_READ) ySum += two ? a0 + a1 : a0;
             }
             if (oB >= 0 && oB < chs) {
                 st_as<T>((T*)(outRow + p.ys[2]), b0);
                 if (two) st_as<T>((T*)(outRow + p.ys[2] + p.ys[3]), b1);
+                if (MODE == SG3_SIGNS_READ) ySum += two ? b0 + b1 : b0;
             }
         }
         outRow += 2 * p.ys[2];             // the lane's store address walks down two output rows per group
@@ -578,6 +582,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
         else run(std::integral_constant<int, (UP == 4 ? 3 : 0)>());
     }
     if (TMA) tmaWait(nextPair);           // never leave with a bulk copy still writing this warp's shared memory
+    if (MODE == SG3_SIGNS_READ && p.ysum) {        // bias gradient: one fp32 atomic per strip
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ySum += __shfl_xor_sync(0xffffffffu, ySum, o);
+        if (lane == 0) atomicAdd(p.ysum + c, ySum);
+    }
 }
 
 }  // namespace flrelu_stream

@@ -70,8 +70,9 @@ def _act_inplace(y, si, sx, sy, gain, slope, clamp, write_signs):
     return s if write_signs else None
 
 
-def _fused(x, fu, fd, b, si, sx, sy, cfg, write_signs):
-    """Try the fused kernel.  Returns (y, signs_written) or None when no specialisation exists."""
+def _fused(x, fu, fd, b, si, sx, sy, cfg, write_signs, ysum=None):
+    """Try the fused kernel.  Returns (y, signs_written) or None when no specialisation exists.
+    `ysum` (float32 [C], zeroed): the kernel adds the per-channel sum of y -- the bias gradient when y = dx."""
     up, down, px0, px1, py0, py1, gain, slope, clamp, flip = cfg
     if x.dtype not in (torch.float16, torch.float32):
         return None
@@ -113,6 +114,7 @@ def _fused(x, fu, fd, b, si, sx, sy, cfg, write_signs):
     d.sH, d.sWb = (s.shape[2], s.shape[3]) if s is not None else (0, 0)
     d.sx, d.sy = int(sx), int(sy)
     d.dtype = capi.dtype_code(x.dtype)
+    d.ysum = ysum.data_ptr() if ysum is not None else None
     with torch.cuda.device(x.device):
         rc = L.sg3_filtered_lrelu(ctypes.byref(d), capi.stream_ptr(x.device))
     if rc == capi.SG3_E_NOKERNEL:
@@ -182,8 +184,17 @@ class _FilteredLRelu(torch.autograd.Function):
                    (fu_w - 1) + (fd_w - 1) - px0, xw * up - yw * down + px0 - (up - 1),
                    (fu_h - 1) + (fd_h - 1) - py0, xh * up - yh * down + py0 - (up - 1),
                    gain * (up ** 2) / (down ** 2), slope, float('inf'), not flip)
-            dx = _FilteredLRelu.apply(dy, fd, fu, None, signs, sx - (fu_w - 1) + px0, sy - (fu_h - 1) + py0, adj)
-        if ctx.needs_input_grad[3]:
+            s_ofs = (sx - (fu_w - 1) + px0, sy - (fu_h - 1) + py0)
+            if ctx.needs_input_grad[3] and not torch.is_grad_enabled() and dy.dtype in (torch.float16, torch.float32):
+                # first-order backward: the backward kernel also accumulates db = sum(dx) per channel (fp32 atomics),
+                # which saves the separate reduction pass over dx of filtered_lrelu.py:268
+                ysum = torch.zeros([dy.shape[1]], dtype=torch.float32, device=dy.device)
+                res = _fused(dy, fd, fu, None, signs, s_ofs[0], s_ofs[1], adj, False, ysum=ysum)
+                if res is not None:
+                    dx, db = res[0], ysum.to(dy.dtype)
+            if dx is None:
+                dx = _FilteredLRelu.apply(dy, fd, fu, None, signs, s_ofs[0], s_ofs[1], adj)
+        if ctx.needs_input_grad[3] and db is None:
             db = dx.sum([0, 2, 3])
         return dx, None, None, db, None, None, None, None
 

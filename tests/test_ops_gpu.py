@@ -374,3 +374,22 @@ def test_upfirdn2d_fast_paths(ops, case, dtype):
     ref = orc.upfirdn2d(x, f, up=up, down=down, padding=padding, flip_filter=flip, gain=up * up)
     assert y.shape == ref.shape
     assert rel_err(y.float().cpu().numpy(), ref) < (TOL32 if dtype == torch.float32 else 2e-3)
+
+
+def test_fused_backward_accumulates_bias_gradient(ops):
+    """desc.ysum: the sign-READ kernels add the per-channel sum of their output (db of the backward pass) with fp32 atomics;
+    the autograd path then skips the reduction over dx.  Compared with dx.sum of the create_graph path (torch reduction)."""
+    for up, radial in ((2, True), (4, True), (2, False)):
+        fu, fd = _design(6 * up, radial)
+        rng = np.random.RandomState(up + 10 * radial)
+        x = cu((rng.randn(2, 5, 40, 44) * 3).astype(np.float32), True)
+        b = cu(rng.randn(5).astype(np.float32), True)
+        pad = [11, 10, 11, 10] if up == 2 else [-2, -5, -2, -5]
+        y = ops.filtered_lrelu.filtered_lrelu(x, cu(fu), cu(fd), b, up=up, down=2, padding=pad, clamp=6.0)
+        dy = torch.randn_like(y)
+        before = ops.capi.lib().sg3_launch_count()
+        dx, db = torch.autograd.grad(y, [x, b], dy, retain_graph=True)
+        assert ops.capi.lib().sg3_launch_count() - before == 1            # one fused launch, no separate reduction kernel of ours
+        dx2, db2 = torch.autograd.grad(y, [x, b], dy, create_graph=True)   # reference-style path: db = dx.sum([0, 2, 3])
+        assert torch.equal(dx, dx2.detach())
+        assert rel_err(db.cpu().numpy(), db2.detach().cpu().numpy()) < 1e-5
