@@ -131,6 +131,16 @@ int sg3_upfirdn2d(const void* x, void* y, const float* f,
                   int padx0, int pady0, int flip, float gain,
                   int dtype, void* stream);
 
+/* Separable filter with the same up / down factor on both axes in ONE pass over HBM (the reference and sg3_upfirdn2d run
+ * it as two launches with an intermediate image, upfirdn2d.py:241-246).  fx [fW], fy [fH]: host taps (NULL = 1);
+ * power-of-two factor 1 / 2 / 4 on one side, <= 24 taps per polyphase branch, W-contiguous f32 / f16 tensors; otherwise
+ * SG3_E_NOKERNEL (call sg3_upfirdn2d twice). */
+int sg3_upfirdn2d_sep(const void* x, void* y, const float* fx, const float* fy,
+                      int N, int C, int inH, int inW, int outH, int outW,
+                      const int64_t xStride[4], const int64_t yStride[4],
+                      int fW, int fH, int up, int down, int padx0, int pady0, int flip, float gain,
+                      int dtype, void* stream);
+
 /* ------------------------------------------------------------------------
  * modulated_conv2d (networks_stylegan3.py:24-63).  The reference has no native entry
  * point here: it runs ~10 eager elementwise kernels and a cuDNN grouped convolution.

@@ -108,11 +108,36 @@ def upfirdn2d_raw(x, taps2d, upx, upy, downx, downy, padx0, padx1, pady0, pady1,
     return y
 
 
+def upfirdn2d_sep_raw(x, taps1d, up, down, padx0, padx1, pady0, pady1, flip, gain):
+    """Separable filter in one launch (sg3_upfirdn2d_sep).  Returns None when the library has no kernel for the shape."""
+    capi.require_cuda(x, 'upfirdn2d')
+    ft = int(taps1d.shape[0])
+    n, c, ih, iw = x.shape
+    ow = (iw * up + padx0 + padx1 - ft + down) // down
+    oh = (ih * up + pady0 + pady1 - ft + down) // down
+    if ow < 1 or oh < 1:
+        raise RuntimeError('upfirdn2d: output must be at least 1x1')
+    if x.numel() == 0 or x.dtype not in (torch.float16, torch.float32) or x.stride(3) != 1:
+        return None
+    y = torch.empty([n, c, oh, ow], dtype=x.dtype, device=x.device)
+    xs = capi.c_i64x4(*x.stride())
+    ys = capi.c_i64x4(*y.stride())
+    with torch.cuda.device(x.device):
+        rc = capi.lib().sg3_upfirdn2d_sep(
+            x.data_ptr(), y.data_ptr(), taps1d.ctypes.data, taps1d.ctypes.data, n, c, ih, iw, oh, ow,
+            ctypes.byref(xs), ctypes.byref(ys), ft, ft, up, down, padx0, pady0,
+            int(bool(flip)), float(gain), capi.dtype_code(x.dtype), capi.stream_ptr(x.device))
+    if rc == capi.SG3_E_NOKERNEL:
+        return None
+    capi.check(rc, 'sg3_upfirdn2d_sep')
+    return y
+
+
 _ONE = np.ones((1, 1), np.float32)
 
 
 def _run(x, f, upx, upy, downx, downy, pads, flip, gain):
-    """Dense filter -> one launch; separable filter -> x pass then y pass (upfirdn2d.py:241-246)."""
+    """Dense filter -> one launch; separable filter -> the fused one-pass kernel, else x pass then y pass (upfirdn2d.py:241-246)."""
     px0, px1, py0, py1 = pads
     if f is None:
         return upfirdn2d_raw(x, _ONE, upx, upy, downx, downy, px0, px1, py0, py1, flip, gain)
@@ -121,6 +146,10 @@ def _run(x, f, upx, upy, downx, downy, pads, flip, gain):
         taps = (taps * taps).reshape(1, 1)
     if taps.ndim == 2:
         return upfirdn2d_raw(x, taps, upx, upy, downx, downy, px0, px1, py0, py1, flip, gain)
+    if upx == upy and downx == downy:          # one pass over HBM instead of the reference's two launches
+        y = upfirdn2d_sep_raw(x, taps, upx, downx, px0, px1, py0, py1, flip, gain)
+        if y is not None:
+            return y
     y = upfirdn2d_raw(x, taps.reshape(1, -1), upx, 1, downx, 1, px0, px1, 0, 0, flip, 1.0)
     return upfirdn2d_raw(y, taps.reshape(-1, 1), 1, upy, 1, downy, 0, 0, py0, py1, flip, gain)
 

@@ -370,10 +370,16 @@ def test_upfirdn2d_fast_paths(ops, case, dtype):
         x = x.astype(np.float16).astype(np.float32)
     before = ops.capi.lib().sg3_launch_count()
     y = ops.upfirdn2d.upfirdn2d(cu(x).to(dtype), cu(f), up=up, down=down, padding=padding, flip_filter=flip, gain=up * up)
-    assert ops.capi.lib().sg3_launch_count() - before == (2 if isinstance(taps, int) else 1)
+    assert ops.capi.lib().sg3_launch_count() - before == 1, 'separable filters run the one-pass kernel, dense ones a single launch'
     ref = orc.upfirdn2d(x, f, up=up, down=down, padding=padding, flip_filter=flip, gain=up * up)
     assert y.shape == ref.shape
     assert rel_err(y.float().cpu().numpy(), ref) < (TOL32 if dtype == torch.float32 else 2e-3)
+    if isinstance(taps, int):       # the two-launch 1-D kernels (what other up/down combinations use) agree as well
+        px0, px1, py0, py1 = ops.upfirdn2d._padding(padding)
+        t = ops.upfirdn2d.host_taps(cu(f))
+        y1 = ops.upfirdn2d.upfirdn2d_raw(cu(x).to(dtype), t.reshape(1, -1), up, 1, down, 1, px0, px1, 0, 0, flip, 1.0)
+        y2 = ops.upfirdn2d.upfirdn2d_raw(y1, t.reshape(-1, 1), 1, up, 1, down, 0, 0, py0, py1, flip, up * up)
+        assert rel_err(y2.float().cpu().numpy(), ref) < (TOL32 if dtype == torch.float32 else 4e-3)
 
 
 def test_fused_backward_accumulates_bias_gradient(ops):
