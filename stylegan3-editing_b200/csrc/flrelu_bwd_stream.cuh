@@ -39,7 +39,7 @@ template <int DOWN> struct Geo {
     static constexpr int RING = 4;                                    // row pairs per ring
     static constexpr int ROW_BYTES = ((TIW * 8 + 15) / 16) * 16;      // one ring row: TIW float2
     static constexpr int RING_BYTES = RING * ROW_BYTES;
-    static constexpr int SV_BYTES = kBW * 8;                          // finished V rows: [column][2] floats
+    static constexpr int SV_BYTES = 4 * (kBW / 4 + 1) * 8;            // finished V rows: [vslot(column)][2] floats
     static constexpr int WARP_BYTES = ((2 * RING_BYTES + SV_BYTES + 127) / 128) * 128;
     static_assert(AW + 1 <= kBW, "strip geometry");
 };
@@ -59,6 +59,10 @@ struct Params {
 };
 
 __device__ __forceinline__ float2 ffma2(float2 a, float t, float2 c) { return __ffma2_rn(a, make_float2(t, t), c); }
+
+// Slot of column c in the finished-row buffer: grouped by c % 4 so that stage H's reads (lane stride 4 columns) are
+// conflict-free (see flrelu_stream.cuh, vslot).
+__device__ __forceinline__ int vslot(int c) { return (c & 3) * (kBW / 4 + 1) + (c >> 2); }
 
 template <class T, int DOWN, int MODE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_constant__ Params p)
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
         }
 #pragma unroll
         for (int q = 0; q < 4; q++)
-            if (xd + q >= 0 && xd + q < kBW) sV[xd + q] = outv[q];
+            if (xd + q >= 0 && xd + q < kBW) sV[vslot(xd + q)] = outv[q];
         // slide the accumulators
         if (DOWN == 2) {
 #pragma unroll
@@ -280,7 +284,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             const int base = min(4 * lane, kBW - 16);
 #pragma unroll
             for (int q = 0; q < 14; q++) {
-                const float2 v = sV[base + q];
+                const float2 v = sV[vslot(base + q)];
                 if (q < 12) h0 = ffma2(v, p.fd[q], h0);
                 if (q >= 2) h1 = ffma2(v, p.fd[q - 2], h1);
             }
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             const int base = min(4 * lane, kBW - 24);
             float h = 0.f;
 #pragma unroll
-            for (int q = 0; q < 24; q++) h = fmaf(sV[base + q].x, p.fd[q], h);
+            for (int q = 0; q < 24; q++) h = fmaf(sV[vslot(base + q)].x, p.fd[q], h);
             if (lane < tws && o >= 0 && o < chs) { st_as<T>((T*)outRow, h); ySum += h; }
             outRow += p.ys[2];
         }

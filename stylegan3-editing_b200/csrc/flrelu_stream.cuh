@@ -113,6 +113,11 @@ __device__ __forceinline__ float2 ffma2(float2 a, float t, float2 c) { return __
 
 __device__ __forceinline__ int swz(int xh) { return xh ^ ((xh >> 3) & 1); }
 
+// Slot of activation column c in the [column] float2 row buffer the horizontal down pass reads with a lane stride of 4
+// columns: columns are grouped by c % 4 (33 slots per group, odd so that the writers' column pairs hit different banks)
+// and the readers of one tap find 32 consecutive slots -- no bank conflicts (plain [c] order is 8-way conflicted).
+__device__ __forceinline__ int vslot(int c) { return (c & 3) * 33 + (c >> 2); }
+
 // leaky ReLU + clamp of two values that already carry the gain; 2-bit sign codes in WRITE mode.
 //   NONE : max3(v, slope*v, -clamp) then min(., clamp): one packed FMUL2, one FMNMX3 and one FMNMX per value
 //   WRITE: same value, plus code = clamped ? 2 : negative ? 1 : 0
@@ -336,6 +341,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
         cSlot1[r] = __shfl_sync(0xffffffffu, cSlot1[r], lane);
     }
     const long long sPlane = (long long)plane * p.sH;
+    // FD == 0 only: live output rows of the vertical down filter per activation column pair (slot k = output row 2g+1-k),
+    // and the two finished rows of a group as [column] (row 2g-5, row 2g-4) pairs, in the memory sC uses for dense filters
+    float2 vacc[7][2];
+#pragma unroll
+    for (int k = 0; k < 7; k++) vacc[k][0] = vacc[k][1] = make_float2(0.f, 0.f);
+    float2* sV = (float2*)sC;
     auto stageC = [&](int g, auto EYc) {
         constexpr int EY = decltype(EYc)::value;
         const float* win = sB + groupSlot * G::BW;       // 8 contiguous window rows (ring + mirrored tail)
@@ -384,8 +395,17 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
                 }
                 v[j] = act2<MODE>(u, p, rc0, rc1, code0[j], code1[j]);
             }
+            if (FD == 0) {
+                // separable down filter: its vertical half is applied right here, from registers.  Activation row 4g + j
+                // feeds output rows 2g + (j >> 1) - k through tap (j & 1) + 2k, k = 0..5 -> accumulator slot k + 1 - (j >> 1).
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+#pragma unroll
+                    for (int k = 0; k < 6; k++)
+                        vacc[k + 1 - (j >> 1)][r] = ffma2(v[j], p.fdx[(j & 1) + 2 * k], vacc[k + 1 - (j >> 1)][r]);
+            }
             if (cSlot0[r] >= 0) {
-                sC[cSlot0[r]] = make_float4(v[0].x, v[2].x, v[1].x, v[3].x);
+                if (FD != 0) sC[cSlot0[r]] = make_float4(v[0].x, v[2].x, v[1].x, v[3].x);
                 if (MODE == SG3_SIGNS_WRITE) {
                     const int xd0 = xp - ex;
 #pragma unroll
@@ -393,12 +413,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
                 }
             }
             if (cSlot1[r] >= 0) {
-                sC[cSlot1[r]] = make_float4(v[0].y, v[2].y, v[1].y, v[3].y);
+                if (FD != 0) sC[cSlot1[r]] = make_float4(v[0].y, v[2].y, v[1].y, v[3].y);
                 if (MODE == SG3_SIGNS_WRITE) {
                     const int xd1 = xp - ex + 1;
 #pragma unroll
                     for (int j = 0; j < 4; j++) sS[j * G::SS_ROW + xd1] = (unsigned char)code1[j];
                 }
+            }
+        }
+        if (FD == 0) {
+            // rows 2g-5 (slot 6) and 2g-4 (slot 5) are complete: publish them as (row, row) pairs per column for the horizontal
+            // pass of stage D, then slide the accumulators by two output rows
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                const int xd0 = 2 * (lane + 32 * r) - ex;
+                if (xd0 >= 0 && xd0 < G::BW) sV[vslot(xd0)] = make_float2(vacc[6][r].x, vacc[5][r].x);
+                if (xd0 + 1 >= 0 && xd0 + 1 < G::BW) sV[vslot(xd0 + 1)] = make_float2(vacc[6][r].y, vacc[5][r].y);
+#pragma unroll
+                for (int k = 6; k >= 2; k--) vacc[k][r] = vacc[k - 2][r];
+                vacc[0][r] = vacc[1][r] = make_float2(0.f, 0.f);
             }
         }
     };
@@ -484,41 +517,31 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
                     }
                 }
             }
-        } else {
-            float2 ha[2], hb[2];
-            ha[0] = ha[1] = hb[0] = hb[1] = make_float2(0.f, 0.f);
+        }
+        float a0, a1, b0, b1;
+        if (FD == 0) {
+            // horizontal half of the separable filter on the two rows stage C finished (sV): (row 2g-5, row 2g-4) per column,
+            // output columns 2*lane (h0) and 2*lane + 1 (h1, two activation columns further)
+            const int base = min(4 * lane, G::BW - 16);          // idle lanes read valid columns
+            float2 h0 = make_float2(0.f, 0.f), h1 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < kDownTaps + 2; q++) {
-                const float4 px = (q & 1) ? planeO[dSlot[q >> 1]] : planeE[dSlot[q >> 1]];
-                const float2 pa = make_float2(px.x, px.y);
-                const float2 pb = make_float2(px.z, px.w);
-#pragma unroll
-                for (int cc = 0; cc < 2; cc++) {
-                    const int b = q - 2 * cc;
-                    if (b >= 0 && b < kDownTaps) {
-                        ha[cc] = ffma2(pa, p.fdx[b], ha[cc]);
-                        hb[cc] = ffma2(pb, p.fdx[b], hb[cc]);
-                    }
-                }
+                const float2 v = sV[vslot(base + q)];
+                if (q < kDownTaps) h0 = ffma2(v, p.fdx[q], h0);
+                if (q >= 2) h1 = ffma2(v, p.fdx[q - 2], h1);
             }
-#pragma unroll
-            for (int cc = 0; cc < 2; cc++)
-#pragma unroll
-                for (int i = 0; i < 6; i++) {
-                    acc[i][cc] = ffma2(ha[cc], p.fdvr[rot][0][i], acc[i][cc]);
-                    acc[i][cc] = ffma2(hb[cc], p.fdvr[rot][1][i], acc[i][cc]);
-                }
-        }
-        // Retire output rows 2g-5 and 2g-4: logical accumulators 5 and 4 = slots (5 + 4*rot) % 6 and (4 + 4*rot) % 6;
-        // the freed slots start the next group as logical 1 and 0.
-        float a0, a1, b0, b1;
+            a0 = h0.x; a1 = h1.x; b0 = h0.y; b1 = h1.y;
+        } else {
+            // Retire output rows 2g-5 and 2g-4: logical accumulators 5 and 4 = slots (5 + 4*rot) % 6 and (4 + 4*rot) % 6;
+            // the freed slots start the next group as logical 1 and 0.
 #define SG3_RETIRE(S4, S5)                                                                      \
-        a0 = acc[S5][0].x + carry[0]; a1 = acc[S5][1].x + carry[1];                             \
-        b0 = acc[S4][0].x + acc[S5][0].y; b1 = acc[S4][1].x + acc[S5][1].y;                     \
-        carry[0] = acc[S4][0].y; carry[1] = acc[S4][1].y;                                       \
-        acc[S4][0] = acc[S4][1] = acc[S5][0] = acc[S5][1] = make_float2(0.f, 0.f);
-        if (rot == 0) { SG3_RETIRE(4, 5) } else if (rot == 1) { SG3_RETIRE(2, 3) } else { SG3_RETIRE(0, 1) }
+            a0 = acc[S5][0].x + carry[0]; a1 = acc[S5][1].x + carry[1];                             \
+            b0 = acc[S4][0].x + acc[S5][0].y; b1 = acc[S4][1].x + acc[S5][1].y;                     \
+            carry[0] = acc[S4][0].y; carry[1] = acc[S4][1].y;                                       \
+            acc[S4][0] = acc[S4][1] = acc[S5][0] = acc[S5][1] = make_float2(0.f, 0.f);
+            if (rot == 0) { SG3_RETIRE(4, 5) } else if (rot == 1) { SG3_RETIRE(2, 3) } else { SG3_RETIRE(0, 1) }
 #undef SG3_RETIRE
+        }
         const int oA = 2 * g - 5, oB = 2 * g - 4;
         const int oxl = 2 * lane;
         if (oxl < tws) {
