@@ -163,6 +163,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
     auto stageUV = [&](int g, auto EYc) {
         constexpr int EY = decltype(EYc)::value;
         // window row r (0..7) = input row 2g + r of the strip; pair (r, r+1) lives in E (r even) or O (r odd)
+        // Sign bytes: the lane's 4 columns are 8 bits of the two bytes covering pixels 4*lane .. 4*lane+7 (byte-aligned
+        // base).  Loaded at the point of use they were the largest stall of the kernel (global latency, every group), and
+        // the register budget does not allow holding them across stage U -- so the NEXT group's bytes are prefetched into
+        // L1 here, a group ahead, and the loads below hit.
+        if (MODE == SG3_SIGNS_READ) {
+            const int byte0 = ((Xs - ex + p.sx) >> 2) + lane;
+            if (byte0 >= 0 && byte0 < p.sWb) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int sY = Ys + 4 * (g + 1) + j + p.sy;
+                    if (sY >= 0 && sY < p.sH)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.s + (sPlane + sY) * p.sWb + byte0));
+                }
+            }
+        }
         float2 acc[2][2][2];                   // [row pair jp: rows (jp, jp+2)][column block][px]
 #pragma unroll
         for (int a = 0; a < 8; a++) ((float2*)acc)[a] = make_float2(0.f, 0.f);
@@ -207,7 +222,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                 v[q] = hi ? a2.y : a2.x;
             }
             if (MODE == SG3_SIGNS_READ) {
-                // the lane's 4 columns are 8 bits of the two sign bytes covering pixels 4*lane .. 4*lane+7 (byte-aligned base)
                 const int sY = Ys + 4 * g + j + p.sy;
                 const int signX0 = Xs - ex + p.sx;
                 const int byte0 = (signX0 >> 2) + lane;
