@@ -159,25 +159,32 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
 #pragma unroll
     for (int k = 0; k < NV; k++) vacc[k][0] = vacc[k][1] = make_float2(0.f, 0.f);
 
+    // Sign bytes of the 4 activation rows of group g for the lane's 4 columns: the two bytes covering pixels
+    // 4*lane .. 4*lane+7 from a byte-aligned base.  Loaded at the point of use they were the largest stall of the kernel
+    // (global latency in every group), so the RAW bytes of the next group are fetched at the end of the current one and
+    // carried across the loop; they are only combined where the activation needs them, a whole stage U later.
+    unsigned sLo[4] = {0u, 0u, 0u, 0u}, sHi[4] = {0u, 0u, 0u, 0u};
+    auto loadSigns = [&](int g) {
+        if (MODE == SG3_SIGNS_READ) {
+            const int byte0 = ((Xs - ex + p.sx) >> 2) + lane;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int sY = Ys + 4 * g + j + p.sy;
+                sLo[j] = sHi[j] = 0u;
+                if (sY >= 0 && sY < p.sH) {
+                    const uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
+                    if (byte0 >= 0 && byte0 < p.sWb) sLo[j] = __ldg(srow + byte0);
+                    if (byte0 + 1 >= 0 && byte0 + 1 < p.sWb) sHi[j] = __ldg(srow + byte0 + 1);
+                }
+            }
+        }
+    };
+    loadSigns(0);
+
     // ---- stage U + V for group g ----
     auto stageUV = [&](int g, auto EYc) {
         constexpr int EY = decltype(EYc)::value;
         // window row r (0..7) = input row 2g + r of the strip; pair (r, r+1) lives in E (r even) or O (r odd)
-        // Sign bytes: the lane's 4 columns are 8 bits of the two bytes covering pixels 4*lane .. 4*lane+7 (byte-aligned
-        // base).  Loaded at the point of use they were the largest stall of the kernel (global latency, every group), and
-        // the register budget does not allow holding them across stage U -- so the NEXT group's bytes are prefetched into
-        // L1 here, a group ahead, and the loads below hit.
-        if (MODE == SG3_SIGNS_READ) {
-            const int byte0 = ((Xs - ex + p.sx) >> 2) + lane;
-            if (byte0 >= 0 && byte0 < p.sWb) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int sY = Ys + 4 * (g + 1) + j + p.sy;
-                    if (sY >= 0 && sY < p.sH)
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(p.s + (sPlane + sY) * p.sWb + byte0));
-                }
-            }
-        }
         float2 acc[2][2][2];                   // [row pair jp: rows (jp, jp+2)][column block][px]
 #pragma unroll
         for (int a = 0; a < 8; a++) ((float2*)acc)[a] = make_float2(0.f, 0.f);
@@ -222,16 +229,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
                 v[q] = hi ? a2.y : a2.x;
             }
             if (MODE == SG3_SIGNS_READ) {
-                const int sY = Ys + 4 * g + j + p.sy;
-                const int signX0 = Xs - ex + p.sx;
-                const int byte0 = (signX0 >> 2) + lane;
-                unsigned lo = 0, hi = 0;
-                if (sY >= 0 && sY < p.sH) {
-                    const uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
-                    if (byte0 >= 0 && byte0 < p.sWb) lo = __ldg(srow + byte0);
-                    if (byte0 + 1 >= 0 && byte0 + 1 < p.sWb) hi = __ldg(srow + byte0 + 1);
-                }
-                const unsigned bits = (lo | (hi << 8)) >> (2 * (signX0 & 3));
+                const unsigned bits = (sLo[j] | (sHi[j] << 8)) >> (2 * ((Xs - ex + p.sx) & 3));      // loaded a group ago (loadSigns)
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const unsigned code = (bits >> (2 * q)) & 3u;
@@ -284,6 +282,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_cons
             for (int k = NV - 1; k >= 1; k--) { vacc[k][0] = vacc[k - 1][0]; vacc[k][1] = vacc[k - 1][1]; }
             vacc[0][0] = vacc[0][1] = make_float2(0.f, 0.f);
         }
+        loadSigns(g + 1);
     };
 
     // ---- stage H: horizontal down filter of the finished rows, store ----
