@@ -347,6 +347,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
 #pragma unroll
     for (int k = 0; k < 7; k++) vacc[k][0] = vacc[k][1] = make_float2(0.f, 0.f);
     float2* sV = (float2*)sC;
+    // Sign READ: raw sign bytes of the 4 activation rows of group g (lane l: the two bytes covering pixels 4l .. 4l+7 of the
+    // strip's upsampled columns, byte-aligned base), fetched one group ahead and carried across the loop so that their
+    // global-load latency never sits in front of the activation.
+    unsigned sLo[4] = {0u, 0u, 0u, 0u}, sHi[4] = {0u, 0u, 0u, 0u};
+    auto loadSigns = [&](int g) {
+        if (MODE == SG3_SIGNS_READ) {
+            const int byte0 = ((Xs - ex + p.sx) >> 2) + lane;      // arithmetic shift: floor for negative coordinates
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int sY = Ys + 4 * g + j + p.sy;
+                sLo[j] = sHi[j] = 0u;
+                if (sY >= 0 && sY < p.sH) {
+                    const uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
+                    if (byte0 >= 0 && byte0 < p.sWb) sLo[j] = __ldg(srow + byte0);
+                    if (byte0 + 1 >= 0 && byte0 + 1 < p.sWb) sHi[j] = __ldg(srow + byte0 + 1);
+                }
+            }
+        }
+    };
+    loadSigns(0);
     auto stageC = [&](int g, auto EYc) {
         constexpr int EY = decltype(EYc)::value;
         const float* win = sB + groupSlot * G::BW;       // 8 contiguous window rows (ring + mirrored tail)
@@ -356,18 +376,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
         const int signX0 = Xs - ex + p.sx;               // sign-tensor x of upsampled column 0 of the strip
         const int signOff = signX0 & 3;                  // pixel offset inside the first byte (arithmetic & also for negatives)
         if (MODE == SG3_SIGNS_READ) {
-            const int byte0 = (signX0 >> 2) + lane;      // arithmetic shift: floor for negative coordinates
+            // the raw bytes were fetched at the end of the previous group (loadSigns): their global latency is long gone
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int sY = Ys + 4 * g + j + p.sy;
-                unsigned lo = 0, hi = 0;
-                if (sY >= 0 && sY < p.sH) {
-                    const uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
-                    if (byte0 >= 0 && byte0 < p.sWb) lo = __ldg(srow + byte0);
-                    if (byte0 + 1 >= 0 && byte0 + 1 < p.sWb) hi = __ldg(srow + byte0 + 1);
-                }
-                signWin[j] = lo | (hi << 8);
-            }
+            for (int j = 0; j < 4; j++) signWin[j] = sLo[j] | (sHi[j] << 8);
         }
 #pragma unroll
         for (int r = 0; r < 2; r++) {
@@ -434,6 +445,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
                 vacc[0][r] = vacc[1][r] = make_float2(0.f, 0.f);
             }
         }
+        loadSigns(g + 1);
     };
 
     // sign bytes this strip owns: columns [0, ownW) of D's frame (whole bytes: Xs + sx is a multiple of 4),
