@@ -219,7 +219,10 @@ TC3_CASES = [
     (1, 512, 323, 16, 24, 2),      # 16 chunks, three channel tiles (ragged last)
     (1, 40, 200, 12, 276, 2),      # wide rows: several column tiles per row
     (2, 48, 32, 18, 20, 0),        # padding 0 ('valid'), the dgrad form
-    (1, 128, 81, 30, 532, 2),      # short K loop -> double-buffered accumulators, 532-wide rows
+    (1, 128, 81, 30, 532, 2),      # short K loop, 532-wide rows
+    (2, 96, 128, 96, 128, 2),      # streamed weights (3 chunks x 9 taps do not fit the ring), full 128-channel block
+    (1, 64, 256, 75, 100, 2),      # odd number of pixel tiles, two channel blocks
+    (3, 512, 512, 36, 36, 2),      # T-1024 L0 at batch 3: 16 chunks, four channel blocks
 ]
 
 
