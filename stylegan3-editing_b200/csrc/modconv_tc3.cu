@@ -258,7 +258,7 @@ bool plan_tc3(Tc3Params& p)
             const long long tiles = (long long)((p.OW + s - 1) / s) * ((p.OH + r - 1) / r);
             const double perMma = npx / 2.0 > 32.0 + npx / 4.0 ? npx / 2.0 : 32.0 + npx / 4.0;       // tools/tc_mma_bench.cu
             const double mma = 36.0 * r * perMma;
-            const double load = ((resident ? 0.0 : 9.0 * p.wSlotBytes) + (double)xGroup) / 40.0;
+            const double load = ((resident ? 0.0 : 9.0 * p.wSlotBytes) + (double)xGroup) / 80.0;     // operand stream at ~80 B/clk/SM (fitted; 40 over-penalised wide tiles)
             const double epi = 530.0 * r * ((p.colBase + s + 31) / 32);
             const double cost = (double)tiles * (1700.0 + p.kChunks * (mma > load ? mma : load) + epi);
             if (cost < best) {
