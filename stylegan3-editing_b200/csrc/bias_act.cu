@@ -139,6 +139,15 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActParams p)
         // 32-bit division per packet).
         S bvec = (S)0;
         if (p.biasMode == 1) bvec = ld_as<T>(b + ((uint32_t)base / (uint32_t)p.stepB) % (uint32_t)p.sizeB);
+        if (p.grad == 0 && p.biasMode <= 1) {
+            // forward value with one bias per packet (every NCHW activation): no per-element branches
+#pragma unroll
+            for (int j = 0; j < VN; j++) {
+                S r = Act<A, S>::f(ld_as<T>(xs + j) + bvec, alpha) * gain;
+                if (clamp >= 0) r = min(max(r, -clamp), clamp);
+                st_as<T>(out + j, r);
+            }
+        } else
 #pragma unroll
         for (int j = 0; j < VN; j++) {
             S bv = bvec;
