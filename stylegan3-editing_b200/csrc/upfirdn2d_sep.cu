@@ -41,6 +41,56 @@ __device__ __forceinline__ void branch(int o, int pad, int& first, int& a0)
     first = (mid + a0) >> SepGeo<UP, DOWN>::SH;      // exact division; arithmetic shift for negatives
 }
 
+// Polyphase geometry of a run of consecutive outputs o = base + u whose base is a multiple of UP: with
+// rho = pad & (UP - 1), output u uses taps a0(u) + k * UP and inputs first(base) + d(u) + k.  Everything is a compile-time
+// function of (u, RHO), so both passes keep their windows in registers with static indices.
+template <int UP, int DOWN, int RHO> struct Poly {
+    static __host__ __device__ constexpr int a0(int u) { return ((RHO - u * DOWN) % UP + UP) % UP; }
+    // first(base + u) - first(base) for base * DOWN a multiple of UP:  ((u * DOWN - RHO' + a0(u)) - (a0(0) - RHO')) / UP
+    static __host__ __device__ constexpr int d(int u) { return (u * DOWN + a0(u) - a0(0)) / UP; }
+};
+
+template <int UP, int DOWN, int KP, int RUN> struct Win {              // window rows / columns a run of RUN outputs reads
+    static constexpr int N = ((RUN - 1) * DOWN + UP - 1) / UP + KP + 1;
+};
+
+// x pass of one (row, 8-column block) item: lanes run along the rows, so the shared-memory reads of a warp are IWP (odd)
+// floats apart -- conflict-free -- and a thread slides a register window along x.
+template <int UP, int DOWN, int KP, int RHO, int IWP, int MP>
+__device__ __forceinline__ void sep_xrun(const float* __restrict__ src, float* __restrict__ dst, const float* __restrict__ fx)
+{
+    constexpr int NW = Win<UP, DOWN, KP, 8>::N;
+    float w[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) w[k] = src[k];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; k++) acc = fmaf(w[Poly<UP, DOWN, RHO>::d(u) + k], fx[Poly<UP, DOWN, RHO>::a0(u) + k * UP], acc);
+        dst[u] = acc;
+    }
+}
+
+// y pass of RPT consecutive output rows of one column: the window comes from sMid with lanes along x (conflict-free).
+template <class T, int UP, int DOWN, int KP, int RHO, int RPT, int MP>
+__device__ __forceinline__ void sep_yrun(const float* __restrict__ src, int rowsAvail, T* __restrict__ out, int64_t outStride, int rowsOut,
+                                         const float* __restrict__ fy, float gain)
+{
+    typedef typename Arith<T>::type S;
+    constexpr int NW = Win<UP, DOWN, KP, RPT>::N;
+    float w[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) w[k] = k < rowsAvail ? src[k * MP] : 0.f;
+#pragma unroll
+    for (int q = 0; q < RPT; q++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; k++) acc = fmaf(w[Poly<UP, DOWN, RHO>::d(q) + k], fy[Poly<UP, DOWN, RHO>::a0(q) + k * UP], acc);
+        if (q < rowsOut) st_as<T>(out + q * outStride, (S)(acc * gain));
+    }
+}
+
 template <class T, int UP, int DOWN, int KP>
 __global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const __grid_constant__ SepParams p)
 {
@@ -48,13 +98,16 @@ __global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const __grid_constan
     constexpr int TW = G::TW, TH = G::TH;
     constexpr int IW = ((TW - 1) * DOWN + UP - 1) / UP + KP + 1;        // input columns / rows a tile can touch
     constexpr int IH = ((TH - 1) * DOWN + UP - 1) / UP + KP + 1;
-    constexpr int IWP = IW | 1;                                         // odd pitch: rows start in different banks
+    constexpr int IWP = (IW + 8) | 1;                                   // odd pitch (+8: the last x window may run past IW)
+    constexpr int MP = TW + 1;                                          // odd pitch of the x-filtered tile
+    constexpr int RPT = TH / (256 / TW);                                // output rows per thread in the y pass
     extern __shared__ float smem[];
     float* sIn = smem;                      // [IH][IWP]
-    float* sMid = smem + IH * IWP;          // [IH][TW]
+    float* sMid = smem + IH * IWP;          // [IH][MP]
     const int tid = threadIdx.x;
     const int64_t tilesPerPlane = (int64_t)p.tilesX * p.tilesY;
     const int64_t total = tilesPerPlane * p.N * p.C;
+    const int rhoX = p.padx0 & (UP - 1), rhoY = p.pady0 & (UP - 1);
     for (int64_t t = blockIdx.x; t < total; t += gridDim.x) {
         const int64_t plane = t / tilesPerPlane;
         const int rem = (int)(t - plane * tilesPerPlane);
@@ -67,56 +120,57 @@ __global__ void __launch_bounds__(256) upfirdn2d_sep_kernel(const __grid_constan
         branch<UP, DOWN>(ox0, p.padx0, j0, dummy);
         branch<UP, DOWN>(oy0, p.pady0, i0, dummy);
         __syncthreads();                                    // previous tile's readers are done with both buffers
-        // ---- input tile -> smem (zero outside the image); 8 independent loads per thread in flight ----
-        constexpr int NIN = IH * IW;
+        // ---- input tile -> smem (zero outside the image and in the pitch padding); 8 independent loads per thread in flight ----
+        constexpr int NIN = IH * IWP;
         for (int e0 = tid; e0 < NIN; e0 += 256 * 8) {
             float v[8];
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int e = e0 + 256 * u;
-                const int r = e / IW, q = e - r * IW;
+                const int r = e / IWP, q = e - r * IWP;
                 const int i = i0 + r, j = j0 + q;
                 v[u] = 0.f;
-                if (e < NIN && i >= 0 && i < p.inH && j >= 0 && j < p.inW) v[u] = (float)ld_as<T>(xp + (int64_t)i * p.xs[2] + j);
+                if (e < NIN && q < IW && i >= 0 && i < p.inH && j >= 0 && j < p.inW) v[u] = (float)ld_as<T>(xp + (int64_t)i * p.xs[2] + j);
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
                 const int e = e0 + 256 * u;
-                const int r = e / IW, q = e - r * IW;
-                if (e < NIN) sIn[r * IWP + q] = v[u];
+                if (e < NIN) sIn[e] = v[u];
             }
         }
         __syncthreads();
-        // ---- x pass: sMid[r][cx] = sum_k fx[b0 + k UP] * sIn[r][first(cx) - j0 + k] ----
-        {
-            const int cx = tid % TW, rg = tid / TW;             // column of this thread, first row; rows step 256 / TW
-            int first, b0;
-            branch<UP, DOWN>(ox0 + cx, p.padx0, first, b0);
-            float tap[KP];
-#pragma unroll
-            for (int k = 0; k < KP; k++) tap[k] = p.fx[b0 + k * UP];
-            const float* src = sIn + (first - j0);
-            for (int r = rg; r < IH; r += 256 / TW) {
-                float acc = 0.f;
-#pragma unroll
-                for (int k = 0; k < KP; k++) acc = fmaf(src[r * IWP + k], tap[k], acc);
-                sMid[r * TW + cx] = acc;
+        // ---- x pass: items (row r, block of 8 output columns), rows fastest so that a warp reads IWP-strided addresses ----
+        for (int it = tid; it < IH * (TW / 8); it += 256) {
+            const int cb = it / IH, r = it - cb * IH;
+            const float* src = sIn + r * IWP + (8 * cb * DOWN) / UP;       // first(ox0 + 8 cb) - j0: 8 cb DOWN is a multiple of UP
+            float* dst = sMid + r * MP + 8 * cb;
+            if (UP == 1) sep_xrun<UP, DOWN, KP, 0, IWP, MP>(src, dst, p.fx);
+            else if (UP == 2) { if (rhoX == 0) sep_xrun<UP, DOWN, KP, 0, IWP, MP>(src, dst, p.fx); else sep_xrun<UP, DOWN, KP, 1 % UP, IWP, MP>(src, dst, p.fx); }
+            else {
+                if (rhoX == 0) sep_xrun<UP, DOWN, KP, 0, IWP, MP>(src, dst, p.fx);
+                else if (rhoX == 1) sep_xrun<UP, DOWN, KP, 1 % UP, IWP, MP>(src, dst, p.fx);
+                else if (rhoX == 2) sep_xrun<UP, DOWN, KP, 2 % UP, IWP, MP>(src, dst, p.fx);
+                else sep_xrun<UP, DOWN, KP, 3 % UP, IWP, MP>(src, dst, p.fx);
             }
         }
         __syncthreads();
-        // ---- y pass: y[oy][ox] = gain * sum_k fy[a0 + k UP] * sMid[first(oy) - i0 + k][cx] ----
+        // ---- y pass: thread = (column, RPT consecutive output rows) ----
         {
             const int cx = tid % TW, rg = tid / TW;
-            const int ox = ox0 + cx;
-            for (int ry = rg; ry < TH; ry += 256 / TW) {
-                const int oy = oy0 + ry;
-                int first, a0;
-                branch<UP, DOWN>(oy, p.pady0, first, a0);      // uniform across the warp (TW >= 32): uniform tap loads
-                const float* src = sMid + (first - i0) * TW + cx;
-                float acc = 0.f;
-#pragma unroll
-                for (int k = 0; k < KP; k++) acc = fmaf(src[k * TW], p.fy[a0 + k * UP], acc);
-                if (ox < p.outW && oy < p.outH) st_as<T>(yp + (int64_t)oy * p.ys[2] + ox, acc * p.gain);
+            const int ox = ox0 + cx, oyA = oy0 + rg * RPT;
+            if (ox < p.outW && oyA < p.outH) {
+                const int rowA = (rg * RPT * DOWN) / UP;                  // first(oyA) - i0 (rg RPT DOWN is a multiple of UP)
+                const float* src = sMid + rowA * MP + cx;
+                T* out = yp + (int64_t)oyA * p.ys[2] + ox;
+                const int rowsOut = min(RPT, p.outH - oyA), rowsAvail = IH - rowA;
+                if (UP == 1) sep_yrun<T, UP, DOWN, KP, 0, RPT, MP>(src, rowsAvail, out, p.ys[2], rowsOut, p.fy, p.gain);
+                else if (UP == 2) { if (rhoY == 0) sep_yrun<T, UP, DOWN, KP, 0, RPT, MP>(src, rowsAvail, out, p.ys[2], rowsOut, p.fy, p.gain); else sep_yrun<T, UP, DOWN, KP, 1 % UP, RPT, MP>(src, rowsAvail, out, p.ys[2], rowsOut, p.fy, p.gain); }
+                else {
+                    if (rhoY == 0) sep_yrun<T, UP, DOWN, KP, 0, RPT, MP>(src, rowsAvail, out, p.ys[2], rowsOut, p.fy, p.gain);
+                    else if (rhoY == 1) sep_yrun<T, UP, DOWN, KP, 1 % UP, RPT, MP>(src, rowsAvail, out, p.ys[2], rowsOut, p.fy, p.gain);
+                    else if (rhoY == 2) sep_yrun<T, UP, DOWN, KP, 2 % UP, RPT, MP>(src, rowsAvail, out, p.ys[2], rowsOut, p.fy, p.gain);
+                    else sep_yrun<T, UP, DOWN, KP, 3 % UP, RPT, MP>(src, rowsAvail, out, p.ys[2], rowsOut, p.fy, p.gain);
+                }
             }
         }
     }
@@ -127,7 +181,7 @@ int launch_sep(const SepParams& p0, cudaStream_t stream)
 {
     typedef SepGeo<UP, DOWN> G;
     constexpr int IW = ((G::TW - 1) * DOWN + UP - 1) / UP + KP + 1, IH = ((G::TH - 1) * DOWN + UP - 1) / UP + KP + 1;
-    constexpr int smemBytes = (IH * (IW | 1) + IH * G::TW) * 4;
+    constexpr int smemBytes = (IH * ((IW + 8) | 1) + IH * (G::TW + 1)) * 4;
     SepParams p = p0;
     p.tilesX = (p.outW + G::TW - 1) / G::TW;
     p.tilesY = (p.outH + G::TH - 1) / G::TH;
