@@ -191,16 +191,23 @@ __global__ void __launch_bounds__(256) upfirdn2d_small_kernel(const __grid_const
             const int a0 = (-midY) & (UP - 1);
             const int i0 = (midY + a0) >> SH;
             S acc = (S)0;
+            // taps: 16 x 16 table (launch_small), zero beyond the filter -> no tap predicates
+            const float* f0 = p.taps + a0 * 16 + b0;
+            const T* x0 = xp + (int64_t)i0 * p.xs[2] + j0;
+            if (colsIn && i0 >= 0 && i0 + KP <= p.inH) {          // interior: KP x KP unconditional loads
 #pragma unroll
-            for (int ka = 0; ka < KP; ka++) {
-                const int i = i0 + ka;
-                if (i < 0 || i >= p.inH) continue;
-                const T* xr = xp + (int64_t)i * p.xs[2] + j0;
-                const float* fr = p.taps + (a0 + ka * UP) * p.fW + b0;       // zero beyond the filter (padded table)
+                for (int ka = 0; ka < KP; ka++)
 #pragma unroll
-                for (int kb = 0; kb < KP; kb++) {
-                    const bool tapIn = b0 + kb * UP < p.fW;
-                    if (tapIn && (colsIn || (j0 + kb >= 0 && j0 + kb < p.inW))) acc += ld_as<T>(xr + kb) * (S)fr[kb * UP];
+                    for (int kb = 0; kb < KP; kb++)
+                        acc += ld_as<T>(x0 + (int64_t)ka * p.xs[2] + kb) * (S)f0[ka * UP * 16 + kb * UP];
+            } else {
+#pragma unroll
+                for (int ka = 0; ka < KP; ka++) {
+                    const int i = i0 + ka;
+                    if (i < 0 || i >= p.inH) continue;
+#pragma unroll
+                    for (int kb = 0; kb < KP; kb++)
+                        if (j0 + kb >= 0 && j0 + kb < p.inW) acc += ld_as<T>(x0 + (int64_t)ka * p.xs[2] + kb) * (S)f0[ka * UP * 16 + kb * UP];
                 }
             }
             st_as<T>(yp + (int64_t)oy * p.ys[2] + ox, acc * (S)p.gain);
@@ -209,8 +216,12 @@ __global__ void __launch_bounds__(256) upfirdn2d_small_kernel(const __grid_const
 }
 
 template <class T, int UP, int DOWN, int KP>
-int launch_small(const UpfirdnParams& p, cudaStream_t stream)
+int launch_small(const UpfirdnParams& p0, cudaStream_t stream)
 {
+    UpfirdnParams p = p0;                      // re-pitch the taps to 16 x 16, zero padded (UP * KP <= 16 per axis)
+    for (int q = 0; q < 256; q++) p.taps[q] = 0.f;
+    for (int a = 0; a < p0.fH; a++)
+        for (int b = 0; b < p0.fW; b++) p.taps[a * 16 + b] = p0.taps[a * p0.fW + b];
     const int64_t total = (int64_t)((p.outW + 31) / 32) * ((p.outH + 8 * kFastQ - 1) / (8 * kFastQ)) * p.N * p.C;
     const int64_t cap = (int64_t)sg3_sm_count() * 32;
     upfirdn2d_small_kernel<T, UP, DOWN, KP><<<(unsigned)(total < cap ? total : cap), 256, 0, stream>>>(p);
