@@ -295,8 +295,14 @@ def run_ours(args):
     except Exception:
         pass
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-    from oracle import sg3_oracle as orc   # layer geometry only (host arithmetic), for the algorithmic-work table
-    _, specs = orc.layer_specs(1024, **{k: v for k, v in R1024.items() if k in ('channel_base', 'channel_max', 'conv_kernel', 'use_radial_filters')})
+    # layer geometry for the algorithmic-work table, read off the generator that was just timed
+    specs = []
+    for lname in G.synthesis.layer_names:
+        L = getattr(G.synthesis, lname)
+        specs.append(dict(name=lname, conv_kernel=int(L.conv_kernel), in_size=int(L.in_size[0]), out_size=int(L.out_size[0]),
+                          in_channels=int(L.in_channels), out_channels=int(L.out_channels), up=int(L.up_factor),
+                          up_taps=int(L.up_taps), padding=list(L.padding),
+                          down_filter=None if L.down_filter is None else L.down_filter.detach().cpu().numpy()))
     work = layer_work(specs)
     fma_per_img = sum(r['flrelu_fma'] for r in work)
     n_calls = len(fl_events)
