@@ -129,3 +129,31 @@ def test_dropin_seam(pkg):
         for k in [k for k in sys.modules if k == 'torch_utils' or k.startswith('torch_utils.')]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_bench_work_table_matches_oracle_geometry():
+    """bench.py derives its algorithmic bytes / FLOPs from the generator it times; the numbers equal those of the oracle's
+    independent layer-geometry restatement (R-1024 4.170 GB and 247.6 GFLOP, T-1024 2.109 GB and 570.4 GFLOP)."""
+    import sys
+    sys.path.insert(0, ROOT) if ROOT not in sys.path else None
+    import torch
+    import bench
+    import sg3_b200  # noqa: F401
+    from sg3_b200 import networks
+    from oracle import sg3_oracle as orc
+    for cfg, gb, gflop in ((bench.R1024, 4.170, 247.6), (bench.T1024, 2.109, 570.4)):
+        torch.manual_seed(0)
+        G = networks.Generator(**{**cfg, 'img_resolution': 1024})
+        specs = []
+        for lname in G.synthesis.layer_names:
+            L = getattr(G.synthesis, lname)
+            specs.append(dict(name=lname, conv_kernel=int(L.conv_kernel), in_size=int(L.in_size[0]), out_size=int(L.out_size[0]),
+                              in_channels=int(L.in_channels), out_channels=int(L.out_channels), up=int(L.up_factor),
+                              up_taps=int(L.up_taps), padding=list(L.padding),
+                              down_filter=None if L.down_filter is None else L.down_filter.numpy()))
+        mine = bench.layer_work(specs)
+        _, osp = orc.layer_specs(1024, **{k: v for k, v in cfg.items() if k in ('channel_base', 'channel_max', 'conv_kernel', 'use_radial_filters')})
+        ref = bench.layer_work(osp)
+        assert [(r['flrelu_bytes'], r['conv_flops'], r['flrelu_fma']) for r in mine] == [(r['flrelu_bytes'], r['conv_flops'], r['flrelu_fma']) for r in ref]
+        assert abs(sum(r['flrelu_bytes'] for r in mine) / 1e9 - gb) < 2e-3
+        assert abs(sum(r['conv_flops'] for r in mine) / 1e9 - gflop) < 0.1
