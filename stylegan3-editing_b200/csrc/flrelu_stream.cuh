@@ -489,7 +489,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
     // store address of output row 2g-5 (the first row retired by group g), column 2*lane of this strip
     char* outRow = yPlane + (long long)(oy0 - 5) * p.ys[2] + (long long)(ox0 + 2 * lane) * p.ys[3];
     float ySum = 0.f;                   // sum of the outputs this lane stored (sign-READ kernels = backward pass only)
-    auto stageD = [&](int g, int rot) {
+    auto stageD = [&](int g, auto ROTc) {
+        constexpr int rot = decltype(ROTc)::value;        // compile-time rotation: immediate tap-table offsets, branch-free retire
         const float4* planeE = sC;
         const float4* planeO = sC + G::XH;
         if (FD == 2) {
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
             b0 = acc[S4][0].x + acc[S5][0].y; b1 = acc[S4][1].x + acc[S5][1].y;                     \
             carry[0] = acc[S4][0].y; carry[1] = acc[S4][1].y;                                       \
             acc[S4][0] = acc[S4][1] = acc[S5][0] = acc[S5][1] = make_float2(0.f, 0.f);
-            if (rot == 0) { SG3_RETIRE(4, 5) } else if (rot == 1) { SG3_RETIRE(2, 3) } else { SG3_RETIRE(0, 1) }
+            if (rot == 0) { SG3_RETIRE(4, 5) } else if (rot == 1) { SG3_RETIRE(2, 3) } else { SG3_RETIRE(0, 1) }      // resolved at compile time
 #undef SG3_RETIRE
         }
         const int oA = 2 * g - 5, oB = 2 * g - 4;
@@ -600,7 +601,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
             stageC(g, EYc);
             __syncwarp();
             flushSigns(g);
-            stageD(g, rot);
+            if (rot == 0) stageD(g, std::integral_constant<int, 0>());
+            else if (rot == 1) stageD(g, std::integral_constant<int, 1>());
+            else stageD(g, std::integral_constant<int, 2>());
             __syncwarp();
             rot = rot == 2 ? 0 : rot + 1;
             groupSlot += (UP == 2 ? 2 : 1);
