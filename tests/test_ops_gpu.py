@@ -399,3 +399,36 @@ def test_fused_backward_accumulates_bias_gradient(ops):
         dx2, db2 = torch.autograd.grad(y, [x, b], dy, create_graph=True)   # reference-style path: db = dx.sum([0, 2, 3])
         assert torch.equal(dx, dx2.detach())
         assert rel_err(db.cpu().numpy(), db2.detach().cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize('seed', list(range(24)))
+def test_fused_random_shapes_forward_backward(ops, seed):
+    """Randomised sweep over the fused kernels (strip / chunk edges, paddings of both signs, odd sizes, all filter kinds):
+    forward, dx and db against the oracle."""
+    from oracle import sg3_oracle as orc
+    rng = np.random.RandomState(1000 + seed)
+    up = int(rng.choice([2, 4]))
+    radial = bool(rng.randint(2))
+    fu, fd = _design(6 * up, radial)
+    N, C = int(rng.randint(1, 3)), int(rng.randint(1, 5))
+    H, W = int(rng.randint(20, 140)), int(rng.randint(20, 200))
+    base = [11, 10, 11, 10] if up == 2 else [-2, -5, -2, -5]
+    pad = [int(b + rng.randint(-6, 7)) for b in base]
+    x = (rng.randn(N, C, H, W) * 3).astype(np.float32)
+    b = rng.randn(C).astype(np.float32)
+    kw = dict(up=up, down=2, padding=pad, gain=float(np.sqrt(2)), slope=0.2, clamp=float(rng.choice([4.0, 256.0])))
+    try:
+        y_ref, signs = orc.filtered_lrelu(x, fu, fd, b, return_signs=True, **kw)
+    except Exception:
+        pytest.skip('degenerate output size')
+    xt, bt = cu(x, True), cu(b, True)
+    y = ops.filtered_lrelu.filtered_lrelu(xt, cu(fu), cu(fd), bt, **kw)
+    assert y.shape == y_ref.shape
+    assert rel_err(y.detach().cpu().numpy(), y_ref) < TOL32
+    dy = rng.randn(*y_ref.shape).astype(np.float32)
+    kwb = dict(kw)
+    kwb.pop('clamp')
+    dx_ref, db_ref = orc.filtered_lrelu_bwd(dy, signs, x.shape, fu, fd, **kwb)
+    dx, db = torch.autograd.grad(y, [xt, bt], cu(dy))
+    assert rel_err(dx.cpu().numpy(), dx_ref) < 5e-5
+    assert rel_err(db.cpu().numpy(), db_ref) < 5e-5
