@@ -329,3 +329,25 @@ def test_modconv_half_weights(pkg):
     b = pkg.modulated_conv.modconv_weights(cu(w), cu(s), True, torch.tensor(0.7).cuda(), half=True)
     assert b.dtype == torch.float16 and b.shape[2] == 128
     assert torch.equal(a.half(), b[:, :, :70]) and float(b[:, :, 70:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('seed', list(range(12)))
+def test_modconv_tc_random_shapes(pkg, seed):
+    """Randomised sweep over the tensor-core contractions (1x1 TF32 and 3x3 TF32) through the public modulated_conv2d op:
+    ragged channel counts, odd heights, several tile shapes; vs the oracle at the TF32 tolerance."""
+    from oracle import sg3_oracle as orc
+    rng = np.random.RandomState(500 + seed)
+    k = 1 if seed % 2 == 0 else 3
+    N, I, O = int(rng.randint(1, 4)), int(rng.randint(3, 200)), int(rng.randint(3, 300))
+    H, W = int(rng.randint(5, 90)), 4 * int(rng.randint(2, 60))
+    if k == 1 and (H * W) % 4:
+        H += 4 - (H % 4)
+    x = rng.randn(N, I, H, W).astype(np.float32)
+    w = rng.randn(O, I, k, k).astype(np.float32)
+    s = rng.randn(N, I).astype(np.float32)
+    ref = orc.modulated_conv2d(x, w, s, demodulate=True, padding=k - 1, input_gain=np.float32(0.8))
+    before = pkg.capi.lib().sg3_launch_count()
+    y = pkg.modulated_conv.modulated_conv2d(cu(x), cu(w), cu(s), demodulate=True, padding=k - 1, input_gain=torch.tensor(0.8).cuda(), math='tf32')
+    assert pkg.capi.lib().sg3_modconv_tc_supported(I, O, H, W, k, k - 1) == 0
+    assert pkg.capi.lib().sg3_launch_count() - before == 3           # style norm, weight prologue, tensor-core contraction
+    assert rel_err(y.cpu().numpy(), ref) < 3e-3
