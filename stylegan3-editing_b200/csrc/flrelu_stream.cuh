@@ -66,7 +66,7 @@ template <int UP> struct Geo {
     static constexpr int SIN_BYTES = 2 * TMA_BUF + 128;
     static constexpr int SB_BYTES = (RING + kDup) * BW * 4;
     static constexpr int SC_BYTES = 2 * XH * 16;
-    static constexpr int SS_ROW = 144;                               // sign staging bytes per row (>= AW + 3, mult of 16)
+    static constexpr int SS_ROW = 144;                               // sign staging words (>= AW + 3, multiple of 4)
     static constexpr int SS_BYTES = 4 * SS_ROW;
     // per-warp shared memory; the sign staging area exists only in sign-WRITE kernels (5 instead of 4 CTAs per SM otherwise)
     static constexpr int warp_bytes(int mode) { return ((SIN_BYTES + SB_BYTES + SC_BYTES + (mode == SG3_SIGNS_WRITE ? SS_BYTES : 0) + 127) / 128) * 128; }
@@ -135,9 +135,11 @@ __device__ __forceinline__ float2 act2(float2 v, const Params& p, unsigned rc0, 
     // lrelu(v) = max(v, slope * v) for 0 <= slope <= 1 (checked on the host); the lower clamp rides in the same 3-input max
     const float2 sv = __fmul2_rn(v, make_float2(p.slope, p.slope));
     if (MODE == SG3_SIGNS_WRITE) {
+        // code = clamped ? 2 : negative ? 1 : 0.  The sign bit of v is the "negative" code (slope >= 0: lrelu keeps the
+        // sign; -0.0 scales to -0.0 either way); |lrelu(v)| > clamp <=> v > clamp or slope * v < -clamp.
         const float r0 = fmaxf(v.x, sv.x), r1 = fmaxf(v.y, sv.y);
-        wc0 = (fabsf(r0) > p.clamp) ? 2u : ((v.x < 0.f) ? 1u : 0u);
-        wc1 = (fabsf(r1) > p.clamp) ? 2u : ((v.y < 0.f) ? 1u : 0u);
+        wc0 = (fabsf(r0) > p.clamp) ? 2u : (__float_as_uint(v.x) >> 31);
+        wc1 = (fabsf(r1) > p.clamp) ? 2u : (__float_as_uint(v.y) >> 31);
         return make_float2(fminf(fmaxf(r0, -p.clamp), p.clamp), fminf(fmaxf(r1, -p.clamp), p.clamp));
     }
     float r0, r1;
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
     uint64_t* sBar = (uint64_t*)(wsm + 2 * G::TMA_BUF);               // TMA path: one mbarrier per landing buffer
     float* sB = (float*)(wsm + G::SIN_BYTES);                          // [RING + kDup][BW]
     float4* sC = (float4*)(wsm + G::SIN_BYTES + G::SB_BYTES);          // [2][XH] rows (0,2,1,3) of one pixel
-    unsigned char* sS = wsm + G::SIN_BYTES + G::SB_BYTES + G::SC_BYTES;  // [4][SS_ROW] sign codes, one byte per pixel
+    unsigned* sS = (unsigned*)(wsm + G::SIN_BYTES + G::SB_BYTES + G::SC_BYTES);   // [SS_ROW] sign codes: one word per column, byte j = row j
 
     // ---- strip geometry --------------------------------------------------------------------------
     const int sxi = (int)(strip % p.stripsX);
@@ -419,16 +421,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
                 if (FD != 0) sC[cSlot0[r]] = make_float4(v[0].x, v[2].x, v[1].x, v[3].x);
                 if (MODE == SG3_SIGNS_WRITE) {
                     const int xd0 = xp - ex;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) sS[j * G::SS_ROW + xd0] = (unsigned char)code0[j];
+                    sS[xd0] = code0[0] | (code0[1] << 8) | (code0[2] << 16) | (code0[3] << 24);
                 }
             }
             if (cSlot1[r] >= 0) {
                 if (FD != 0) sC[cSlot1[r]] = make_float4(v[0].y, v[2].y, v[1].y, v[3].y);
                 if (MODE == SG3_SIGNS_WRITE) {
                     const int xd1 = xp - ex + 1;
-#pragma unroll
-                    for (int j = 0; j < 4; j++) sS[j * G::SS_ROW + xd1] = (unsigned char)code1[j];
+                    sS[xd1] = code1[0] | (code1[1] << 8) | (code1[2] << 16) | (code1[3] << 24);
                 }
             }
         }
@@ -452,24 +452,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, UP == 2 ? 5 : 4) kernel(con
     // rows [0, ownH) -- the last strip/chunk also owns the filter tail.
     const int ownW = (sxi == p.stripsX - 1) ? 2 * (tws - 1) + kDownTaps : 2 * G::TW;
     const int ownH = (cyi == p.chunksY - 1) ? 2 * (chs - 1) + kDownTaps : 2 * p.chunkRows;
+    // lane l owns sign byte l of the strip (columns 4l .. 4l+3 of D's frame), if the strip owns that byte at all
+    const int sgnByte = ((Xs + p.sx) >> 2) + lane;
+    const bool sgnLane = lane < ((ownW + 3) >> 2) && sgnByte >= 0 && sgnByte < p.sWb;
+    uint8_t* sgnPtr = p.s + (sPlane + Ys + p.sy) * p.sWb + sgnByte;       // row 4g + j of the strip: + (4g + j) * sWb
     auto flushSigns = [&](int g) {
         if (MODE != SG3_SIGNS_WRITE) return;
-        const int nb = (ownW + 3) >> 2;
-        const int byte0 = (Xs + p.sx) >> 2;
+        if (sgnLane) {
+            // four columns x four rows -> one word whose byte j is the packed sign byte of row j
+            // (& 0x03030303: staging words of columns this strip never computes are uninitialised)
+            const uint4 c4 = *(const uint4*)(sS + 4 * lane);
+            const unsigned t = (c4.x & 0x03030303u) | ((c4.y & 0x03030303u) << 2) | ((c4.z & 0x03030303u) << 4) | ((c4.w & 0x03030303u) << 6);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int rd = 4 * g + j;
-            const int sY = Ys + rd + p.sy;
-            if (rd >= ownH || sY < 0 || sY >= p.sH) continue;
-            uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
-            for (int q = lane; q < nb; q += 32) {
-                // & 0x03030303: staging bytes of columns this strip never computes are uninitialised
-                const unsigned wv = *(const unsigned*)(sS + j * G::SS_ROW + 4 * q) & 0x03030303u;
-                const unsigned packed = (wv | (wv >> 6) | (wv >> 12) | (wv >> 18)) & 0xffu;
-                const int bq = byte0 + q;
-                if (bq >= 0 && bq < p.sWb) srow[bq] = (uint8_t)packed;
+            for (int j = 0; j < 4; j++) {
+                const int rd = 4 * g + j;
+                const int sY = Ys + rd + p.sy;
+                if (rd < ownH && sY >= 0 && sY < p.sH) sgnPtr[(long long)j * p.sWb] = (uint8_t)(t >> (8 * j));
             }
         }
+        sgnPtr += 4LL * p.sWb;
     };
 
     // ---- stage D: down-by-2 FIR, accumulated in registers -------------------------------------------
