@@ -65,7 +65,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float t, float2 c) { return __
 __device__ __forceinline__ int vslot(int c) { return (c & 3) * (kBW / 4 + 1) + (c >> 2); }
 
 template <class T, int DOWN, int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 4) kernel(const __grid_constant__ Params p)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, DOWN == 2 ? 5 : 4) kernel(const __grid_constant__ Params p)
 {
     typedef Geo<DOWN> G;
     extern __shared__ __align__(128) unsigned char smem_raw[];
