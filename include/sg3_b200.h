@@ -178,6 +178,12 @@ int sg3_modconv_wgrad(const float* dy, const float* x, float* dw, int N, int I, 
 
 int sg3_modconv_tc_supported(int I, int O, int H, int W, int k, int pad);
 
+/* Backward of sg3_modconv_weights for 1x1 kernels (the chain rule of networks_stylegan3.py:39-56, ~35 eager kernels per layer
+ * when left to autograd): dwmod [N][O][ldw] = gradient wrt the per-sample weights (e.g. from sg3_modconv_wgrad) ->
+ * dw [O][I], ds [N][I].  scratch: >= (1 + N*I) floats of device memory.  I <= 2048, otherwise SG3_E_NOKERNEL. */
+int sg3_modconv_weights_bwd(const float* dwmod, const float* w, const float* s, const float* input_gain, int gainMode,
+                            float* dw, float* ds, float* scratch, int N, int I, int O, int ldw, int demodulate, void* stream);
+
 int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
                     int N, int I, int O, int H, int W, int k, int pad, int ldw,
                     int mathMode, int dtype, void* stream);

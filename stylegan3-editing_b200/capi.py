@@ -57,6 +57,7 @@ _PROTOS = {
     'sg3_upfirdn2d_sep': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, ctypes.POINTER(c_i64x4), ctypes.POINTER(c_i64x4),
                                 _I, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
     'sg3_modconv_weights': (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    'sg3_modconv_weights_bwd': (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'sg3_modconv_tc_supported': (_I, [_I, _I, _I, _I, _I, _I]),
     'sg3_modconv_wgrad': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'sg3_modconv_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -104,6 +104,98 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
     }
 }
 
+
+// ---- backward of the weight prologue (1x1 kernels): dWf = dL/d wmod [N][O][ldw]  ->  dw [O][I], dsn [N][I] ---------------
+// Chain rule of networks_stylegan3.py:39-56 in one pass per output channel (the torch version of this chain is ~35 small
+// kernels per layer):  wn = w rw, sn = s rs, Wm = wn sn, q = sum_i Wm^2 + 1e-8, wmod = Wm q^-1/2 g
+//   dW = dWf g;  dd = sum_i dW Wm;  dWm = dW q^-1/2 - Wm dd q^-3/2;  dwn = sum_n dWm sn;  dsn = sum_o dWm wn (atomics)
+//   dw = rw dwn - w rw^3 (sum_i dwn w) / I.     The style side (ds from dsn, a global reduction) is modconv_style_bwd_kernel.
+// One CTA per output channel o; thread t owns input channels t, t + 256, ... (up to kMaxIPerThread of them).
+constexpr int kMaxIPerThread = 8;      // I <= 2048
+
+__global__ void __launch_bounds__(256) modconv_weights_bwd_kernel(
+    const float* __restrict__ dWf, const float* __restrict__ w, const float* __restrict__ s, const float* __restrict__ gain, int gainMode,
+    const float* __restrict__ scratch, float* __restrict__ dw, float* __restrict__ dsn,
+    int N, int I, int O, int ldw, int demodulate)
+{
+    __shared__ float red[32];
+    const int o = blockIdx.x;
+    const float* wo = w + (size_t)o * I;
+    float wreg[kMaxIPerThread], dwn[kMaxIPerThread];
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < kMaxIPerThread; u++) {
+        const int i = threadIdx.x + 256 * u;
+        wreg[u] = i < I ? wo[i] : 0.f;
+        dwn[u] = 0.f;
+        acc += wreg[u] * wreg[u];
+    }
+    float rw = 1.f, rs = 1.f;
+    if (demodulate) {
+        acc = block_sum(acc, red);
+        rw = rsqrtf(acc / (float)I);
+        rs = scratch[0];
+    }
+    for (int n = 0; n < N; n++) {
+        const float* sn = s + (size_t)n * I;
+        const float* dr = dWf + ((size_t)n * O + o) * ldw;
+        float Wm[kMaxIPerThread], dW[kMaxIPerThread];
+        float q = 0.f, dd = 0.f;
+#pragma unroll
+        for (int u = 0; u < kMaxIPerThread; u++) {
+            const int i = threadIdx.x + 256 * u;
+            float g = 1.f;
+            if (i < I) g = gainMode == 1 ? gain[0] : gainMode == 2 ? gain[i] : gainMode == 3 ? gain[(size_t)n * I + i] : 1.f;
+            Wm[u] = i < I ? (wreg[u] * rw) * (sn[i] * rs) : 0.f;
+            dW[u] = i < I ? dr[i] * g : 0.f;
+            q += Wm[u] * Wm[u];
+            dd += dW[u] * Wm[u];
+        }
+        float d = 1.f, c = 0.f;
+        if (demodulate) {
+            q = block_sum(q, red) + 1e-8f;
+            dd = block_sum(dd, red);
+            d = rsqrtf(q);
+            c = dd * d / q;                       // dd q^-3/2
+        }
+#pragma unroll
+        for (int u = 0; u < kMaxIPerThread; u++) {
+            const int i = threadIdx.x + 256 * u;
+            if (i < I) {
+                const float dWm = dW[u] * d - Wm[u] * c;
+                dwn[u] += dWm * (sn[i] * rs);
+                atomicAdd(dsn + (size_t)n * I + i, dWm * (wreg[u] * rw));
+            }
+        }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int u = 0; u < kMaxIPerThread; u++) dot += dwn[u] * wreg[u];
+    if (demodulate) dot = block_sum(dot, red);
+#pragma unroll
+    for (int u = 0; u < kMaxIPerThread; u++) {
+        const int i = threadIdx.x + 256 * u;
+        if (i < I) dw[(size_t)o * I + i] = demodulate ? rw * dwn[u] - wreg[u] * rw * rw * rw * dot / (float)I : dwn[u];
+    }
+}
+
+// ds = rs dsn - s rs^3 (sum_{n,i} dsn s) / (N I)   (demodulate), else ds = dsn.  One CTA.
+__global__ void __launch_bounds__(1024) modconv_style_bwd_kernel(const float* __restrict__ dsn, const float* __restrict__ s,
+                                                                 const float* __restrict__ scratch, float* __restrict__ ds, int count, int demodulate)
+{
+    __shared__ float red[32];
+    if (!demodulate) {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) ds[i] = dsn[i];
+        return;
+    }
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) acc += dsn[i] * s[i];
+    acc = block_sum(acc, red);
+    const float rs = scratch[0];
+    const float k = rs * rs * rs * acc / (float)count;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) ds[i] = rs * dsn[i] - s[i] * k;
+}
+
 // ---- exact FP32 contraction: 64 output channels x 64 pixels per CTA, K chunks of 16 --------
 constexpr int BO = 64, BP = 64, BK = 16;
 
@@ -220,6 +312,23 @@ SG3_EXPORT int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
     unsigned grid = (unsigned)(total < cap ? total : cap);
     modconv_fwd_simt_kernel<<<grid, 256, 0, st>>>((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, OH, OW, ldw);
     return sg3_launch_status();
+}
+
+SG3_EXPORT int sg3_modconv_weights_bwd(const float* dwmod, const float* w, const float* s, const float* input_gain, int gainMode,
+                                       float* dw, float* ds, float* scratch, int N, int I, int O, int ldw, int demodulate, void* stream)
+{
+    if (!dwmod || !w || !s || !dw || !ds || !scratch || N < 1 || I < 1 || O < 1 || ldw < I) return SG3_E_INVALID;
+    if (gainMode < 0 || gainMode > 3 || (gainMode && !input_gain)) return SG3_E_INVALID;
+    if (I > 256 * kMaxIPerThread) return SG3_E_NOKERNEL;
+    if ((int64_t)N * I > INT32_MAX) return SG3_E_TOOLARGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    // scratch: [0] = rs, [1 .. 1 + N*I) = dsn accumulator (zeroed here)
+    cudaError_t e = cudaMemsetAsync(scratch + 1, 0, (size_t)N * I * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    if (demodulate) style_norm_kernel<<<1, 1024, 0, st>>>(s, N * I, scratch);
+    modconv_weights_bwd_kernel<<<(unsigned)O, 256, 0, st>>>(dwmod, w, s, input_gain, gainMode, scratch, dw, scratch + 1, N, I, O, ldw, demodulate);
+    modconv_style_bwd_kernel<<<1, 1024, 0, st>>>(scratch + 1, s, scratch, ds, N * I, demodulate);
+    return sg3_launch_status(demodulate ? 3 : 2);
 }
 
 SG3_EXPORT int sg3_modconv_tc_supported(int I, int O, int H, int W, int k, int pad)

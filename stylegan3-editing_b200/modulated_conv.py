@@ -157,6 +157,39 @@ class _ModConv(torch.autograd.Function):
         return out[0], out[1], out[2], None, None, None, None
 
 
+def _gain_arg(input_gain, N, I):
+    """(gainMode, contiguous float32 tensor or None) as sg3_modconv_weights expects."""
+    if input_gain is None:
+        return 0, None
+    g = input_gain.detach().float()
+    if g.numel() == 1:
+        return 1, g.reshape(1).contiguous()
+    if g.ndim == 1 and g.shape[0] == I:
+        return 2, g.contiguous()
+    return 3, g.expand(N, I).contiguous()
+
+
+def _weights_backward(dWn, w, s, input_gain, demodulate, ldw):
+    """Chain rule through the weight prologue (:39-56) on one kernel pair (`sg3_modconv_weights_bwd`): gradient wrt the
+    per-sample weights [N, O, ldw] -> (dw [O, I], ds [N, I]).  None when the library has no kernel (I > 2048)."""
+    O, I = w.shape[0], w.shape[1]
+    N = s.shape[0]
+    w2 = w.detach().reshape(O, I).float().contiguous()
+    s2 = s.detach().float().contiguous()
+    mode, g = _gain_arg(input_gain, N, I)
+    dw = torch.empty([O, I], dtype=torch.float32, device=w.device)
+    ds = torch.empty([N, I], dtype=torch.float32, device=w.device)
+    scratch = torch.empty([1 + N * I], dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        rc = capi.lib().sg3_modconv_weights_bwd(dWn.data_ptr(), w2.data_ptr(), s2.data_ptr(), g.data_ptr() if g is not None else None,
+                                                mode, dw.data_ptr(), ds.data_ptr(), scratch.data_ptr(), N, I, O, ldw,
+                                                int(bool(demodulate)), capi.stream_ptr(w.device))
+    if rc == capi.SG3_E_NOKERNEL:
+        return None
+    capi.check(rc, 'sg3_modconv_weights_bwd')
+    return dw, ds
+
+
 def _native_backward_1x1(x, w, s, input_gain, dy, demodulate, need):
     """dx, dw, ds of the 1x1 modulated conv on the tcgen05 kernels (TF32): dgrad = the forward GEMM with the
     transposed modulated weights; wgrad = split-K GEMM over pixels; then the chain rule through the weight
@@ -176,6 +209,10 @@ def _native_backward_1x1(x, w, s, input_gain, dy, demodulate, need):
             rc = capi.lib().sg3_modconv_wgrad(dy.data_ptr(), xc.data_ptr(), dWn.data_ptr(), N, I, O, H, W, ldw,
                                               capi.stream_ptr(x.device))
         capi.check(rc, 'sg3_modconv_wgrad')
+        fused = _weights_backward(dWn, w, s, input_gain, demodulate, ldw)
+        if fused is not None:
+            dw, ds = fused
+            return dx, (dw.reshape(w.shape).to(w.dtype) if need[1] else None), (ds.to(s.dtype) if need[2] else None)
         dW = dWn[:, :, :I]                                             # grad wrt the final per-sample weights [N, O, I]
         w2 = w.detach().reshape(O, I).float()
         s2 = s.detach().float()

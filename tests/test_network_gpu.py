@@ -351,3 +351,30 @@ def test_modconv_tc_random_shapes(pkg, seed):
     assert pkg.capi.lib().sg3_modconv_tc_supported(I, O, H, W, k, k - 1) == 0
     assert pkg.capi.lib().sg3_launch_count() - before == 3           # style norm, weight prologue, tensor-core contraction
     assert rel_err(y.cpu().numpy(), ref) < 3e-3
+
+
+@pytest.mark.parametrize('demod', [True, False])
+def test_modconv_weights_backward_kernel(pkg, demod):
+    """sg3_modconv_weights_bwd (fused chain rule through the weight prologue) vs torch autograd through the same formula."""
+    rng = np.random.RandomState(11)
+    N, O, I = 3, 45, 70
+    w = cu(rng.randn(O, I, 1, 1).astype(np.float32), True)
+    s = cu(rng.randn(N, I).astype(np.float32), True)
+    for gain in (None, torch.tensor(0.7).cuda(), cu(rng.rand(I).astype(np.float32) + 0.5)):
+        ldw = (I + 31) // 32 * 32
+        dWn = torch.zeros(N, O, ldw, device='cuda')
+        dWn[:, :, :I] = cu(rng.randn(N, O, I).astype(np.float32))
+        # reference: autograd through the prologue expression of networks_stylegan3.py:39-56
+        ww, ss = w, s
+        if demod:
+            ww = ww * ww.square().mean([1, 2, 3], keepdim=True).rsqrt()
+            ss = ss * ss.square().mean().rsqrt()
+        W = ww.reshape(1, O, I) * ss.unsqueeze(1)
+        if demod:
+            W = W * (W.square().sum(dim=2, keepdim=True) + 1e-8).rsqrt()
+        if gain is not None:
+            W = W * gain.expand(N, I).unsqueeze(1)
+        dw_ref, ds_ref = torch.autograd.grad(W, [w, s], dWn[:, :, :I])
+        dw, ds = pkg.modulated_conv._weights_backward(dWn, w, s, gain, demod, ldw)
+        assert rel_err(dw.cpu().numpy(), dw_ref.reshape(O, I).cpu().numpy()) < 2e-5
+        assert rel_err(ds.cpu().numpy(), ds_ref.cpu().numpy()) < 2e-5
