@@ -88,8 +88,10 @@ def cpu_sample(seconds, threads=None):
     from oracle import sg3_oracle as orc
     import sg3_b200  # noqa: F401  (only for the random-init weights; no kernel is launched here)
     from sg3_b200 import networks
-    if threads:
-        orc.set_num_threads(threads)
+    if not threads:
+        # all host cores of this process: torchrun exports OMP_NUM_THREADS=1, which would make the CPU arm 16x slower than it is
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    orc.set_num_threads(threads)
     cores = orc.num_threads()
     torch.manual_seed(0)
     G = networks.Generator(**R1024).eval().requires_grad_(False)
@@ -342,8 +344,8 @@ def run_ours(args):
                       fp32_pipe=dict(achieved_tfma=fma_rate, peak_tfma=fp32_peak_tfma, frac=fma_rate / fp32_peak_tfma,
                                      note='polyphase FMAs of the fused op; fp32 SIMT is the roof that binds it (DESIGN.md)')),
     )
-    if not args.no_cpu_baseline:
-        out['cpu_baseline'] = cpu_sample(args.cpu_seconds)
+    # cpu_baseline: timed on rank 0 at N = 1 only (the host cores are shared by all ranks of a multi-GPU run)
+    out['cpu_baseline'] = cpu_sample(args.cpu_seconds) if (world == 1 and not args.no_cpu_baseline) else None
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
