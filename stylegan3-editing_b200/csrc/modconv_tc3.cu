@@ -51,6 +51,8 @@ struct Tc3Params {
     int wSlots, xGroupBytes;
     int wRows, wSlotBytes;     // rows of a W slot (min(128, ceil8(O))) and its size
     int resident;              // the ring holds every (chunk, tap) of the layer: W is reloaded only when (n, o-tile) changes
+    int m64;                   // O <= 64: M = 64 MMAs; their accumulator occupies lanes 32q .. 32q+15 of TMEM (measured,
+                               // tools/tc_m64_probe.cu), a second one fits at lane offset 16 in the SAME columns -> two stages
     long long totalTiles;
 };
 
@@ -129,7 +131,7 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
         // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues (tc_common.cuh) ----------------
         // D = F32, A = B = TF32, A K-major (bit 15 = 0), B MN-major (bit 16 = 1), N = NPX, M = 128
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
-                               ((uint32_t)(p.NPX >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                               ((uint32_t)(p.NPX >> 3) << 17) | ((uint32_t)((p.m64 ? 64 : 128) >> 4) << 24);
         const uint64_t dA = umma_desc(wRing, 16, 1024), dB = umma_desc(xRing, BK3 * 128, 512, kLayoutSw128Base32);
         const uint32_t aLo0 = (uint32_t)dA, aHi = (uint32_t)(dA >> 32), bLo0 = (uint32_t)dB, bHi = (uint32_t)(dB >> 32);
         const uint32_t rowStep = rowBytes >> 4, groupStep = (uint32_t)p.xGroupBytes >> 4;
@@ -138,7 +140,7 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             const uint32_t as = p.accStages == 2 ? (tc & 1) : 0, use = p.accStages == 2 ? (tc >> 1) : tc;
             if (use > 0) mbar_wait(smem_u32(&barAccEmpty[as]), (use - 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t acc = tmem + as * (uint32_t)p.accStageCols;
+            const uint32_t acc = p.m64 ? tmem + (as ? (16u << 16) : 0u) : tmem + as * (uint32_t)p.accStageCols;
             for (int c = 0; c < p.kChunks; c++, xIt++) {
                 const uint32_t xg = xIt & 1;
                 mbar_wait(smem_u32(&barXFull[xg]), (xIt >> 1) & 1);
@@ -170,7 +172,6 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
         // A warp can only read its own 32 TMEM lanes (= 32 channels), but once a 32-column block is staged in shared memory
         // any warp can store it: the four warps share the channel rows of every block, so narrow layers (O = 32: one
         // warp owns all the channels) still store with 128 threads.
-        float* st = stage + warp * (32 * STAGE_PITCH);
         uint32_t tc = 0;
         for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x, tc++) {
             int n, oy0, tx, o0;
@@ -178,9 +179,13 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             const uint32_t as = p.accStages == 2 ? (tc & 1) : 0, use = p.accStages == 2 ? (tc >> 1) : tc;
             mbar_wait(smem_u32(&barAccFull[as]), use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t acc = tmem + ((uint32_t)(32 * warp) << 16) + as * (uint32_t)p.accStageCols;
-            const int nrows = min(128, p.O - o0);                 // valid channels (TMEM lanes) of this tile
-            const bool mine = 32 * warp < nrows;
+            const uint32_t acc = tmem + ((uint32_t)(32 * warp) << 16) + (p.m64 ? 0u : as * (uint32_t)p.accStageCols);
+            const int nrows = min(128, p.O - o0);                 // valid channels of this tile
+            // channel held by this lane: M = 128 -> lane 32w + l; M = 64 -> lanes 16 as .. 16 as + 15 of each warp hold rows 16w ..
+            const int laneRow = p.m64 ? 16 * warp + (lane & 15) : 32 * warp + lane;
+            const bool laneValid = !p.m64 || (uint32_t)(lane >> 4) == as;
+            const bool mine = (p.m64 ? 16 * warp : 32 * warp) < nrows;
+            float* st = stage + laneRow * STAGE_PITCH;
             const int colEnd = p.colBase + p.S;
             const size_t chStep = (size_t)p.OH * p.OW;
             for (int oyl = 0; oyl < p.R; oyl++) {
@@ -199,7 +204,7 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                             v.y = __uint_as_float(e[j + 1]) + __uint_as_float(o[j]);
                             v.z = __uint_as_float(e[j + 2]) + __uint_as_float(o[j + 1]);
                             v.w = __uint_as_float(e[j + 3]) + __uint_as_float(o[j + 2]);
-                            *reinterpret_cast<float4*>(st + lane * STAGE_PITCH + j) = v;
+                            if (laneValid) *reinterpret_cast<float4*>(st + j) = v;
                         }
                         carry = __uint_as_float(o[31]);
                     }
@@ -261,10 +266,12 @@ bool plan_tc3(Tc3Params& p)
             const double mma = 36.0 * r * perMma;
             const double load = ((resident ? 0.0 : 9.0 * p.wSlotBytes) + (double)xGroup) / 80.0;     // operand stream at ~80 B/clk/SM (fitted; 40 over-penalised wide tiles)
             const double epi = 530.0 * r * ((p.colBase + s + 31) / 32);
-            const double cost = (double)tiles * (1700.0 + p.kChunks * (mma > load ? mma : load) + epi);
+            const double kloop = p.kChunks * (mma > load ? mma : load);
+            // M = 64 (two accumulator stages): the epilogue of a tile overlaps the K loop of the next one
+            const double cost = (double)tiles * (1700.0 + (p.m64 ? (kloop > epi ? kloop : epi) : kloop + epi));
             if (cost < best) {
                 best = cost; found = true;
-                p.NPX = npx; p.R = r; p.CW = cw; p.S = s; p.accStages = 1; p.accStageCols = stageCols;
+                p.NPX = npx; p.R = r; p.CW = cw; p.S = s; p.accStages = p.m64 ? 2 : 1; p.accStageCols = stageCols;
                 p.wSlots = wSlots; p.xGroupBytes = xGroup; p.resident = resident ? 1 : 0;
                 int cols = 32;
                 while (cols < need) cols <<= 1;
@@ -299,6 +306,7 @@ int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int 
     p.kChunks = (I + BK3 - 1) / BK3;
     p.xoff = pad == 2 ? 4 : 0;
     p.colBase = pad == 2 ? 4 : 2;
+    p.m64 = O <= 64 ? 1 : 0;
     p.wRows = O >= 128 ? 128 : (O + 7) & ~7;
     p.wSlotBytes = p.wRows * BK3 * 4;
     if (!plan_tc3(p)) return SG3_E_NOKERNEL;
