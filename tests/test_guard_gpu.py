@@ -246,3 +246,55 @@ def test_guard_tiny_generator_forward_backward(pkg, name, force_fp32):
         pkg.modulated_conv.set_math(None)
     assert bool(torch.isfinite(img).all())
     assert all(g is None or bool(torch.isfinite(g).all()) for g in grads)
+
+
+@pytest.mark.parametrize('case', ['R_up2_dense', 'R_up4_dense', 'T_up2_sep'])
+def test_fused_kernels_are_deterministic(pkg, case):
+    """The racecheck substitute: warps of the stream kernels share nothing and order their private shared-memory ring
+    with __syncwarp / mbarriers only, so a missing fence shows up as run-to-run differences.  The same launch is repeated
+    with the SMs oversubscribed (several waves, a second stream competing) and must be bit-identical every time: forward,
+    sign tensor and dx.  (db uses fp32 atomics and is order-dependent by design; it is not compared.)"""
+    up, radial = {'R_up2_dense': (2, True), 'R_up4_dense': (4, True), 'T_up2_sep': (2, False)}[case]
+    fu, fd = _design(pkg, 6 * up, radial)
+    torch.manual_seed(1)
+    x = (torch.randn(2, 24, 276 if up == 2 else 148, 276 if up == 2 else 148, device='cuda') * 3).requires_grad_(True)
+    b = torch.randn(24, device='cuda')
+    pad = [11, 10, 11, 10] if up == 2 else [-2, -5, -2, -5]
+    side = torch.cuda.Stream()
+    noise = torch.randn(1 << 24, device='cuda')
+    ref = None
+    for it in range(6):
+        with torch.cuda.stream(side):                      # a competing memory-bound kernel on another stream
+            noise.mul_(1.0001)
+        y = pkg.filtered_lrelu.filtered_lrelu(x, fu, fd, b, up=up, down=2, padding=pad, clamp=4.0)
+        nb = (2 * y.shape[3] - 1 + 11) // 4                # whole bytes of the active sign region (the 16-pixel row padding is never written)
+        signs = y.grad_fn.saved_tensors[0][..., :nb].clone()      # the sign tensor the forward kernel wrote (before backward frees it)
+        (dx,) = torch.autograd.grad(y, x, torch.ones_like(y))
+        cur = (y.detach().clone(), dx.clone(), signs)
+        if ref is None:
+            ref = cur
+        else:
+            assert torch.equal(cur[0], ref[0]), f'forward differs in run {it}'
+            assert torch.equal(cur[1], ref[1]), f'dx differs in run {it}'
+            assert torch.equal(cur[2], ref[2]), f'sign tensor differs in run {it}'
+    torch.cuda.synchronize()
+
+
+def test_tensor_core_conv_is_deterministic(pkg):
+    """Same for the tcgen05 kernels (TMA ring, TMEM double buffering, mbarrier hand-overs): forward and dgrad of the 1x1 and
+    3x3 contractions are bit-identical from run to run (wgrad is split-K with fp32 atomics: order-dependent by design)."""
+    torch.manual_seed(2)
+    for k, (I, O, H, W) in ((1, (161, 102, 96, 128)), (3, (81, 51, 94, 132)), (3, (40, 32, 70, 224))):
+        x = torch.randn(3, I, H, W, device='cuda', requires_grad=True)
+        w = torch.randn(O, I, k, k, device='cuda')
+        s = torch.randn(3, I, device='cuda')
+        ref = None
+        for it in range(5):
+            y = pkg.modulated_conv.modulated_conv2d(x, w, s, demodulate=True, padding=k - 1, math='tf32')
+            (dx,) = torch.autograd.grad(y, x, torch.ones_like(y))
+            if ref is None:
+                ref = (y.detach().clone(), dx.clone())
+            else:
+                assert torch.equal(y.detach(), ref[0]), f'k={k} forward differs in run {it}'
+                if k == 1:                              # 3x3 dgrad is cuDNN (may pick non-deterministic algorithms)
+                    assert torch.equal(dx, ref[1]), f'k={k} dgrad differs in run {it}'
