@@ -12,7 +12,7 @@ Everything is backed by libsg3_b200.so (C ABI in include/sg3_b200.h); there is n
 from . import capi
 from . import bias_act, filtered_lrelu, upfirdn2d   # noqa: F401  (reference-compatible op modules)
 
-__all__ = ['capi', 'bias_act', 'filtered_lrelu', 'upfirdn2d', 'install']
+__all__ = ['capi', 'bias_act', 'filtered_lrelu', 'upfirdn2d', 'install', 'patch_modulated_conv']
 
 
 def install():
@@ -24,3 +24,11 @@ def install():
     """
     from . import dropin
     return dropin.install()
+
+
+def patch_modulated_conv(target=None):
+    """Also route the reference's module-level `modulated_conv2d` (pure PyTorch + cuDNN, networks_stylegan3.py:24-63) to the
+    fused prologue + tcgen05 contraction; `target` = None (the imported `models.stylegan3.networks_stylegan3`), a module, or a
+    generator object (covers unpickled generators).  See dropin.patch_modulated_conv."""
+    from . import dropin
+    return dropin.patch_modulated_conv(target)

@@ -1,6 +1,7 @@
 """Drop-in seam: expose this package's op modules as `torch_utils.ops.{filtered_lrelu,bias_act,
 upfirdn2d,conv2d_gradfix}` so the reference's model code (`from torch_utils.ops import ...`,
 networks_stylegan3.py:18) and pickled generators pick them up unchanged."""
+import importlib
 import sys
 import types
 
@@ -34,15 +35,20 @@ def install(override_existing=True):
         'torch_utils.ops.bias_act': bias_act,
         'torch_utils.ops.upfirdn2d': upfirdn2d,
     }
-    if 'torch_utils' not in sys.modules:
-        pkg = types.ModuleType('torch_utils')
-        pkg.__path__ = []
-        sys.modules['torch_utils'] = pkg
-    if 'torch_utils.ops' not in sys.modules:
-        ops = types.ModuleType('torch_utils.ops')
-        ops.__path__ = []
-        sys.modules['torch_utils.ops'] = ops
-        setattr(sys.modules['torch_utils'], 'ops', ops)
+    # Prefer the real packages when the reference tree is on sys.path (its `torch_utils.misc` / `.persistence` must stay
+    # importable: networks_stylegan3.py:17); synthesise empty ones only when there is no `torch_utils` at all.  Importing the
+    # reference's `torch_utils.ops` package itself is harmless (empty __init__); its op submodules are never imported because
+    # the aliases below are registered first.
+    for name in ('torch_utils', 'torch_utils.ops'):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except ImportError:
+                pkg = types.ModuleType(name)
+                pkg.__path__ = []
+                sys.modules[name] = pkg
+    if getattr(sys.modules['torch_utils'], 'ops', None) is not sys.modules['torch_utils.ops']:
+        setattr(sys.modules['torch_utils'], 'ops', sys.modules['torch_utils.ops'])
     ops = sys.modules['torch_utils.ops']
     if 'torch_utils.ops.conv2d_gradfix' not in sys.modules:
         mods['torch_utils.ops.conv2d_gradfix'] = _conv2d_gradfix_module()
@@ -51,3 +57,45 @@ def install(override_existing=True):
             sys.modules[name] = mod
             setattr(ops, name.rsplit('.', 1)[1], mod)
     return sorted(mods)
+
+
+def patch_modulated_conv(target=None):
+    """Point the reference's module-level `modulated_conv2d` (networks_stylegan3.py:24, looked up as a module global by
+    `SynthesisLayer.forward`, :360) at this package's fused implementation (same signature).
+
+    `target` may be
+      * None: `models.stylegan3.networks_stylegan3`, if it has been imported;
+      * a module;
+      * a generator / any `torch.nn.Module`: every Python module that defines the class of one of its submodules and has a
+        `modulated_conv2d` global is patched -- this covers pickled generators, whose source `torch_utils/persistence.py:191-229`
+        re-imports under a private module name.
+    Returns the names of the patched modules (empty list: nothing to patch)."""
+    from .modulated_conv import modulated_conv2d
+    mods = []
+    if target is None:
+        m = sys.modules.get('models.stylegan3.networks_stylegan3')
+        if m is not None:
+            mods.append(m)
+    elif isinstance(target, types.ModuleType):
+        mods.append(target)
+    elif isinstance(target, torch.nn.Module):
+        seen = set()
+        for sub in target.modules():
+            # walk the MRO: `persistence.persistent_class` wraps every reference class in a subclass that lives in
+            # torch_utils.persistence; the class whose forward() looks up `modulated_conv2d` is one step up
+            for klass in type(sub).__mro__:
+                name = klass.__module__
+                if name not in seen:
+                    seen.add(name)
+                    m = sys.modules.get(name)
+                    if m is not None:
+                        mods.append(m)
+    else:
+        raise TypeError('patch_modulated_conv: expected None, a module or a torch.nn.Module')
+    done = []
+    for m in mods:
+        if callable(getattr(m, 'modulated_conv2d', None)) and m.modulated_conv2d is not modulated_conv2d:
+            m._sg3_b200_original_modulated_conv2d = m.modulated_conv2d
+            m.modulated_conv2d = modulated_conv2d
+            done.append(m.__name__)
+    return done

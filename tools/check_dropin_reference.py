@@ -1,0 +1,178 @@
+"""Zero-edit drop-in check: the UNMODIFIED reference model code (models/stylegan3/networks_stylegan3.py) on these kernels.
+
+    python tools/check_dropin_reference.py [--time]
+
+Needs a CUDA device and the reference tree: $SG3_REF_ROOT, else baseline/_ref/ (git-ignored staging copy of the reference's
+`models/stylegan3`, `torch_utils/{misc,persistence}.py` and `dnnlib` -- made with tools/stage_reference.sh in the authoring
+container; the reference itself is never part of this repository).  What it does, per INTEGRATION.md section 1:
+
+  1. `sg3_b200.install()` and then `from models.stylegan3 import networks_stylegan3` -- the reference's SynthesisLayer now
+     calls sg3_b200.filtered_lrelu / bias_act; its own `modulated_conv2d` (PyTorch + cuDNN) is still in place;
+  2. the reference Generator (seed-0 random init) reproduces the golden images the reference produced on CPU with impl='ref'
+     (tests/golden/tiny.npz, r256.npz), forward and all parameter gradients;
+  3. `sg3_b200.patch_modulated_conv(G)` swaps the conv for the fused prologue + tcgen05 kernels: same checks (fp32 and TF32);
+  4. --time: StyleGAN3-R 1024^2, batch 4, reference model code on (a) our stencil ops + its own cuDNN conv, (b) all kernels
+     ours, (c) sg3_b200.networks.Generator.
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = os.environ.get('SG3_REF_ROOT') or os.path.join(ROOT, 'baseline', '_ref')
+if not os.path.exists(os.path.join(REF, 'models', 'stylegan3', 'networks_stylegan3.py')):
+    print(f'reference tree not found at {REF}: nothing checked')
+    sys.exit(0)
+sys.path.insert(0, REF)
+
+import numpy as np
+import torch
+
+import sg3_b200
+from sg3_b200 import modulated_conv, networks
+
+print('install():', sg3_b200.install())
+from models.stylegan3 import networks_stylegan3 as ref          # noqa: E402  (the reference, unmodified)
+
+assert ref.filtered_lrelu is sg3_b200.filtered_lrelu and ref.bias_act is sg3_b200.bias_act
+assert ref.modulated_conv2d is not modulated_conv.modulated_conv2d      # still the reference's own (decorated) function
+sg3_b200.filtered_lrelu._quiet_fallback = True
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
+TINY = dict(
+    tinyR=dict(z_dim=64, c_dim=0, w_dim=64, img_resolution=64, img_channels=3, channel_base=2048, channel_max=32,
+               conv_kernel=1, use_radial_filters=True),
+    tinyT=dict(z_dim=64, c_dim=0, w_dim=64, img_resolution=64, img_channels=3, channel_base=2048, channel_max=32,
+               conv_kernel=3, use_radial_filters=False),
+)
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def unpatch():
+    if hasattr(ref, '_sg3_b200_original_modulated_conv2d'):
+        ref.modulated_conv2d = ref._sg3_b200_original_modulated_conv2d
+
+
+def grads_err(G, g, name, ws):
+    G.requires_grad_(True)
+    img = G.synthesis(ws, noise_mode='const', force_fp32=True)
+    loss = (img * cu(g[f'{name}/tgt'])).mean()
+    params = dict(G.synthesis.named_parameters())
+    grads = torch.autograd.grad(loss, list(params.values()), allow_unused=True)
+    worst, n = 0.0, 0
+    for (k, _), gr in zip(params.items(), grads):
+        key = f'{name}/grad/{k}'
+        if key in g.files and np.abs(g[key]).max() > 0:
+            worst = max(worst, rel(gr.cpu().numpy(), g[key]))
+            n += 1
+    G.requires_grad_(False)
+    return abs(float(loss) - float(g[f'{name}/loss'])), worst, n
+
+
+failed = False
+launch0 = sg3_b200.capi.lib().sg3_launch_count()
+g = np.load(os.path.join(ROOT, 'tests', 'golden', 'tiny.npz'))
+for name, cfg in TINY.items():
+    torch.manual_seed(0)
+    Gr = ref.Generator(**cfg).eval().requires_grad_(False)
+    for k, v in Gr.synthesis.state_dict().items():                 # same seed -> the weights the golden run used
+        assert np.array_equal(v.numpy(), g[f'{name}/state/{k}']), k
+    Gr = Gr.cuda()
+    ws = cu(g[f'{name}/ws'])
+    rows = []
+    # (a) reference code, our stencil ops, the reference's own conv (cuDNN fp32)
+    unpatch()
+    img = Gr.synthesis(ws, noise_mode='const', force_fp32=True)
+    rows.append(('reference conv (cuDNN fp32)', rel(img.cpu().numpy(), g[f'{name}/img']), 1e-4) + grads_err(Gr, g, name, ws))
+    # the same with cuDNN's TF32 convolution (the reference's default, torch.backends.cudnn.allow_tf32): the yardstick for the
+    # TF32 rows below -- through 15 layers of a 32-channel toy network TF32 rounding costs ~1e-2 on images and gradients
+    torch.backends.cudnn.allow_tf32 = True
+    img = Gr.synthesis(ws, noise_mode='const', force_fp32=True)
+    rows.append(('reference conv (cuDNN tf32)', rel(img.cpu().numpy(), g[f'{name}/img']), 2e-2) + grads_err(Gr, g, name, ws))
+    torch.backends.cudnn.allow_tf32 = False
+    # (b) + our conv
+    assert sg3_b200.patch_modulated_conv(Gr) == ['models.stylegan3.networks_stylegan3']
+    for math, tol in (('fp32', 1e-4), ('tf32', 2e-2)):
+        modulated_conv.set_math(math)
+        img = Gr.synthesis(ws, noise_mode='const', force_fp32=True)
+        rows.append((f'sg3_b200 conv ({math})', rel(img.cpu().numpy(), g[f'{name}/img']), tol) + grads_err(Gr, g, name, ws))
+    modulated_conv.set_math(None)
+    # fp16 layers (the reference's default on CUDA): reference code on our kernels vs our generator on our kernels
+    torch.manual_seed(0)
+    Go = networks.Generator(**cfg).eval().requires_grad_(False).cuda()
+    a = Gr.synthesis(ws, noise_mode='const').float().cpu().numpy()
+    b = Go.synthesis(ws, noise_mode='const').float().cpu().numpy()
+    rows.append(('fp16 layers: reference code vs sg3_b200.networks', rel(a, b), 2e-3, 0.0, 0.0, 0))
+    print(f'\n{name}: reference Generator code on sg3_b200 kernels vs the golden CPU impl=ref run')
+    for what, e, tol, dl, ge, n in rows:
+        ok = e < tol and ge < (1e-1 if 'tf32' in what else 1e-3)     # TF32 stated separately (north_star)
+        failed |= not ok
+        print(f'  {what:52s} image rel err {e:.2e} (tol {tol:.0e})   |dloss| {dl:.1e}   worst grad rel err {ge:.2e} over {n} params   {"ok" if ok else "FAIL"}')
+
+# BASELINE configs[0]: StyleGAN3-R 256^2, batch 4
+g2 = np.load(os.path.join(ROOT, 'tests', 'golden', 'r256.npz'))
+torch.manual_seed(0)
+Gr = ref.Generator(z_dim=512, c_dim=0, w_dim=512, img_resolution=256, img_channels=3, channel_base=65536, channel_max=1024,
+                   conv_kernel=1, use_radial_filters=True).eval().requires_grad_(False).cuda()
+for patched in (False, True):
+    unpatch()
+    if patched:
+        sg3_b200.patch_modulated_conv(Gr)
+        modulated_conv.set_math('fp32')
+    img = Gr.synthesis(cu(g2['r256/ws']), noise_mode='const', force_fp32=True).cpu().numpy()
+    modulated_conv.set_math(None)
+    e = rel(img[:, :, ::4, ::4], g2['r256/img_sub4'])           # the golden file keeps every 4th pixel
+    ok = e < 1e-3
+    failed |= not ok
+    print(f'R-256 batch 4 (BASELINE configs[0]), {"sg3_b200 conv (fp32)" if patched else "reference conv (cuDNN fp32)"}: image rel err {e:.2e}   {"ok" if ok else "FAIL"}')
+print(f'\nsg3_b200 kernel launches during the checks: {sg3_b200.capi.lib().sg3_launch_count() - launch0}')
+
+if '--time' in sys.argv:
+    torch.backends.cudnn.allow_tf32 = True                  # the reference's default
+    R1024 = dict(z_dim=512, c_dim=0, w_dim=512, img_resolution=1024, img_channels=3, channel_base=65536, channel_max=1024,
+                 conv_kernel=1, use_radial_filters=True)
+    torch.manual_seed(0)
+    Gr = ref.Generator(**R1024).eval().requires_grad_(False).cuda()
+    torch.manual_seed(0)
+    Go = networks.Generator(**R1024).eval().requires_grad_(False).cuda()
+    ws = Go.mapping(torch.randn(4, 512, device='cuda'), None)
+
+    def bench(fn, what):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(4):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 4
+        print(f'  {what:66s} {ms:8.2f} ms / batch of 4 = {4000 / ms:7.1f} images/s')
+        return out
+
+    print('\nStyleGAN3-R 1024^2 forward, batch 4, force_fp32 (TF32 conv):')
+    unpatch()
+    a = bench(lambda: Gr.synthesis(ws, noise_mode='const', force_fp32=True), 'reference model code, sg3_b200 stencils, reference conv (cuDNN)')
+    sg3_b200.patch_modulated_conv(Gr)
+    b = bench(lambda: Gr.synthesis(ws, noise_mode='const', force_fp32=True), 'reference model code, all kernels sg3_b200 (patch_modulated_conv)')
+    c = bench(lambda: Go.synthesis(ws, noise_mode='const', force_fp32=True), 'sg3_b200.networks.Generator')
+    print(f'  image rel err  (a) vs (c): {rel(a.cpu().numpy(), c.cpu().numpy()):.2e}   (b) vs (c): {rel(b.cpu().numpy(), c.cpu().numpy()):.2e}')
+    unpatch()
+    a = bench(lambda: Gr.synthesis(ws, noise_mode='const'), 'fp16 layers (reference default): reference code, reference conv')
+    sg3_b200.patch_modulated_conv(Gr)
+    b = bench(lambda: Gr.synthesis(ws, noise_mode='const'), 'fp16 layers: reference code, all kernels sg3_b200')
+    c = bench(lambda: Go.synthesis(ws, noise_mode='const'), 'fp16 layers: sg3_b200.networks.Generator')
+    print(f'  image rel err  (a) vs (c): {rel(a.float().cpu().numpy(), c.float().cpu().numpy()):.2e}   (b) vs (c): {rel(b.float().cpu().numpy(), c.float().cpu().numpy()):.2e}')
+
+print('\nDROP-IN CHECK', 'FAILED' if failed else 'PASSED')
+sys.exit(1 if failed else 0)
