@@ -131,6 +131,56 @@ def test_dropin_seam(pkg):
         sys.modules.update(saved)
 
 
+def test_dropin_seam_with_a_real_torch_utils_package(pkg, tmp_path):
+    """With a reference-like tree on sys.path, install() must keep the real `torch_utils` package importable
+    (networks_stylegan3.py:17 imports torch_utils.misc / persistence next to the aliased ops) and must win over the
+    tree's own op modules; patch_modulated_conv() re-points the module global that SynthesisLayer.forward looks up, also
+    through a persistence-style wrapper subclass defined in another module."""
+    tree = tmp_path / 'fake_ref'
+    (tree / 'torch_utils' / 'ops').mkdir(parents=True)
+    (tree / 'fakemodels').mkdir()
+    (tree / 'torch_utils' / '__init__.py').write_text('')
+    (tree / 'torch_utils' / 'misc.py').write_text('MARK = "real misc"\n')
+    (tree / 'torch_utils' / 'wrap.py').write_text(
+        'def persistent_class(c):\n'
+        '    class Decorator(c):\n        pass\n'
+        '    Decorator.__name__ = c.__name__\n    return Decorator\n')
+    (tree / 'torch_utils' / 'ops' / '__init__.py').write_text('')
+    (tree / 'torch_utils' / 'ops' / 'filtered_lrelu.py').write_text('raise ImportError("the tree\'s own plugin wrapper must never be imported")\n')
+    (tree / 'fakemodels' / '__init__.py').write_text('')
+    (tree / 'fakemodels' / 'net.py').write_text(
+        'import torch\nfrom torch_utils import misc, wrap\nfrom torch_utils.ops import filtered_lrelu, bias_act\n'
+        'def modulated_conv2d(x, w, s, demodulate=True, padding=0, input_gain=None):\n    return "reference conv"\n'
+        '@wrap.persistent_class\nclass Layer(torch.nn.Module):\n'
+        '    def forward(self):\n        return modulated_conv2d\n')
+    saved = {k: v for k, v in sys.modules.items() if k == 'torch_utils' or k.startswith('torch_utils.')}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, str(tree))
+    try:
+        pkg.install()
+        import importlib
+        net = importlib.import_module('fakemodels.net')
+        assert net.misc.MARK == 'real misc'
+        assert net.filtered_lrelu is pkg.filtered_lrelu and net.bias_act is pkg.bias_act
+        layer = net.Layer()
+        assert type(layer).__module__ == 'torch_utils.wrap'          # like torch_utils.persistence's Decorator subclass
+        assert layer.forward()(None, None, None) == 'reference conv'
+        assert pkg.patch_modulated_conv(layer) == ['fakemodels.net']
+        from sg3_b200.modulated_conv import modulated_conv2d
+        assert layer.forward() is modulated_conv2d
+        assert pkg.patch_modulated_conv(layer) == []                 # idempotent
+        assert net._sg3_b200_original_modulated_conv2d(None, None, None) == 'reference conv'
+        assert pkg.patch_modulated_conv() == []                      # the reference module itself is not imported here
+        with pytest.raises(TypeError):
+            pkg.patch_modulated_conv(42)
+    finally:
+        sys.path.remove(str(tree))
+        for k in [k for k in sys.modules if k == 'torch_utils' or k.startswith('torch_utils.') or k.startswith('fakemodels')]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
 def test_bench_work_table_matches_oracle_geometry():
     """bench.py derives its algorithmic bytes / FLOPs from the generator it times; the numbers equal those of the oracle's
     independent layer-geometry restatement (R-1024 4.170 GB and 247.6 GFLOP, T-1024 2.109 GB and 570.4 GFLOP)."""
