@@ -3,7 +3,7 @@
 Run in the authoring container only (the reference tree does not exist on the GPU box):
 
     python tests/golden/make_golden.py            # all files
-    python tests/golden/make_golden.py ops        # one group: ops | modconv | tiny | r256
+    python tests/golden/make_golden.py ops        # one group: ops | modconv | tiny | r256 | transform
 
 The reference has no tests or fixtures of its own, so these files,
 made by importing /root/reference unmodified, are what pins oracle/ and the CUDA path.
@@ -260,8 +260,33 @@ def gen_r256(out):
     print('r256 stats', out['r256/stats'])
 
 
+def gen_transform(out):
+    """Per-sample user transforms on `synthesis.input.transform` ([N, 3, 3]: what the ReStyle / pSp inversion sets from the
+    landmarks, models/setgan/encoder/psp3.py:63-65, and the video FOV expansion translates, utils/fov_expansion.py:20-27) and a
+    single [3, 3] transform (the reference's default buffer shape).  Weights = the tiny.npz generators (same seed)."""
+    for name, cfg in TINY.items():
+        torch.manual_seed(0)
+        G = ref_net.Generator(**cfg).eval().requires_grad_(False)
+        ws = G.mapping(torch.randn(2, cfg['z_dim'], generator=torch.Generator().manual_seed(1)), None)
+        rng = np.random.RandomState(7)
+        mats = []
+        for ang, sc, tx, ty in ((0.3, 1.15, 0.12, -0.07), (-1.1, 0.8, -0.3, 0.25)):
+            c, s = np.cos(ang) * sc, np.sin(ang) * sc
+            mats.append(np.array([[c, -s, tx], [s, c, ty], [0, 0, 1]], np.float32))
+        for tag, m in (('per_sample', np.stack(mats)), ('single', mats[0])):
+            G.synthesis.input.transform = torch.from_numpy(m)
+            x = G.synthesis.input(ws[:, 0])
+            img = G.synthesis(ws, noise_mode='const', force_fp32=True)
+            k = f'{name}/{tag}/'
+            out[k + 'transform'] = m
+            out[k + 'input'] = x[:, :8].contiguous().numpy()
+            out[k + 'img'] = img.numpy()
+            print(name, tag, 'img absmax', float(img.abs().max()))
+        out[f'{name}/ws'] = ws.numpy()
+
+
 def main():
-    which = sys.argv[1:] or ['ops', 'modconv', 'tiny', 'r256']
+    which = sys.argv[1:] or ['ops', 'modconv', 'tiny', 'r256', 'transform']
     torch.set_num_threads(os.cpu_count())
     if 'ops' in which:
         out = {}
@@ -278,6 +303,10 @@ def main():
         out = {}
         gen_tiny(out)
         np.savez_compressed(os.path.join(HERE, 'tiny.npz'), **out)
+    if 'transform' in which:
+        out = {}
+        gen_transform(out)
+        np.savez_compressed(os.path.join(HERE, 'transform.npz'), **out)
     if 'r256' in which:
         out = {}
         gen_r256(out)

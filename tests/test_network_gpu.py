@@ -140,6 +140,31 @@ def test_tiny_generator_gradients(pkg, name):
         pkg.modulated_conv.set_math(None)
 
 
+@pytest.mark.parametrize('tag', ['per_sample', 'single'])
+@pytest.mark.parametrize('name', ['tinyR', 'tinyT'])
+def test_user_transform(pkg, name, tag):
+    """BASELINE configs[3] (ReStyle / pSp inversion) sets one landmarks transform per sample on `synthesis.input.transform`
+    (models/setgan/encoder/psp3.py:63-65), the video FOV expansion translates it (utils/fov_expansion.py:20-27): [N, 3, 3] and
+    [3, 3] user transforms vs the reference, eagerly and through the CUDA-graph wrapper (in-place update of the buffer)."""
+    G, _ = _build(pkg, name)
+    g = golden('transform.npz').z
+    ws, m = cu(g[f'{name}/ws']), cu(g[f'{name}/{tag}/transform'])
+    pkg.modulated_conv.set_math('fp32')
+    try:
+        G.synthesis.input.transform = m
+        x = G.synthesis.input(ws[:, 0])
+        assert rel_err(x[:, :8].cpu().numpy(), g[f'{name}/{tag}/input']) < 1e-5
+        img = G.synthesis(ws, noise_mode='const', force_fp32=True)
+        assert rel_err(img.cpu().numpy(), g[f'{name}/{tag}/img']) < 1e-4
+        # graph captured with identity transforms of the same shape, then the buffer is updated in place and replayed
+        G.synthesis.input.transform = torch.eye(3, device='cuda').expand_as(m).contiguous()
+        graphed = pkg.networks.GraphedSynthesis(G.synthesis, ws)
+        G.synthesis.input.transform.copy_(m)
+        assert rel_err(graphed(ws).cpu().numpy(), g[f'{name}/{tag}/img']) < 1e-4
+    finally:
+        pkg.modulated_conv.set_math(None)
+
+
 def test_r256_config1(pkg):
     """BASELINE.json configs[0]: StyleGAN3-R 256^2, seed-0 random init, batch 4, fp32 -- against the image the
     reference produced on CPU with impl='ref' (strided subsample stored in tests/golden/r256.npz)."""

@@ -118,3 +118,16 @@ def test_tiny_generator(name):
     assert rel_err(img, g.z[f'{name}/img']) < 1e-4
     feat = net.forward(ws, num_layers=3)
     assert rel_err(feat[:1, :8], g.z[f'{name}/feat/after_2']) < 5e-5
+
+
+@pytest.mark.parametrize('tag', ['per_sample', 'single'])
+@pytest.mark.parametrize('name', ['tinyR', 'tinyT'])
+def test_user_transform(name, tag):
+    """`synthesis.input.transform` as one [3, 3] matrix or one per sample ([N, 3, 3]: ReStyle landmarks transform,
+    video FOV expansion) -- Fourier features and final image vs the reference."""
+    g = golden('transform.npz').z
+    net = orc.SynthesisOracle(golden('tiny.npz').sub(f'{name}/state/'), **TINY_CFG[name])
+    ws, m = g[f'{name}/ws'], g[f'{name}/{tag}/transform']
+    x = net.input_features(ws[:, 0], transform=m)
+    assert rel_err(x[:, :8], g[f'{name}/{tag}/input']) < TOL
+    assert rel_err(net.forward(ws, transform=m), g[f'{name}/{tag}/img']) < 1e-4
