@@ -134,6 +134,23 @@ for patched in (False, True):
     ok = e < 1e-3
     failed |= not ok
     print(f'R-256 batch 4 (BASELINE configs[0]), {"sg3_b200 conv (fp32)" if patched else "reference conv (cuDNN fp32)"}: image rel err {e:.2e}   {"ok" if ok else "FAIL"}')
+# A generator unpickled through the reference's persistence machinery: its classes live in a private module re-created from
+# the pickled source, whose `from torch_utils.ops import ...` line resolves to the aliases (persistence.py:191-229).
+pkl = os.path.join(REF, 'tinyR_seed0.pkl')
+if os.path.exists(pkl):
+    import pickle
+    unpatch()
+    Gp = pickle.load(open(pkl, 'rb'))['G_ema'].cuda()
+    ws = cu(g['tinyR/ws'])
+    e0 = rel(Gp.synthesis(ws, noise_mode='const', force_fp32=True).cpu().numpy(), g['tinyR/img'])
+    patched = sg3_b200.patch_modulated_conv(Gp)
+    modulated_conv.set_math('fp32')
+    e1 = rel(Gp.synthesis(ws, noise_mode='const', force_fp32=True).cpu().numpy(), g['tinyR/img'])
+    modulated_conv.set_math(None)
+    # (persistence re-uses an already imported module with identical source, else a private `_imported_module_<id>`)
+    ok = e0 < 1e-4 and e1 < 1e-4 and len(patched) == 1
+    failed |= not ok
+    print(f'unpickled tiny R generator: image rel err {e0:.2e} (reference conv), {e1:.2e} (patched {patched})   {"ok" if ok else "FAIL"}')
 print(f'\nsg3_b200 kernel launches during the checks: {sg3_b200.capi.lib().sg3_launch_count() - launch0}')
 
 if '--time' in sys.argv:
