@@ -7,6 +7,8 @@ krylea/stylegan3-editing, behind the reference's own op API.
 
     sg3_b200.install()                      # alias the ops as torch_utils.ops.* for the reference's models
 
+    from sg3_b200.fov import Expander       # utils/fov_expansion.Expander in one batched synthesis call
+
 Everything is backed by libsg3_b200.so (C ABI in include/sg3_b200.h); there is no CPU fallback.
 """
 from . import capi

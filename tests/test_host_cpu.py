@@ -181,6 +181,35 @@ def test_dropin_seam_with_a_real_torch_utils_package(pkg, tmp_path):
         sys.modules.update(saved)
 
 
+def test_fov_view_transforms(pkg):
+    """sg3_b200.fov.view_transforms vs the construction of utils/fov_expansion.py:34-84 restated here:
+    inverse of make_transform(translate, 0) (utils/common.py:9-19) per edge / corner, None for unused views."""
+    from sg3_b200 import fov
+
+    def make_transform(translate, angle=0.0):
+        m = np.eye(3)
+        s, c = np.sin(angle / 360.0 * np.pi * 2), np.cos(angle / 360.0 * np.pi * 2)
+        m[0][0], m[0][1], m[0][2], m[1][0], m[1][1], m[1][2] = c, s, translate[0], -s, c, translate[1]
+        return m
+
+    res = 1024
+    for r, l, t, b in ((100, 50, 30, 70), (0, 64, 0, 0), (10, 0, 0, 20), (0, 0, 0, 0)):
+        want = [make_transform((0, 0)),
+                make_transform((l / res, 0)) if l else None, make_transform((0, t / res)) if t else None,
+                make_transform((-r / res, 0)) if r else None, make_transform((0, -b / res)) if b else None,
+                make_transform((l / res, t / res)) if l and t else None, make_transform((-r / res, t / res)) if r and t else None,
+                make_transform((-r / res, -b / res)) if r and b else None, make_transform((l / res, -b / res)) if l and b else None]
+        got = fov.view_transforms(res, pixels_right=r, pixels_left=l, pixels_top=t, pixels_bottom=b)
+        assert len(got) == 9
+        for w, g in zip(want, got):
+            assert (w is None) == (g is None)
+            if w is not None:
+                assert np.allclose(np.linalg.inv(w), g, atol=1e-12)
+    import inspect
+    assert list(inspect.signature(fov.Expander.generate_expanded_image).parameters)[:8] == [
+        'self', 'ws', 'all_s', 'landmark_t', 'pixels_right', 'pixels_left', 'pixels_top', 'pixels_bottom']
+
+
 def test_bench_work_table_matches_oracle_geometry():
     """bench.py derives its algorithmic bytes / FLOPs from the generator it times; the numbers equal those of the oracle's
     independent layer-geometry restatement (R-1024 4.170 GB and 247.6 GFLOP, T-1024 2.109 GB and 570.4 GFLOP)."""

@@ -165,6 +165,65 @@ def test_user_transform(pkg, name, tag):
         pkg.modulated_conv.set_math(None)
 
 
+@pytest.mark.parametrize('margins', [(10, 6, 4, 12), (0, 8, 0, 0), (5, 0, 0, 7)])
+def test_fov_expander_matches_sequential_views(pkg, margins):
+    """sg3_b200.fov.Expander (one batched call with per-sample transforms) vs the reference's procedure restated here
+    (utils/fov_expansion.py:14-31, 88-110: one batch-1 synthesis call per view with a single [3, 3] transform, then paste)."""
+    from sg3_b200 import fov
+    G, g = _build(pkg, 'tinyR')
+    pkg.modulated_conv.set_math('fp32')      # exact contraction: with TF32 the batch-global style RMS moves weight roundings
+    try:
+        _fov_check(pkg, fov, G, g, margins)
+    finally:
+        pkg.modulated_conv.set_math(None)
+
+
+def _fov_check(pkg, fov, G, g, margins):
+    res = G.img_resolution
+    right, left, top, bottom = margins
+    ws = cu(g.z['tinyR/ws'])
+    ang = 0.2
+    lt = np.array([[np.cos(ang), np.sin(ang), 0.05], [-np.sin(ang), np.cos(ang), -0.02], [0, 0, 1]])
+    views = fov.view_transforms(res, right, left, top, bottom)
+    imgs = []
+    for t in views:
+        if t is None:
+            imgs.append(None)
+            continue
+        G.synthesis.input.transform = torch.from_numpy(lt @ t).float().cuda()
+        with torch.no_grad():
+            imgs.append(G.synthesis(ws, noise_mode='const', force_fp32=True))
+    want = torch.zeros(ws.shape[0], 3, top + res + bottom, left + res + right, device='cuda')
+    want[:, :, top:top + res, left:left + res] = imgs[0]
+    if left:
+        want[:, :, top:top + res, :left] = imgs[1][:, :, :, :left]
+    if top:
+        want[:, :, :top, left:left + res] = imgs[2][:, :, :top, :]
+    if right:
+        want[:, :, top:top + res, left + res:] = imgs[3][:, :, :, res - right:]
+    if bottom:
+        want[:, :, top + res:, left:left + res] = imgs[4][:, :, res - bottom:, :]
+    if top and left:
+        want[:, :, :top, :left] = imgs[5][:, :, :top, :left]
+    if top and right:
+        want[:, :, :top, res + left:] = imgs[6][:, :, :top, res - right:]
+    if bottom and right:
+        want[:, :, res + top:, res + left:] = imgs[7][:, :, res - bottom:, res - right:]
+    if bottom and left:
+        want[:, :, res + top:, :left] = imgs[8][:, :, res - bottom:, :left]
+    eye = torch.eye(3, device='cuda')
+    G.synthesis.input.transform = eye
+    ex = fov.Expander(G)
+    got = ex.generate_expanded_image(ws=ws, landmark_t=lt, pixels_right=right, pixels_left=left, pixels_top=top,
+                                     pixels_bottom=bottom, noise_mode='const', force_fp32=True)
+    assert got.shape == want.shape and G.synthesis.input.transform is eye
+    # per-sample kernels throughout; the only cross-sample term is the batch-global style RMS, which demodulation cancels
+    assert rel_err(got.cpu().numpy(), want.cpu().numpy()) < 1e-5
+    got_s = ex.generate_expanded_image(all_s=G.synthesis.W2S(ws), landmark_t=torch.from_numpy(lt), pixels_right=right,
+                                       pixels_left=left, pixels_top=top, pixels_bottom=bottom, noise_mode='const', force_fp32=True)
+    assert rel_err(got_s.cpu().numpy(), want.cpu().numpy()) < 1e-5
+
+
 def test_r256_config1(pkg):
     """BASELINE.json configs[0]: StyleGAN3-R 256^2, seed-0 random init, batch 4, fp32 -- against the image the
     reference produced on CPU with impl='ref' (strided subsample stored in tests/golden/r256.npz)."""
