@@ -210,6 +210,70 @@ def test_fov_view_transforms(pkg):
         'self', 'ws', 'all_s', 'landmark_t', 'pixels_right', 'pixels_left', 'pixels_top', 'pixels_bottom']
 
 
+def test_fov_expander_paste_logic_with_a_stub_generator(pkg):
+    """Expander's batching and paste table on a stub generator (CPU tensors; no kernel involved): the stub renders, for every
+    sample, an image that encodes which view transform it was given and the pixel coordinates, so the expected canvas follows
+    from the paste rules of utils/fov_expansion.py:88-110 alone."""
+    from sg3_b200 import fov
+    res, n = 16, 2
+
+    class StubInput(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.register_buffer('transform', torch.eye(3))
+
+    class StubSynthesis(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.input = StubInput()
+            self.calls = []
+
+        def forward(self, ws, all_s=None, **kw):
+            t = self.input.transform
+            self.calls.append((ws.shape[0], tuple(t.shape)))
+            assert t.shape == (ws.shape[0], 3, 3)
+            yy, xx = torch.meshgrid(torch.arange(res), torch.arange(res), indexing='ij')
+            base = (yy * res + xx).float()
+            # translation in pixels identifies the view; the latent's first entry identifies the sample
+            tag = (t[:, 0, 2] * res).round() * 1000 + (t[:, 1, 2] * res).round() * 100000 + ws[:, 0, 0] * 1e7
+            return (base[None, None] + tag[:, None, None, None]).expand(-1, 3, -1, -1).contiguous()
+
+    class StubG:
+        img_resolution = res
+        synthesis = StubSynthesis()
+
+    G = StubG()
+    ws = torch.arange(n).float().reshape(n, 1, 1).expand(n, 4, 8).contiguous()
+    R, L, T, B = 3, 2, 4, 1
+    out = fov.Expander(G).generate_expanded_image(ws=ws, landmark_t=np.eye(3), pixels_right=R, pixels_left=L, pixels_top=T, pixels_bottom=B)
+    assert G.synthesis.calls == [(9 * n, (9 * n, 3, 3))]                      # ONE batched call for the nine views
+    assert torch.equal(G.synthesis.input.transform, torch.eye(3))             # user transform restored
+    assert out.shape == (n, 3, T + res + B, L + res + R)
+    yy, xx = np.meshgrid(np.arange(res), np.arange(res), indexing='ij')
+    base = (yy * res + xx).astype(np.float64)
+
+    def view(sample, dx, dy):          # image of the view translated by (dx, dy) pixels (inverse of make_transform((dx/res, dy/res)))
+        return base + (-dx) * 1000 + (-dy) * 100000 + sample * 1e7
+
+    for smp in range(n):
+        want = np.zeros((T + res + B, L + res + R))
+        want[T:T + res, L:L + res] = view(smp, 0, 0)
+        want[T:T + res, :L] = view(smp, L, 0)[:, :L]
+        want[:T, L:L + res] = view(smp, 0, T)[:T, :]
+        want[T:T + res, L + res:] = view(smp, -R, 0)[:, res - R:]
+        want[T + res:, L:L + res] = view(smp, 0, -B)[res - B:, :]
+        want[:T, :L] = view(smp, L, T)[:T, :L]
+        want[:T, res + L:] = view(smp, -R, T)[:T, res - R:]
+        want[res + T:, res + L:] = view(smp, -R, -B)[res - B:, res - R:]
+        want[res + T:, :L] = view(smp, L, -B)[res - B:, :L]
+        for ch in range(3):
+            assert np.array_equal(out[smp, ch].numpy().astype(np.float64), want), (smp, ch)
+    # only the views that are needed are rendered
+    G.synthesis.calls.clear()
+    out = fov.Expander(G).generate_expanded_image(ws=ws, landmark_t=np.eye(3), pixels_left=5)
+    assert G.synthesis.calls == [(2 * n, (2 * n, 3, 3))] and out.shape == (n, 3, res, res + 5)
+
+
 def test_bench_work_table_matches_oracle_geometry():
     """bench.py derives its algorithmic bytes / FLOPs from the generator it times; the numbers equal those of the oracle's
     independent layer-geometry restatement (R-1024 4.170 GB and 247.6 GFLOP, T-1024 2.109 GB and 570.4 GFLOP)."""
