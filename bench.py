@@ -229,6 +229,21 @@ def run_ours(args):
         return y
     fl_mod.filtered_lrelu = timed_fl
 
+    # same for modulated_conv2d (weight prologue + contraction), the second-largest item: tensor-pipe evidence
+    cv_events = []
+    orig_cv = networks.modulated_conv2d
+
+    def timed_cv(*a, **k):
+        if not record['on']:
+            return orig_cv(*a, **k)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        y = orig_cv(*a, **k)
+        c1.record()
+        cv_events.append((c0, c1))
+        return y
+    networks.modulated_conv2d = timed_cv
+
     def step_resident():
         with torch.no_grad():
             return G.synthesis(ws, noise_mode='const', force_fp32=True)
@@ -273,6 +288,8 @@ def run_ours(args):
     fl_ms = sum(a.elapsed_time(b) for a, b, _ in fl_events)
     fl_bytes = sum(nb for _, _, nb in fl_events)
     fl_mod.filtered_lrelu = orig_fl
+    networks.modulated_conv2d = orig_cv
+    cv_ms = sum(a.elapsed_time(b) for a, b in cv_events)
 
     # ---- timed: end to end with host buffers ----
     for _ in range(2):
@@ -323,6 +340,24 @@ def run_ours(args):
     except Exception:
         pass
 
+    # modulated_conv2d: FLOPs 2*N*O*I*k^2*(H+k-1)^2 and minimum bytes 4*N*(I*H^2 + O*(H+k-1)^2) per layer; the TF32
+    # tensor peak is taken as half the measured dense bf16 cuBLAS rate (tcgen05 kind::tf32 runs at half the kind::f16 rate)
+    conv = None
+    try:
+        if cv_ms > 0:
+            flops = sum(r['conv_flops'] for r in work) * B * args.steps
+            cbytes = sum(4 * (sp['in_channels'] * sp['in_size'] ** 2 + sp['out_channels'] * (sp['in_size'] + sp['conv_kernel'] - 1) ** 2)
+                         for sp in specs) * B * args.steps
+            tf32_peak = float(peaks.get('bf16_tflops_sustained', peaks.get('bf16_tflops', 2250.0 * 0.62))) / 2
+            conv = dict(kernel='modulated_conv2d = weight prologue + tcgen05 TF32 contraction (15 calls per step, CUDA events)',
+                        ms_per_step=cv_ms / args.steps, achieved_tflops=flops / (cv_ms * 1e-3) / 1e12, tf32_peak_tflops=tf32_peak,
+                        tensor_frac=flops / (cv_ms * 1e-3) / 1e12 / tf32_peak,
+                        achieved_gbs=cbytes / (cv_ms * 1e-3) / 1e9, hbm_frac=cbytes / (cv_ms * 1e-3) / 1e9 / hbm_peak,
+                        bound='hbm' if CFG_NAME == 'R' else 'tensor',
+                        note='config R: 1x1 convs at 59 FLOP/B sit under the HBM roof on tensor cores; config T: 3x3 convs are tensor bound (DESIGN.md 4.3/4.4)')
+    except Exception as e:            # never lose the bench line over the secondary table
+        conv = dict(error=repr(e))
+
     value = world * B * args.steps / (ms_total * 1e-3)
     out = dict(
         metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
@@ -336,6 +371,7 @@ def run_ours(args):
         e2e=dict(value=world * B * args.steps / (e2e_ms * 1e-3), unit='images/s',
                  h2d_bytes_per_step=int(ws_host.numel() * 4), d2h_bytes_per_step=int(img_host[0].numel() * 4)),
         gpu_launches=int(launches),
+        conv=conv,
         roofline=dict(bound='hbm', achieved=achieved, peak=hbm_peak, unit='GB/s', frac=achieved / hbm_peak,
                       traffic=traffic, algorithmic_bytes=fl_bytes / args.steps, traffic_note=traffic_note,
                       kernel='filtered_lrelu (15 calls per step, all timed with CUDA events)',
