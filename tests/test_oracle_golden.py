@@ -131,3 +131,26 @@ def test_user_transform(name, tag):
     x = net.input_features(ws[:, 0], transform=m)
     assert rel_err(x[:, :8], g[f'{name}/{tag}/input']) < TOL
     assert rel_err(net.forward(ws, transform=m), g[f'{name}/{tag}/img']) < 1e-4
+
+
+def test_radial_down_filters_are_numerically_low_rank():
+    """the 12x12 jinc x Kaiser down filters of config R (taps are data, networks_stylegan3.py:371-391)
+    equal a sum of at most 4 separable filters to within fp32 rounding of their largest tap (3 terms: within 4e-7, except the two
+    layers with the widest transition band, L8 / L11, 2e-5); the claim is pinned here on the oracle's filter design, which
+    test_tiny_generator holds to the reference's buffers."""
+    _, specs = orc.layer_specs(1024, channel_base=65536, channel_max=1024, conv_kernel=1, use_radial_filters=True)
+    seen = 0
+    for sp in specs:
+        f = sp['down_filter']
+        if f is None or np.ndim(f) != 2:
+            continue
+        seen += 1
+        f = np.asarray(f, np.float64)
+        assert f.shape == (12, 12) and np.array_equal(f, f.T) and np.allclose(f, f[::-1, ::-1], atol=1e-9)      # radial
+        assert np.array_equal(f[:, :6], f[:, :5:-1])             # the exact x mirror symmetry stage D of the fused kernel relies on
+        u, s, vt = np.linalg.svd(f)
+        err = [np.abs((u[:, :r] * s[:r]) @ vt[:r] - f).max() / np.abs(f).max() for r in range(6)]
+        assert err[4] < 6e-8, (sp['name'], err)                   # fp32 epsilon
+        assert err[3] < (2e-5 if sp['name'].split('_')[0] in ('L8', 'L11') else 4e-7), (sp['name'], err)
+        assert err[2] > 1e-7                                      # two terms never suffice
+    assert seen == 12
