@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/sg3_b200.h"
 
 #define SG3_EXPORT extern "C" __attribute__((visibility("default")))
@@ -47,3 +49,19 @@ __host__ __device__ __forceinline__ int pos_mod(int a, int b)
 
 // Cached SM count of the current device (grid sizing in multiples of the SM count).
 int sg3_sm_count();
+
+// One-time per-DEVICE setup of kernel attributes: cudaFuncSetAttribute applies to the current device only, so a
+// process that drives several GPUs (G.to('cuda:1'), one thread per device) must repeat it on each of them.
+// `f` is idempotent; two threads racing on the same device may both run it.
+struct Sg3DeviceOnce {
+    std::atomic<int> done[64];
+    template <class F> cudaError_t run(F&& f)
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return f();
+        if (done[dev].load(std::memory_order_acquire)) return cudaSuccess;
+        const cudaError_t e = f();
+        if (e == cudaSuccess) done[dev].store(1, std::memory_order_release);
+        return e;
+    }
+};

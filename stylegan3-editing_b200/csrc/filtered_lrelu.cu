@@ -127,6 +127,7 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
             const int fh = fuH ? fuH : fuW;
             if (a >= fh || b >= fuW) return 0.f;
             const int sa = d->flip ? a : fh - 1 - a, sb = d->flip ? b : fuW - 1 - b;
+            if (!d->fu) return 1.0f;                  // fu == NULL is the 1x1 identity filter (filtered_lrelu.py:160-162 of the reference)
             return fuH ? d->fu[sa * fuW + sb] : d->fu[sa] * d->fu[sb];
         };
         for (int py = 0; py < 2; py++)

@@ -1,6 +1,4 @@
 // Instantiates flrelu_bwd_stream::kernel (dense-up backward shapes): {float, half} x {down 2, down 4} x {no signs, read}.
-#include <mutex>
-
 #include "flrelu_bwd_stream.cuh"
 
 namespace fb = flrelu_bwd_stream;
@@ -10,9 +8,8 @@ static int launch_one(const fb::Params& p, cudaStream_t stream)
 {
     auto kern = fb::kernel<T, DOWN, MODE>;
     const int smem = fb::kWarpsPerCta * fb::Geo<DOWN>::WARP_BYTES;
-    static std::once_flag once;
-    static cudaError_t attrErr = cudaSuccess;
-    std::call_once(once, [&] { attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
+    static Sg3DeviceOnce once;
+    const cudaError_t attrErr = once.run([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); });
     if (attrErr != cudaSuccess) return (int)attrErr;
     const long long ctas = (p.totalStrips + fb::kWarpsPerCta - 1) / fb::kWarpsPerCta;
     if (ctas > 0x7fffffffLL) return SG3_E_TOOLARGE;

@@ -1,8 +1,6 @@
 // flrelu_launch.cuh -- launch + mode dispatch of flrelu_stream::kernel for one (dtype, up) pair.
 #pragma once
 
-#include <mutex>
-
 #include "flrelu_stream.cuh"
 
 namespace flrelu_stream {
@@ -12,12 +10,12 @@ int launch_one(const Params& p, cudaStream_t stream)
 {
     auto kern = kernel<T, UP, FD, MODE, TMA>;
     const int smem = kWarpsPerCta * Geo<UP>::warp_bytes(MODE);
-    static std::once_flag once;
-    static cudaError_t attrErr = cudaSuccess;
-    std::call_once(once, [&] {
-        attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static Sg3DeviceOnce once;
+    const cudaError_t attrErr = once.run([&] {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         // all of the SM's shared memory: five 44.5 KB CTAs (UP = 2) only fit with the maximum carve-out
-        if (attrErr == cudaSuccess) attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        return e;
     });
     if (attrErr != cudaSuccess) return (int)attrErr;
     const long long ctas = (p.totalStrips + kWarpsPerCta - 1) / kWarpsPerCta;

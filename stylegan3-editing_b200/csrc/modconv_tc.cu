@@ -375,11 +375,11 @@ int launch_fwd_tc(const void* x, const void* wmod, void* y, int N, int I, int O,
     }
     p.stages = bn > 128 ? 4 : 6;                            // 4 x 48 KB or 6 x <= 32 KB of operand stages
     const int smemBytes = p.stages * (A_STAGE_BYTES + bn * BK * 4) + 1024;
-    static std::once_flag once;
-    static cudaError_t attrErr = cudaSuccess;
-    std::call_once(once, [] {
-        attrErr = cudaFuncSetAttribute(modconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (attrErr == cudaSuccess) attrErr = cudaFuncSetAttribute(modconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    static Sg3DeviceOnce once;
+    const cudaError_t attrErr = once.run([] {
+        cudaError_t e = cudaFuncSetAttribute(modconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(modconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        return e;
     });
     if (attrErr != cudaSuccess) return (int)attrErr;
     modconv_tc_kernel<HALF><<<(unsigned)ctas, kThreads, smemBytes, stream>>>(mapX, mapW, p);
@@ -434,9 +434,8 @@ int sg3_modconv_wgrad_tc(const float* dy, const float* x, float* dw, int N, int 
     if (!make_map3(&mapX, x, (uint64_t)P, (uint64_t)I, (uint64_t)N, (uint64_t)P * 4, (uint64_t)P * I * 4, BK, (uint32_t)bn)) return SG3_E_NOKERNEL;
     const int stages = bn > 128 ? 4 : 6;
     const int smemBytes = stages * (A_STAGE_BYTES + bn * BK * 4) + 1024;
-    static std::once_flag once;
-    static cudaError_t attrErr = cudaSuccess;
-    std::call_once(once, [] { attrErr = cudaFuncSetAttribute(modconv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    static Sg3DeviceOnce once;
+    const cudaError_t attrErr = once.run([] { return cudaFuncSetAttribute(modconv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     if (attrErr != cudaSuccess) return (int)attrErr;
     modconv_wgrad_kernel<<<(unsigned)ctas, kThreads, smemBytes, stream>>>(mapDY, mapX, p);
     return sg3_launch_status();

@@ -332,9 +332,8 @@ int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int 
             return SG3_E_NOKERNEL;
     }
     const int smemBytes = 2 * p.xGroupBytes + p.wSlots * p.wSlotBytes + 4 * 32 * STAGE_PITCH * 4 + 1024;
-    static std::once_flag once;
-    static cudaError_t attrErr = cudaSuccess;
-    std::call_once(once, [] { attrErr = cudaFuncSetAttribute(modconv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3); });
+    static Sg3DeviceOnce once;
+    const cudaError_t attrErr = once.run([] { return cudaFuncSetAttribute(modconv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3); });
     if (attrErr != cudaSuccess) return (int)attrErr;
     modconv_tc3_kernel<<<(unsigned)ctas, kThreads3, smemBytes, stream>>>(mapX, mapW, p);
     return sg3_launch_status();

@@ -186,11 +186,11 @@ int launch_sep(const SepParams& p0, cudaStream_t stream)
     p.tilesX = (p.outW + G::TW - 1) / G::TW;
     p.tilesY = (p.outH + G::TH - 1) / G::TH;
     auto kern = upfirdn2d_sep_kernel<T, UP, DOWN, KP>;
-    static std::once_flag once;
-    static cudaError_t attrErr = cudaSuccess;
-    std::call_once(once, [&] {
-        attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
-        if (attrErr == cudaSuccess) attrErr = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    static Sg3DeviceOnce once;
+    const cudaError_t attrErr = once.run([&] {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smemBytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        return e;
     });
     if (attrErr != cudaSuccess) return (int)attrErr;
     const int64_t total = (int64_t)p.tilesX * p.tilesY * p.N * p.C;

@@ -1,6 +1,7 @@
 """Drop-in seam: expose this package's op modules as `torch_utils.ops.{filtered_lrelu,bias_act,
 upfirdn2d,conv2d_gradfix}` so the reference's model code (`from torch_utils.ops import ...`,
 networks_stylegan3.py:18) and pickled generators pick them up unchanged."""
+import contextlib
 import importlib
 import sys
 import types
@@ -23,8 +24,19 @@ def _conv2d_gradfix_module():
         return torch.nn.functional.conv_transpose2d(input=input, weight=weight, bias=bias, stride=stride, padding=padding,
                                                     output_padding=output_padding, groups=groups, dilation=dilation)
 
+    @contextlib.contextmanager
+    def no_weight_gradients(disable=True):
+        # conv2d_gradfix.py:25-33: a flag the reference's custom conv backward consults; with `enabled = False` (plain
+        # F.conv2d) it changes nothing, but callers such as setgan/loss.py:152 still enter the context
+        old = m.weight_gradients_disabled
+        if disable:
+            m.weight_gradients_disabled = True
+        yield
+        m.weight_gradients_disabled = old
+
     m.conv2d = conv2d
     m.conv_transpose2d = conv_transpose2d
+    m.no_weight_gradients = no_weight_gradients
     return m
 
 
@@ -51,7 +63,11 @@ def install(override_existing=True):
         setattr(sys.modules['torch_utils'], 'ops', sys.modules['torch_utils.ops'])
     ops = sys.modules['torch_utils.ops']
     if 'torch_utils.ops.conv2d_gradfix' not in sys.modules:
-        mods['torch_utils.ops.conv2d_gradfix'] = _conv2d_gradfix_module()
+        # the reference's own conv2d_gradfix (pure Python, no plugin) when its tree is importable; the stand-in otherwise
+        try:
+            importlib.import_module('torch_utils.ops.conv2d_gradfix')
+        except Exception:
+            mods['torch_utils.ops.conv2d_gradfix'] = _conv2d_gradfix_module()
     for name, mod in mods.items():
         if override_existing or name not in sys.modules:
             sys.modules[name] = mod

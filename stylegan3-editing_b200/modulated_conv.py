@@ -82,6 +82,8 @@ def conv_forward(x, wmod, O, k, padding, math):
         ldw = wmod.shape[-1]
         rc = capi.lib().sg3_modconv_fwd(x.data_ptr(), wmod.data_ptr(), y.data_ptr(), N, I, O, H, W, k, padding, ldw,
                                         1 if math == 'tf32' else 0, capi.dtype_code(x.dtype), capi.stream_ptr(x.device))
+    if rc == capi.SG3_E_NOKERNEL:
+        return None             # e.g. a base pointer off the 16-byte TMA alignment: the caller reruns the SIMT contraction
     capi.check(rc, 'sg3_modconv_fwd')
     return y
 
@@ -123,15 +125,25 @@ class _ModConv(torch.autograd.Function):
             # no up / down casts of the activations
             wmod = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, half=True)
             y = conv_forward(xin, wmod, O, k, padding, 'tf32')
-            ctx.save_for_backward(x, w, s, input_gain)
-            ctx.cfg = (demodulate, padding, math)
-            return y
+            if y is not None:
+                ctx.save_for_backward(x, w, s, input_gain)
+                ctx.cfg = (demodulate, padding, math)
+                return y
+            math = 'fp32'                  # no fp16 tensor-core launch for this tensor (alignment): upcast + SIMT below
         x32 = xin if xin.dtype == torch.float32 else xin.float()
         if math == 'tf32' and not tc_supported(I, O, x32.shape[2], x32.shape[3], k, padding):
             math = 'fp32'                  # shapes without a tensor-core kernel run the exact SIMT contraction
         wmod = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, round_tf32=(math == 'tf32'),
                                tap_major=(math == 'tf32' and k > 1))
         y = conv_forward(x32, wmod, O, k, padding, math)
+        if y is None and math == 'tf32':
+            # the shape has a tensor-core kernel but this tensor does not (unaligned view, tensor-map encode failure):
+            # rebuild the weights in the plain fp32 layout and run the exact SIMT contraction
+            math = 'fp32'
+            wmod = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain)
+            y = conv_forward(x32, wmod, O, k, padding, math)
+        if y is None:
+            raise capi.Sg3Error('sg3_modconv_fwd: no kernel for these parameters')
         ctx.save_for_backward(x, w, s, input_gain)
         ctx.cfg = (demodulate, padding, math)
         return y if x.dtype == torch.float32 else y.to(x.dtype)
@@ -202,6 +214,8 @@ def _native_backward_1x1(x, w, s, input_gain, dy, demodulate, need):
     if need[0]:
         wT = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, round_tf32=True, transpose=True)
         dx = conv_forward(dy, wT, I, 1, 0, 'tf32')
+        if dx is None:
+            raise capi.Sg3Error('sg3_modconv_fwd (dgrad): no tensor-core kernel for this dy tensor')
     if need[1] or need[2]:
         ldw = (I + 31) // 32 * 32
         dWn = torch.zeros([N, O, ldw], dtype=torch.float32, device=x.device)

@@ -21,14 +21,29 @@ from . import capi
 _taps = {}
 
 
+def _version_of(f):
+    """Version counter of `f`, or None for tensors that do not track one (created under torch.inference_mode())."""
+    try:
+        return f._version
+    except RuntimeError:
+        return None
+
+
 def host_taps(f):
-    """float32 numpy copy of filter tensor `f` (cached per tensor object + version)."""
+    """float32 numpy copy of filter tensor `f`, cached per tensor object + version counter.
+
+    Update a filter with `f.copy_(...)` (bumps the version); writes through `f.data` are invisible to the cache.
+    Inference tensors have no version counter and are immutable outside inference mode: they are keyed on
+    (data_ptr, shape) instead."""
     key = id(f)
+    ver = _version_of(f)
+    if ver is None:
+        ver = ('inference', f.data_ptr(), tuple(f.shape))
     hit = _taps.get(key)
-    if hit is not None and hit[0]() is f and hit[1] == f._version:
+    if hit is not None and hit[0]() is f and hit[1] == ver:
         return hit[2]
     arr = np.ascontiguousarray(f.detach().to(device='cpu', dtype=torch.float32).numpy())
-    _taps[key] = (weakref.ref(f, lambda _r, k=key: _taps.pop(k, None)), f._version, arr)
+    _taps[key] = (weakref.ref(f, lambda _r, k=key: _taps.pop(k, None)), ver, arr)
     return arr
 
 

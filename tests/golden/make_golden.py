@@ -131,6 +131,10 @@ def gen_flrelu(rng, out):
         ('generic_3_2', f2, f2, 3, 2, [2, 3, 1, 4], 1.1, 0.3, 1.5, False, (1, 2, 9, 10)),
         ('up1_dn2', None, F_DN2, 1, 2, [0, 0, 0, 0], np.sqrt(2), 0.2, 1.0, False, (1, 2, 30, 31)),
         ('up2_dn1', F_UP2, None, 2, 1, [6, 5, 6, 5], np.sqrt(2), 0.2, 1.0, False, (1, 2, 12, 13)),
+        # appended in round 2 (the rng stream of the cases above is unchanged): a missing filter next to a factor of 2 -- fu=None is
+        # the 1x1 identity (zero insertion only), fd=None plain decimation; the backward of the second is the first
+        ('fuNone_up2_dn2', None, F_DN2, 2, 2, [3, 2, 3, 2], np.sqrt(2), 0.2, 1.0, False, (1, 2, 20, 21)),
+        ('up2_dn2_fdNone', F_UP2, None, 2, 2, [6, 5, 6, 5], np.sqrt(2), 0.2, 1.0, False, (1, 2, 14, 15)),
     ]
     for name, fu, fd, up, down, pad, gain, slope, clamp, flip, shape in specs:
         x = (rng.randn(*shape) * (4.0 if clamp and clamp < 10 else 2.0)).astype(np.float32)

@@ -300,3 +300,33 @@ def test_bench_work_table_matches_oracle_geometry():
         assert [(r['flrelu_bytes'], r['conv_flops'], r['flrelu_fma']) for r in mine] == [(r['flrelu_bytes'], r['conv_flops'], r['flrelu_fma']) for r in ref]
         assert abs(sum(r['flrelu_bytes'] for r in mine) / 1e9 - gb) < 2e-3
         assert abs(sum(r['conv_flops'] for r in mine) / 1e9 - gflop) < 0.1
+
+
+def test_dropin_conv2d_gradfix_stub_has_no_weight_gradients():
+    """reference code (setgan/loss.py:152) enters conv2d_gradfix.no_weight_gradients() after install()."""
+    from sg3_b200 import dropin
+    m = dropin._conv2d_gradfix_module()
+    assert m.weight_gradients_disabled is False
+    with m.no_weight_gradients():
+        assert m.weight_gradients_disabled is True
+        with m.no_weight_gradients(False):
+            assert m.weight_gradients_disabled is True
+    assert m.weight_gradients_disabled is False
+    import torch
+    y = m.conv2d(torch.ones(1, 1, 4, 4), torch.ones(1, 1, 3, 3), padding=1)
+    assert float(y[0, 0, 1, 1]) == 9.0
+
+
+def test_host_taps_cache_inference_tensors_and_versions():
+    """filter buffers created under torch.inference_mode() have no version counter."""
+    import torch
+    from sg3_b200 import upfirdn2d
+    with torch.inference_mode():
+        f = torch.arange(4, dtype=torch.float32)
+    a = upfirdn2d.host_taps(f)
+    assert a.tolist() == [0, 1, 2, 3] and upfirdn2d.host_taps(f) is a
+    g = torch.ones(3)
+    b = upfirdn2d.host_taps(g)
+    assert upfirdn2d.host_taps(g) is b
+    g.mul_(2)                                   # in-place update bumps the version: the cache must refresh
+    assert upfirdn2d.host_taps(g).tolist() == [2, 2, 2]
