@@ -167,6 +167,8 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
 
     // Correlation-ordered taps: F'[b] = f[b] if flip else f[last - b]; zero beyond the real filter.
     const int up = d->up;
+    memset(p.tu, 0, sizeof(p.tu));
+    memset(p.tv, 0, sizeof(p.tv));
     for (int ph = 0; ph < 4; ph++)
         for (int k = 0; k < fs::kTapsPerPhase; k++) {
             float v = 0.f;
@@ -185,15 +187,19 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
         for (int b = 0; b < fs::kDownTaps; b++)
             fd2[a][b] = (full && a < fdH && b < fdW) ? d->fd[(d->flip ? a : fdH - 1 - a) * fdW + (d->flip ? b : fdW - 1 - b)] : 0.f;
     memset(p.fdr, 0, sizeof(p.fdr));
-    memset(p.fdvr, 0, sizeof(p.fdvr));
     for (int rot = 0; rot < 3; rot++)
         for (int i = 0; i < 6; i++) {
             const int k = (i + 2 * rot) % 6;                      // logical accumulator held by slot i at this rotation
-            for (int half = 0; half < 2; half++) {
-                p.fdvr[rot][half][i] = p.fdx[2 * k + half];
-                for (int b = 0; b < fs::kDownTaps; b++) p.fdr[rot][half][b][i] = fd2[2 * k + half][b];
-            }
+            for (int half = 0; half < 2; half++)
+                for (int b = 0; b < fs::kDownTaps; b++) p.fdr[rot][half][b >> 1][(b & 1) * 6 + i] = fd2[2 * k + half][b];
         }
+    // paired output stores (two adjacent columns per lane): unit pixel stride, every row / plane / base address a multiple
+    // of the pair size (strips start at even columns)
+    {
+        const long long es = d->dtype == SG3_F32 ? 4 : 2;
+        p.vecStore = d->yStride[3] == es && ((uintptr_t)d->y % (2 * es)) == 0 && d->yStride[2] % (2 * es) == 0 &&
+                     d->yStride[1] % (2 * es) == 0 && d->yStride[0] % (2 * es) == 0;
+    }
 
     // Strip decomposition: TW-column strips (58 / 56 outputs for up 2 / 4); rows are chunked only when there are too few strips to
     // fill the machine (one warp per strip, ~16 resident warps per SM, a few waves).

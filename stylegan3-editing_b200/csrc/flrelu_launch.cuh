@@ -9,11 +9,11 @@ template <class T, int UP, int FD, int MODE, bool TMA>
 int launch_one(const Params& p, cudaStream_t stream)
 {
     auto kern = kernel<T, UP, FD, MODE, TMA>;
-    const int smem = kWarpsPerCta * Geo<UP>::warp_bytes(MODE);
+    const int smem = kWarpsPerCta * Geo<UP>::WARP_BYTES;
     static Sg3DeviceOnce once;
     const cudaError_t attrErr = once.run([&] {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        // all of the SM's shared memory: five 44.5 KB CTAs (UP = 2) only fit with the maximum carve-out
+        // four 28 KB CTAs per SM: ask for the large carve-out
         if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         return e;
     });
