@@ -1,6 +1,10 @@
 """bench.py -- StyleGAN3-R 1024^2 generator-forward throughput on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference] [--config R|T|restyle|pti]
+
+--config R (default) is the metric BASELINE.json is quoted on (configs[2]); T = configs[1]; restyle = configs[3] (ReStyle-pSp
+iterative inversion, 5 steps, batch 8); pti = configs[4] (PTI fine-tuning over 64 frames, batch 4 per GPU, data-parallel with
+one NCCL gradient all-reduce per step).
 
 One process per GPU (the driver launches N>1 with torch.distributed.run); the batch is sharded
 across ranks with no data-path collective (weak scaling, fixed per-GPU batch).  A "step" is one
@@ -12,7 +16,7 @@ Rank 0 prints ONE JSON line.  Keys:
                  plus the FP32-pipe fraction that actually binds it
   cpu_baseline   the CPU oracle (port of the reference's impl='ref' path) timed on this box's cores on a bounded sample
 `--impl reference` times the reference's own CPU algorithm (oracle port; the Python reference tree cannot
-travel to the GPU box) with all host threads on a bounded sample of the same workload.
+travel to the GPU box) with all host threads; a step is ONE WHOLE image of the same workload (no extrapolation).
 """
 import argparse
 import json
@@ -44,10 +48,13 @@ def parse_args():
     ap.add_argument('--batch', type=int, default=32, help='images per GPU per step')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--math', default='tf32', choices=['tf32', 'fp32'], help='modulated_conv2d contraction')
-    ap.add_argument('--cpu-seconds', type=float, default=20.0, help='time budget of the cpu_baseline sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--config', default='R', choices=['R', 'T'],
-                    help='R: StyleGAN3-R 1024^2 (the metric BASELINE.json is quoted on, default); T: StyleGAN3-T 1024^2 (configs[1])')
+    ap.add_argument('--config', default='R', choices=['R', 'T', 'restyle', 'pti'],
+                    help='R: StyleGAN3-R 1024^2 forward (the metric BASELINE.json is quoted on, default); T: StyleGAN3-T 1024^2 '
+                         'forward (configs[1]); restyle: ReStyle-pSp inversion, 5 steps, batch 8 (configs[3]); pti: PTI fine-tuning, '
+                         '64 frames, batch 4 per GPU, NCCL gradient all-reduce (configs[4])')
+    ap.add_argument('--frames', type=int, default=64, help='--config pti: global number of frames')
+    ap.add_argument('--eager', action='store_true', help='--config restyle: no CUDA-graph replay of the synthesis calls')
     args = ap.parse_args()
     if args.config == 'T':
         global METRIC, CFG_NAME
@@ -81,9 +88,9 @@ def layer_work(specs, esize=4):
 # --------------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference's impl='ref' path, bounded sample.
 
-def cpu_sample(seconds, threads=None):
-    """Run the oracle's R-1024 synthesis forward for ONE image layer by layer until `seconds` are used up;
-    returns images/s extrapolated by the fraction of the per-image algorithmic FLOPs covered."""
+def cpu_image(threads=None):
+    """ONE whole image of the workload's synthesis forward on the CPU oracle (the reference's impl='ref' algorithm), all
+    layers; returns the wall time in seconds and the thread count.  No extrapolation of any kind."""
     import torch
     from oracle import sg3_oracle as orc
     import sg3_b200  # noqa: F401  (only for the random-init weights; no kernel is launched here)
@@ -93,54 +100,66 @@ def cpu_sample(seconds, threads=None):
         threads = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
     orc.set_num_threads(threads)
     cores = orc.num_threads()
-    torch.manual_seed(0)
-    G = networks.Generator(**R1024).eval().requires_grad_(False)
-    z = torch.randn(1, 512, generator=torch.Generator().manual_seed(1))
-    # mapping network on CPU in plain torch (negligible work; bias_act has no CPU path by design)
-    x = z * (z.square().mean(1, keepdim=True) + 1e-8).rsqrt()
-    for i in range(2):
-        fc = getattr(G.mapping, f'fc{i}')
-        x = torch.nn.functional.leaky_relu(x @ (fc.weight * fc.weight_gain).t() + fc.bias * fc.bias_gain, 0.2) * np.sqrt(2)
-    ws = x.unsqueeze(1).repeat(1, G.num_ws, 1).numpy()
-    state = {k: v.numpy() for k, v in G.synthesis.state_dict().items()}
-    cfg = {k: v for k, v in R1024.items() if k not in ('z_dim', 'c_dim', 'w_dim', 'img_resolution', 'img_channels')}
-    net = orc.SynthesisOracle(state, img_resolution=1024, w_dim=512, **cfg)
-    work = layer_work(net.specs)
-    total = sum(r['conv_flops'] + 2 * r['flrelu_fma'] for r in work)
+    st = _CPU_STATE
+    if 'net' not in st:
+        torch.manual_seed(0)
+        G = networks.Generator(**R1024).eval().requires_grad_(False)
+        z = torch.randn(1, 512, generator=torch.Generator().manual_seed(1))
+        # mapping network on CPU in plain torch (negligible work; bias_act has no CPU path by design)
+        x = z * (z.square().mean(1, keepdim=True) + 1e-8).rsqrt()
+        for i in range(2):
+            fc = getattr(G.mapping, f'fc{i}')
+            x = torch.nn.functional.leaky_relu(x @ (fc.weight * fc.weight_gain).t() + fc.bias * fc.bias_gain, 0.2) * np.sqrt(2)
+        st['ws'] = x.unsqueeze(1).repeat(1, G.num_ws, 1).numpy()
+        state = {k: v.numpy() for k, v in G.synthesis.state_dict().items()}
+        cfg = {k: v for k, v in R1024.items() if k not in ('z_dim', 'c_dim', 'w_dim', 'img_resolution', 'img_channels')}
+        st['net'] = orc.SynthesisOracle(state, img_resolution=1024, w_dim=512, **cfg)
     t0 = time.perf_counter()
-    xa = net.input_features(ws[:, 0])
-    done, nl = 0.0, 0
-    for i, sp in enumerate(net.specs):
-        xa = net.layer(sp, xa, ws[:, i + 1])
-        done += work[i]['conv_flops'] + 2 * work[i]['flrelu_fma']
-        nl = i + 1
-        if time.perf_counter() - t0 > seconds:
-            break
+    img = st['net'].forward(st['ws'])
     dt = time.perf_counter() - t0
-    frac = done / total
-    return dict(value=frac / dt, unit='images/s', cores=cores, kind='port',
-                sample=f'1 image, StyleGAN3-{CFG_NAME} 1024^2 synthesis layers L0..L{nl - 1} of 15 on the CPU oracle '
-                       f'({100 * frac:.1f}% of per-image FLOPs, {dt:.1f} s); images/s extrapolated by FLOP share')
+    assert img.shape == (1, 3, 1024, 1024)
+    return dt, cores
+
+
+_CPU_STATE = {}
+
+
+def cpu_baseline_entry(dt, cores):
+    return dict(value=1.0 / dt, unit='images/s', cores=cores, kind='port',
+                sample=f'1 whole image of StyleGAN3-{CFG_NAME} 1024^2 synthesis forward (all 15 layers) on the CPU oracle = port of the '
+                       f"reference's impl='ref' path, {dt:.1f} s on {cores} threads; no extrapolation")
+
+
+def workload_config(world, B, math):
+    return dict(workload=f'StyleGAN3-{CFG_NAME} 1024^2 synthesis forward (BASELINE.json configs[{2 if CFG_NAME == "R" else 1}]), random-init seed 0, '
+                         'force_fp32, noise_mode=const', per_gpu_batch=B, global_batch=world * B,
+                parallelism=f'batch-sharded x{world}, no collective', conv_math=math,
+                l2='activations of every layer exceed the 126 MB L2 (inputs larger than L2, no flush needed)')
 
 
 def run_reference(args):
+    """Reference arm: the reference's CPU algorithm on this box's host cores.  One step = one whole image (the per-GPU batch of
+    the GPU arm is 32 images of the same kind); `value` = images per second of the timed steps."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    per_step = max(args.cpu_seconds / max(args.steps + args.warmup, 1), 5.0)
-    vals = []
-    info = None
+    if args.config in ('restyle', 'pti'):
+        print(json.dumps(dict(impl='reference', unavailable=f'--config {args.config}: the CPU oracle restates the synthesis hot path only '
+                                                               '(no encoder / LPIPS / whole-network backward); use --config R or T')))
+        return
+    times, cores = [], 1
     for i in range(args.warmup + args.steps):
-        info = cpu_sample(per_step)
+        dt, cores = cpu_image()
         if i >= args.warmup:
-            vals.append(info['value'])
-    v = float(np.mean(vals))
-    info['value'] = v
+            times.append(dt)
+    step_s = float(np.mean(times))
+    v = 1.0 / step_s
+    info = cpu_baseline_entry(step_s, cores)
+    cfg = workload_config(args.gpus, args.batch, args.math)
+    cfg['reference_sample'] = 'one whole image per step on the host CPU (same generator, same seeds)'
     out = dict(metric=METRIC, value=v, unit='images/s', impl='reference', n_gpus=args.gpus, steps=args.steps,
-               warmup=args.warmup, ms_per_step=1e3 / v if v > 0 else None, higher_is_better=True, scaling='weak',
-               vs_baseline=None, dtype='f32', data='synthetic',
-               config=dict(workload=f'StyleGAN3-{CFG_NAME} 1024^2 synthesis forward, random-init, fp32 (force_fp32)',
-                           note='reference CPU algorithm (impl=ref composition) via the oracle port; bounded sample per step'),
+               warmup=args.warmup, ms_per_step=1e3 * step_s, higher_is_better=True, scaling='weak',
+               vs_baseline=None, dtype='f32', data='synthetic', config=cfg,
                cpu_baseline=info, e2e=dict(value=v, unit='images/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(out))
 
@@ -329,16 +348,20 @@ def run_ours(args):
     fp32_peak_tfma = 148 * 128 * 1.965e9 / 1e12          # 37.2 TFMA/s at max SM clock
     fma_rate = fma_per_img * B * args.steps / (fl_ms * 1e-3) / 1e12 if fl_ms > 0 else 0.0
 
-    # measured DRAM traffic of the filtered_lrelu launches (ncu dram__bytes_read.sum + dram__bytes_write.sum, committed capture),
-    # scaled from the profiled batch to this step's batch; compare with `algorithmic_bytes`
-    traffic, traffic_note = None, 'no ncu traffic capture for this config'
-    try:
-        tr = json.load(open(os.path.join(ROOT, 'profiles', 'r01_flrelu_traffic.json')))
-        if tr.get('config') == CFG_NAME:
-            traffic = tr['dram_bytes_per_image'] * B
-            traffic_note = 'bytes per step = ncu dram read+write per image (profiles/r01_flrelu_traffic.json, batch 2 capture) x per-GPU batch'
-    except Exception:
-        pass
+    # DRAM traffic of the filtered_lrelu launches: NOT measured in this run (a number taken under a profiler is not a bench
+    # value) -- a static figure from the committed ncu capture of the same kernels (dram__bytes_read.sum + dram__bytes_write.sum
+    # over the 15 launches of one forward), scaled from the profiled batch to this step's batch; compare with `algorithmic_bytes`
+    traffic, traffic_note = None, 'static: no committed ncu traffic capture for this config'
+    for name in ('r02_flrelu_traffic.json', 'r01_flrelu_traffic.json'):
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', name)))
+            if tr.get('config') == CFG_NAME:
+                traffic = tr['dram_bytes_per_image'] * B
+                traffic_note = (f'static (not measured in this run): ncu dram read+write per image from profiles/{name} '
+                                f'(batch {tr.get("batch", 2)} capture) x per-GPU batch')
+                break
+        except Exception:
+            pass
 
     # modulated_conv2d: FLOPs 2*N*O*I*k^2*(H+k-1)^2 and minimum bytes 4*N*(I*H^2 + O*(H+k-1)^2) per layer; the TF32
     # tensor peak is taken as half the measured dense bf16 cuBLAS rate (tcgen05 kind::tf32 runs at half the kind::f16 rate)
@@ -363,25 +386,27 @@ def run_ours(args):
         metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
         dtype='f32' if args.math == 'fp32' else 'f32 (tf32 tensor-core conv)', data='synthetic',
-        config=dict(workload=f'StyleGAN3-{CFG_NAME} 1024^2 synthesis forward (BASELINE.json configs[{2 if CFG_NAME == "R" else 1}]), random-init seed 0, '
-                             'force_fp32, noise_mode=const', per_gpu_batch=B, global_batch=world * B,
-                    parallelism=f'batch-sharded x{world}, no collective', conv_math=args.math,
-                    l2='activations of every layer exceed the 126 MB L2 (inputs larger than L2, no flush needed)'),
+        config=workload_config(world, B, args.math),
+        build=capi.lib().sg3_build_info().decode(),
         clocks=clocks,
         e2e=dict(value=world * B * args.steps / (e2e_ms * 1e-3), unit='images/s',
                  h2d_bytes_per_step=int(ws_host.numel() * 4), d2h_bytes_per_step=int(img_host[0].numel() * 4)),
         gpu_launches=int(launches),
         conv=conv,
+        # `bound` names the roof `achieved` / `peak` / `frac` are quoted against (the contract's HBM roof); the roof that actually
+        # binds this kernel with fp32 SIMT math is the FP32 pipe: `binds` + the flat fp32_pipe_* keys
         roofline=dict(bound='hbm', achieved=achieved, peak=hbm_peak, unit='GB/s', frac=achieved / hbm_peak,
                       traffic=traffic, algorithmic_bytes=fl_bytes / args.steps, traffic_note=traffic_note,
                       kernel='filtered_lrelu (15 calls per step, all timed with CUDA events)',
                       launches_timed=n_calls, ms_per_step=fl_ms / args.steps,
                       peak_source='MEASURED_PEAKS.json hbm_gbs (of measured)' if peaks else 'fallback 6650 GB/s (of fallback)',
-                      fp32_pipe=dict(achieved_tfma=fma_rate, peak_tfma=fp32_peak_tfma, frac=fma_rate / fp32_peak_tfma,
-                                     note='polyphase FMAs of the fused op; fp32 SIMT is the roof that binds it (DESIGN.md)')),
+                      binds='fp32_pipe', fp32_pipe_frac=fma_rate / fp32_peak_tfma, fp32_pipe_achieved_tfma=fma_rate,
+                      fp32_pipe_peak_tfma=fp32_peak_tfma,
+                      fp32_pipe_note='nominal polyphase FMAs of the fused op (dense 12x12 down filter counted as 144 MACs per output) / '
+                                     'CUDA-event time vs 148 SMs x 128 lanes x 1.965 GHz'),
     )
     # cpu_baseline: timed on rank 0 at N = 1 only (the host cores are shared by all ranks of a multi-GPU run)
-    out['cpu_baseline'] = cpu_sample(args.cpu_seconds) if (world == 1 and not args.no_cpu_baseline) else None
+    out['cpu_baseline'] = cpu_baseline_entry(*cpu_image()) if (world == 1 and not args.no_cpu_baseline) else None
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -391,6 +416,12 @@ def main():
     args = parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.config == 'restyle':
+        from examples import bench_workloads
+        bench_workloads.run_restyle(args, ClockSampler)
+    elif args.config == 'pti':
+        from examples import bench_workloads
+        bench_workloads.run_pti(args, ClockSampler)
     else:
         run_ours(args)
 

@@ -6,6 +6,7 @@ nvcc cross-compiles for sm_100a without a GPU.  Objects go to csrc/build/ (git-i
 shared library next to this file so it travels to the GPU box with the repository snapshot.
 """
 import concurrent.futures
+import hashlib
 import os
 import subprocess
 import sys
@@ -30,13 +31,33 @@ def _deps_mtime():
     return max(os.path.getmtime(h) for h in hdrs)
 
 
+def source_hash():
+    """sha256 over the names and contents of every source the library is built from (csrc/*.{cu,cuh,h}, include/sg3_b200.h)."""
+    h = hashlib.sha256()
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cu', '.cuh', '.h'))]
+    files.append(os.path.join(os.path.dirname(HERE), 'include', 'sg3_b200.h'))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
 def _compile(src, force, verbose):
     obj = os.path.join(OBJ, src[:-3] + '.o')
     path = os.path.join(CSRC, src)
     newest = max(os.path.getmtime(path), _deps_mtime())
+    extra = []
+    if src == 'capi.cu':
+        # the build-info string carries the source hash: this one file is rebuilt whenever any source changed
+        digest = source_hash()
+        extra = ['-DSG3_SOURCE_HASH=' + digest]
+        stamp = obj + '.hash'
+        if not (os.path.exists(stamp) and open(stamp).read() == digest):
+            force = True
     if not force and os.path.exists(obj) and os.path.getmtime(obj) >= newest:
         return obj, False
-    cmd = [NVCC] + ARCH + CFLAGS + ['-c', path, '-o', obj]
+    cmd = [NVCC] + ARCH + CFLAGS + extra + ['-c', path, '-o', obj]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(obj + '.log', 'w') as f:
         f.write(' '.join(cmd) + '\n' + res.stdout)
@@ -44,6 +65,9 @@ def _compile(src, force, verbose):
         raise RuntimeError(f'nvcc failed for {src}:\n{res.stdout}')
     if verbose:
         print(res.stdout)
+    if extra:
+        with open(obj + '.hash', 'w') as f:
+            f.write(extra[0].split('=', 1)[1])
     return obj, True
 
 

@@ -26,9 +26,16 @@ SG3_EXPORT int sg3_abi_version(void) { return SG3_ABI_VERSION; }
 
 SG3_EXPORT int sg3_sizeof_flrelu_desc(void) { return (int)sizeof(sg3_flrelu_desc); }
 
+// SG3_SOURCE_HASH: sha256 (first 12 hex digits) over every file of csrc/ and include/ at build time, passed by build.py, so a
+// bench line or a test log names the exact sources the loaded library was compiled from.
+#ifndef SG3_SOURCE_HASH
+#define SG3_SOURCE_HASH unknown
+#endif
+
 SG3_EXPORT const char* sg3_build_info(void)
 {
-    return "libsg3_b200 sm_100a nvcc " SG3_STR(__CUDACC_VER_MAJOR__) "." SG3_STR(__CUDACC_VER_MINOR__) " abi " SG3_STR(SG3_ABI_VERSION);
+    return "libsg3_b200 sm_100a nvcc " SG3_STR(__CUDACC_VER_MAJOR__) "." SG3_STR(__CUDACC_VER_MINOR__) " abi " SG3_STR(SG3_ABI_VERSION)
+           " src " SG3_STR(SG3_SOURCE_HASH);
 }
 
 SG3_EXPORT const char* sg3_error_string(int code)

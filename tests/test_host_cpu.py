@@ -330,3 +330,41 @@ def test_host_taps_cache_inference_tensors_and_versions():
     assert upfirdn2d.host_taps(g) is b
     g.mul_(2)                                   # in-place update bumps the version: the cache must refresh
     assert upfirdn2d.host_taps(g).tolist() == [2, 2, 2]
+
+
+def test_build_info_carries_the_source_hash():
+    """whether build() recompiled anything must be visible -- the library names the sources it was built from."""
+    import importlib.util
+    import os
+    from sg3_b200 import capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('sg3_b200_build', os.path.join(root, 'stylegan3-editing_b200', 'build.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    info = capi.lib().sg3_build_info().decode()
+    assert info.endswith('src ' + mod.source_hash()), (info, mod.source_hash())
+
+
+def test_bench_reference_arm_config_and_workload_harness_import():
+    """bench.py's reference arm must carry the GPU arm's config keys; the configs[3] / configs[4] harness models build on CPU."""
+    import importlib
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    bench = importlib.import_module('bench')
+    cfg = bench.workload_config(1, 32, 'tf32')
+    assert set(cfg) >= {'workload', 'per_gpu_batch', 'global_batch', 'parallelism', 'conv_math', 'l2'}
+    import torch
+    from examples import workloads
+    enc = workloads.RestyleEncoder(n_styles=16, input_nc=6).eval()
+    with torch.no_grad():
+        codes = enc(torch.zeros(1, 6, 256, 256))
+    assert tuple(codes.shape) == (1, 16, 512)
+    lp = workloads.LPIPSAlex().eval()
+    a = torch.rand(1, 3, 64, 64, requires_grad=True)
+    d = lp(a, torch.rand(1, 3, 64, 64))
+    d.backward()
+    assert d.ndim == 0 and a.grad is not None and float(lp(a.detach(), a.detach())) == 0.0
+    m = workloads.random_landmarks_transforms(3, torch.Generator().manual_seed(0), 'cpu')
+    assert tuple(m.shape) == (3, 3, 3)
