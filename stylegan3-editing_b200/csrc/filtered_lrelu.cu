@@ -151,6 +151,11 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
         q.chunkRows = (d->outH + chunks - 1) / chunks;
         q.chunksY = (d->outH + q.chunkRows - 1) / q.chunkRows;
         q.totalStrips = base * q.chunksY;
+        {
+            const long long es = d->dtype == SG3_F32 ? 4 : 2;
+            q.vecStore = d->yStride[3] == es && ((uintptr_t)d->y % (2 * es)) == 0 && d->yStride[2] % (2 * es) == 0 &&
+                         d->yStride[1] % (2 * es) == 0 && d->yStride[0] % (2 * es) == 0;
+        }
         cudaStream_t st = (cudaStream_t)stream;
         if (d->dtype == SG3_F32) return d->down == 2 ? flrelu_bwd_launch<float, 2>(q, d->signMode, st) : flrelu_bwd_launch<float, 4>(q, d->signMode, st);
         return d->down == 2 ? flrelu_bwd_launch<__half, 2>(q, d->signMode, st) : flrelu_bwd_launch<__half, 4>(q, d->signMode, st);

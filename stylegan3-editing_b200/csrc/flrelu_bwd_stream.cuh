@@ -53,6 +53,7 @@ struct Params {
     float slope, clamp;
     int sH, sWb, sx, sy;
     int stripsX, chunksY, chunkRows;
+    int vecStore;                      // y has unit pixel stride and pair-aligned rows / planes: paired stores (down 2)
     long long totalStrips;
     float tu[2][2][6][6];              // tu[py][px][ka][kb] = up^2 * gain * FU'[ay + 2ka][bx + 2kb]
     float fd[24];                      // separable down taps, correlation order, zero padded
@@ -164,19 +165,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DOWN == 2 ? 5 : 4) kernel(c
     // (global latency in every group), so the RAW bytes of the next group are fetched at the end of the current one and
     // carried across the loop; they are only combined where the activation needs them, a whole stage U later.
     unsigned sLo[4] = {0u, 0u, 0u, 0u}, sHi[4] = {0u, 0u, 0u, 0u};
+    const int sgnRdByte = ((Xs - ex + p.sx) >> 2) + lane;          // arithmetic shift: floor for negative coordinates
+    const bool sgnRdLo = sgnRdByte >= 0 && sgnRdByte < p.sWb, sgnRdHi = sgnRdByte + 1 >= 0 && sgnRdByte + 1 < p.sWb;
+    // row 4g + j of the strip is sgnRd + j * sWb (the pointer walks down 4 rows per call); only dereferenced where row and byte exist
+    const uint8_t* sgnRd = p.s + (sPlane + Ys + p.sy) * p.sWb + sgnRdByte;
     auto loadSigns = [&](int g) {
         if (MODE == SG3_SIGNS_READ) {
-            const int byte0 = ((Xs - ex + p.sx) >> 2) + lane;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int sY = Ys + 4 * g + j + p.sy;
+                const bool rowOk = (unsigned)(Ys + 4 * g + j + p.sy) < (unsigned)p.sH;
+                const uint8_t* q = sgnRd + (long long)j * p.sWb;
                 sLo[j] = sHi[j] = 0u;
-                if (sY >= 0 && sY < p.sH) {
-                    const uint8_t* srow = p.s + (sPlane + sY) * p.sWb;
-                    if (byte0 >= 0 && byte0 < p.sWb) sLo[j] = __ldg(srow + byte0);
-                    if (byte0 + 1 >= 0 && byte0 + 1 < p.sWb) sHi[j] = __ldg(srow + byte0 + 1);
-                }
+                if (rowOk && sgnRdLo) sLo[j] = __ldg(q);
+                if (rowOk && sgnRdHi) sHi[j] = __ldg(q + 1);
             }
+            sgnRd += 4LL * p.sWb;
         }
     };
     loadSigns(0);
@@ -217,8 +220,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DOWN == 2 ? 5 : 4) kernel(c
             }
         }
         // activation (sign lookup or lrelu/clamp) and repack to (column, column+1) pairs per row
-        const int Xg = Xs - ex + 4 * lane;                  // global upsampled x of the lane's first column
         float2 rowv[4][2];                                  // [row j][column pair]
+        unsigned codes4[4] = {0u, 0u, 0u, 0u};              // the lane's four 2-bit codes of each row
+        if (MODE == SG3_SIGNS_READ) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) codes4[j] = (sLo[j] | (sHi[j] << 8)) >> (2 * ((Xs - ex + p.sx) & 3));
+            loadSigns(g + 1);                               // consumed a whole group from now: the bytes come from HBM
+        }
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int jp = j & 1, hi = j >> 1;
@@ -229,7 +237,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DOWN == 2 ? 5 : 4) kernel(c
                 v[q] = hi ? a2.y : a2.x;
             }
             if (MODE == SG3_SIGNS_READ) {
-                const unsigned bits = (sLo[j] | (sHi[j] << 8)) >> (2 * ((Xs - ex + p.sx) & 3));      // loaded a group ago (loadSigns)
+                const unsigned bits = codes4[j];
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     const unsigned code = (bits >> (2 * q)) & 3u;
@@ -282,7 +290,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DOWN == 2 ? 5 : 4) kernel(c
             for (int k = NV - 1; k >= 1; k--) { vacc[k][0] = vacc[k - 1][0]; vacc[k][1] = vacc[k - 1][1]; }
             vacc[0][0] = vacc[0][1] = make_float2(0.f, 0.f);
         }
-        loadSigns(g + 1);
     };
 
     // ---- stage H: horizontal down filter of the finished rows, store ----
@@ -301,7 +308,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DOWN == 2 ? 5 : 4) kernel(c
                 if (q < 12) h0 = ffma2(v, p.fd[q], h0);
                 if (q >= 2) h1 = ffma2(v, p.fd[q - 2], h1);
             }
-            if (oxl < tws) {
+            if (oxl + 1 < tws && p.vecStore) {
+                if (oA >= 0 && oA < chs) {
+                    if (sizeof(T) == 4) *(float2*)outRow = make_float2(h0.x, h1.x);
+                    else *(__half2*)outRow = __floats2half2_rn(h0.x, h1.x);
+                    ySum += h0.x + h1.x;
+                }
+                if (oB >= 0 && oB < chs) {
+                    if (sizeof(T) == 4) *(float2*)(outRow + p.ys[2]) = make_float2(h0.y, h1.y);
+                    else *(__half2*)(outRow + p.ys[2]) = __floats2half2_rn(h0.y, h1.y);
+                    ySum += h0.y + h1.y;
+                }
+            } else if (oxl < tws) {
                 const bool two = oxl + 1 < tws;
                 if (oA >= 0 && oA < chs) {
                     st_as<T>((T*)outRow, h0.x);

@@ -129,11 +129,21 @@ int main()
     for (int variant = 0; variant < 1; variant++)
         for (int N : {32, 64, 96, 128})
             for (int same : {0, 10, 11, 20, 21}) {
+                if ((same == 11 || same == 21) && N > 96) continue;      // four accumulators at column offsets: 4 x N + 2 must fit 512 TMEM columns
                 bench_kernel<<<1, 192, 98 * 1024>>>(variant, N, iters, 0, dout, same);
                 cudaError_t e = cudaDeviceSynchronize();
                 long long h[2]; cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost);
                 printf("variant %d N=%3d dmode=%d: %s  issue %.1f clk/MMA, complete %.1f clk/MMA (floor %d)\n", variant, N, same,
                        cudaGetErrorString(e), (double)h[0] / (4.0 * iters), (double)h[1] / (4.0 * iters), N / 2);
             }
+    // small-N sweep for the tensor-core FIR question (tools/tc_fir_model.py): banded-Toeplitz FIR formulations need
+    // N = 16 .. 64 outputs per MMA; is an M = 128 x N x 8 MMA with smem operands paced by N / 2 clocks or by its operand reads?
+    for (int N : {16, 32, 48, 64, 128, 256}) {
+        bench_kernel<<<1, 192, 98 * 1024>>>(0, N, iters, 0, dout, 20);
+        cudaError_t e = cudaDeviceSynchronize();
+        long long h[2]; cudaMemcpy(h, dout, 16, cudaMemcpyDeviceToHost);
+        printf("FIRSWEEP N=%3d: %s issue %.2f complete %.2f clk/MMA  (tensor floor %d, smem operand bytes %d)\n", N, cudaGetErrorString(e),
+               (double)h[0] / (4.0 * iters), (double)h[1] / (4.0 * iters), N / 2, 128 * 32 + N * 32);
+    }
     return 0;
 }
