@@ -47,7 +47,9 @@ def parse_args():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--batch', type=int, default=32, help='images per GPU per step')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--math', default='tf32', choices=['tf32', 'fp32'], help='modulated_conv2d contraction')
+    ap.add_argument('--math', default='tf32', choices=['tf32', 'fp32', 'fp32x3'],
+                    help='modulated_conv2d contraction: TF32 tensor cores (the reference\'s cuDNN default), exact FP32 SIMT, or '
+                         '3xTF32 tensor cores (fp32-accurate)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--config', default='R', choices=['R', 'T', 'restyle', 'pti'],
                     help='R: StyleGAN3-R 1024^2 forward (the metric BASELINE.json is quoted on, default); T: StyleGAN3-T 1024^2 '
@@ -385,7 +387,8 @@ def run_ours(args):
     out = dict(
         metric=METRIC, value=value, unit='images/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
-        dtype='f32' if args.math == 'fp32' else 'f32 (tf32 tensor-core conv)', data='synthetic',
+        dtype={'fp32': 'f32', 'tf32': 'f32 (tf32 tensor-core conv)', 'fp32x3': 'f32 (3xTF32 tensor-core conv, fp32-accurate)'}[args.math],
+        data='synthetic',
         config=workload_config(world, B, args.math),
         build=capi.lib().sg3_build_info().decode(),
         clocks=clocks,

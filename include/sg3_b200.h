@@ -151,12 +151,15 @@ int sg3_upfirdn2d_sep(const void* x, void* y, const float* fx, const float* fy,
  * 2 = [I], 3 = [N][I].  wmod is f32 [N][O][ldw] with row pitch ldw >= I*k*k floats (zero padded;
  * the tensor-core path needs ldw % 4 == 0); round_tf32 = 1: each value is rounded to the nearest TF32 so the
  * tensor-core contraction sees unbiased operands; round_tf32 = 2: wmod is written as float16 [N][O][ldw] (ldw % 8 == 0),
- * the weight operand of the fp16 tensor-core contraction (what the reference's w.to(x.dtype) produces for fp16 layers).
+ * the weight operand of the fp16 tensor-core contraction (what the reference's w.to(x.dtype) produces for fp16 layers);
+ * round_tf32 = 3 (layout 0): wmod is f32 [N][2][O][ldw], plane 0 = the weights rounded to TF32, plane 1 = the TF32-rounded
+ * residual -- the weight operand of the 3xTF32 contraction (mathMode 2).
  * scratch: >= 4 bytes of device memory (batch-global style norm).
  *
  * sg3_modconv_fwd: y[n][o][p] = sum_{i,tap} wmod[n][o][i][tap] * x[n][i][p + tap - pad]
  * x [N][I][H][W] contiguous, y [N][O][H+2pad-k+1][W+2pad-k+1] contiguous, dtype f32.
- * mathMode 0: FP32 SIMT (exact fp32 accumulate);  1: TF32 tcgen05 implicit GEMM.
+ * mathMode 0: FP32 SIMT (exact fp32 accumulate);  1: TF32 tcgen05 implicit GEMM;  2: 3xTF32 tcgen05 GEMM (k = 1 only: both
+ * operands split into TF32 head + tail, three MMAs per K step, fp32-accurate to ~1e-6; wmod from round_tf32 = 3).
  * dtype f16 (mathMode 1, k = 1, H*W % 8 == 0): x, y and wmod are float16, kind::f16 MMAs with fp32 accumulation.
  * ---------------------------------------------------------------------- */
 int sg3_modconv_weights(const float* w, const float* s, const float* input_gain, int gainMode,
@@ -187,6 +190,14 @@ int sg3_modconv_weights_bwd(const float* dwmod, const float* w, const float* s, 
 int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
                     int N, int I, int O, int H, int W, int k, int pad, int ldw,
                     int mathMode, int dtype, void* stream);
+
+/* Same contraction, output rows `yPitch` floats apart (y is [N][O][OH][yPitch >= OW]; 0 = contiguous).  First step of the
+ * conv -> filtered_lrelu fusion: with a 16-byte-multiple pitch the stencil that consumes y stages its input
+ * by TMA even when OW * 4 is not a multiple of 16 (every 3x3 layer of config T: OW = 38 ... 1046).  Implemented by the 3x3
+ * tensor-core kernel (mathMode 1, k = 3); other paths answer SG3_E_NOKERNEL unless yPitch is 0 or OW. */
+int sg3_modconv_fwd_pitched(const void* x, const float* wmod, void* y,
+                            int N, int I, int O, int H, int W, int k, int pad, int ldw, int yPitch,
+                            int mathMode, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,9 +9,12 @@
 #include "common.cuh"
 
 int sg3_modconv_wgrad_tc(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, cudaStream_t stream);
-int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw, cudaStream_t stream);
+int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw, int yPitch,
+                        cudaStream_t stream);
 int sg3_modconv_tc3_supported(int I, int O, int H, int W, int k, int pad);
 int sg3_modconv_fwd_tc_f16(const void* x, const void* wmod, void* y, int N, int I, int O, int H, int W, int k, int pad, int ldw, cudaStream_t stream);
+int sg3_modconv_fwd_tc_x3(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
+                          cudaStream_t stream);
 int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
                        cudaStream_t stream);
 
@@ -85,6 +88,24 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
         const size_t dstStep = transpose == 1 ? (size_t)ldw : 1;
         const size_t tapStep = (size_t)O * ldw;
         __half* dstH = reinterpret_cast<__half*>(wmod) + ((size_t)n * O + o) * ldw;       // fp16 operand form (layout 0 only)
+        if (roundTf32 == 3) {
+            // 3xTF32 operand form (layout 0 only): [N][2][O][ldw], plane 0 = TF32 head, plane 1 = TF32 tail of the residual
+            float* hi = wmod + ((size_t)(2 * n) * O + o) * ldw;
+            float* lo = hi + (size_t)O * ldw;
+            for (int q = cnt + threadIdx.x; q < ldw; q += blockDim.x) { hi[q] = 0.f; lo[q] = 0.f; }
+            for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
+                const int i = q / kk;
+                float v = (wo[q] * rw) * (sn[i] * rs);
+                if (demodulate) v *= d;
+                if (gainMode == 1) v *= gain[0];
+                else if (gainMode == 2) v *= gain[i];
+                else if (gainMode == 3) v *= gain[(size_t)n * I + i];
+                const float h = round_tf32(v);
+                hi[q] = h;
+                lo[q] = round_tf32(v - h);
+            }
+            continue;
+        }
         if (transpose == 0 && roundTf32 != 2)
             for (int q = cnt + threadIdx.x; q < ldw; q += blockDim.x) dst[q] = 0.f;   // row padding (TMA pitch)
         if (roundTf32 == 2)
@@ -276,8 +297,8 @@ SG3_EXPORT int sg3_modconv_weights(const float* w, const float* s, const float* 
                                    int N, int I, int O, int k, int ldw, int demodulate, int round_tf32_flag, int transpose, void* stream)
 {
     if (!w || !s || !wmod || !scratch || N < 1 || I < 1 || O < 1 || k < 1) return SG3_E_INVALID;
-    if (transpose < 0 || transpose > 2 || round_tf32_flag < 0 || round_tf32_flag > 2) return SG3_E_INVALID;
-    if (round_tf32_flag == 2 && transpose != 0) return SG3_E_INVALID;
+    if (transpose < 0 || transpose > 2 || round_tf32_flag < 0 || round_tf32_flag > 3) return SG3_E_INVALID;
+    if (round_tf32_flag >= 2 && transpose != 0) return SG3_E_INVALID;
     if (transpose == 1 ? (k != 1 || ldw < O) : transpose == 2 ? (ldw < I) : (ldw < I * k * k)) return SG3_E_INVALID;
     if (gainMode < 0 || gainMode > 3 || (gainMode && !input_gain)) return SG3_E_INVALID;
     if ((int64_t)N * I > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
@@ -293,9 +314,17 @@ SG3_EXPORT int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
                                int N, int I, int O, int H, int W, int k, int pad, int ldw,
                                int mathMode, int dtype, void* stream)
 {
+    return sg3_modconv_fwd_pitched(x, wmod, y, N, I, O, H, W, k, pad, ldw, 0, mathMode, dtype, stream);
+}
+
+SG3_EXPORT int sg3_modconv_fwd_pitched(const void* x, const float* wmod, void* y,
+                                       int N, int I, int O, int H, int W, int k, int pad, int ldw, int yPitch,
+                                       int mathMode, int dtype, void* stream)
+{
     if (!x || !wmod || !y || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || k < 1 || pad < 0) return SG3_E_INVALID;
     const bool tapMajor = mathMode == 1 && k > 1;             // the tensor-core kernels for k > 1 read tap-major weights
     if (ldw < (tapMajor ? I : I * k * k)) return SG3_E_INVALID;
+    if (dtype == SG3_F16 && yPitch != 0) return SG3_E_NOKERNEL;
     if (dtype == SG3_F16)        // fp16 activations and fp16 weights (prologue format 2): tensor cores only, 1x1 kernels
         return mathMode == 1 ? sg3_modconv_fwd_tc_f16(x, wmod, y, N, I, O, H, W, k, pad, ldw, (cudaStream_t)stream) : SG3_E_NOKERNEL;
     if (dtype != SG3_F32) return SG3_E_NOKERNEL;
@@ -303,7 +332,10 @@ SG3_EXPORT int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
     if (OH < 1 || OW < 1) return SG3_E_INVALID;
     if ((int64_t)OH * OW > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
     cudaStream_t st = (cudaStream_t)stream;
-    if (mathMode == 1 && k == 3) return sg3_modconv_fwd_tc3((const float*)x, wmod, (float*)y, N, I, O, H, W, pad, ldw, st);
+    if (mathMode == 2)          // 3xTF32: 1x1 kernels (the 3x3 tensor-core kernel has no split variant yet)
+        return k == 1 ? sg3_modconv_fwd_tc_x3((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, ldw, st) : SG3_E_NOKERNEL;
+    if (mathMode == 1 && k == 3) return sg3_modconv_fwd_tc3((const float*)x, wmod, (float*)y, N, I, O, H, W, pad, ldw, yPitch, st);
+    if (yPitch != 0 && yPitch != OW) return SG3_E_NOKERNEL;      // only the 3x3 tensor-core kernel writes a padded row pitch
     if (mathMode == 1) return sg3_modconv_fwd_tc((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, ldw, st);
     if (mathMode != 0) return SG3_E_INVALID;
     const int P = OH * OW;

@@ -17,6 +17,12 @@
 // warp 5 TMEM allocator + MMA issuer.  Persistent: one CTA per SM loops over tiles; the TMA ring runs ahead across
 // tiles and the accumulator is double-buffered in TMEM, so loads, MMAs and the epilogue of consecutive tiles overlap.
 // Every mbarrier wait is bounded (trap instead of hang).
+//
+// X3 (3xTF32, "fp32x3" math): fp32-accurate contraction on the tensor cores.  Both operands are split into a TF32 head and
+// a TF32 tail, W = Wh + Wl (the weight prologue writes the two planes), X = Xh + Xl with Xh = what the tensor core reads of an
+// fp32 word (its top 19 bits) and Xl = X - Xh computed by four extra "splitter" warps from the landed TMA tile into a second
+// smem tile; each K step issues Xh*Wh + Xh*Wl + Xl*Wh (the dropped Xl*Wl term is 2^-22 relative).  The 1x1 convs of config R
+// are HBM-bound with the tensor pipe ~25 % busy, so the two extra MMAs per step mostly hide under the operand stream.
 #include <cuda.h>
 #include <mutex>
 #include <type_traits>
@@ -32,6 +38,7 @@ constexpr int BK = 32;             // input channels per stage (one 128-byte swi
 constexpr int kMaxStages = 6;
 constexpr int A_STAGE_BYTES = BM * BK * 4;      // 16 KB: 4 boxes of [32 rows][128 B]
 constexpr int kThreads = 192;
+constexpr int kThreadsX3 = 320;   // + four splitter warps
 
 struct TcParams {
     void* y;               // float (HALF = false) or __half (HALF = true)
@@ -51,23 +58,36 @@ struct TcParams {
 // HALF: fp16 activations / weights / output with kind::f16 MMAs.  Same stage bytes (a stage is 64 input channels of
 // 2 bytes instead of 32 of 4): A = X^T is MN-major in the standard SWIZZLE_128B form (two TMA boxes [64 k][64 px] per
 // stage, 8-k atoms 1024 B apart, 64-pixel blocks one box apart), B = Wn K-major as before; K = 16 per instruction.
-template <bool HALF>
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ float tf32_rna(float v)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+template <bool HALF, bool X3>
+__global__ void __launch_bounds__(X3 ? kThreadsX3 : kThreads, 1)
 modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const TcParams p)
 {
+    static_assert(!(HALF && X3), "the operand split is an fp32 mode");
     constexpr int KST = HALF ? 64 : 32;            // input channels per stage
     extern __shared__ __align__(1024) unsigned char smem[];
-    __shared__ __align__(8) uint64_t barFull[kMaxStages], barEmpty[kMaxStages], barAccFull[2], barAccEmpty[2];
+    __shared__ __align__(8) uint64_t barFull[kMaxStages], barEmpty[kMaxStages], barSplit[kMaxStages], barAccFull[2], barAccEmpty[2];
     __shared__ uint32_t tmemBase;
 
     // warp index through a shuffle: the role dispatch is then provably warp-uniform and the producer / MMA loops run on the
     // uniform datapath (see tc_common.cuh, "warp-uniform issue")
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const int stageBytes = A_STAGE_BYTES + p.BN * BK * 4;
+    // stage layout: A (X^T tile) [| A tail (X3)] | B (W tile) [| B tail (X3)]
+    constexpr int A_BYTES = X3 ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
+    const int bBytes = p.BN * BK * 4;
+    const int stageBytes = A_BYTES + (X3 ? 2 : 1) * bBytes;
     const uint32_t tiles = (smem_u32(smem) + 1023u) & ~1023u;        // SWIZZLE_128B operands need 1024-byte aligned tiles
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kMaxStages; s++) { mbar_init(smem_u32(&barFull[s]), 1); mbar_init(smem_u32(&barEmpty[s]), 1); }
+        for (int s = 0; s < kMaxStages; s++) {
+            mbar_init(smem_u32(&barFull[s]), 1); mbar_init(smem_u32(&barEmpty[s]), 1); mbar_init(smem_u32(&barSplit[s]), 4);
+        }
         for (int a = 0; a < 2; a++) { mbar_init(smem_u32(&barAccFull[a]), 1); mbar_init(smem_u32(&barAccEmpty[a]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -101,7 +121,7 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 const uint32_t s = it % p.stages, round = it / p.stages;
                 if (round > 0) mbar_wait(smem_u32(&barEmpty[s]), (round - 1) & 1);
                 const uint32_t full = smem_u32(&barFull[s]);
-                mbar_expect_tx_elect(full, (uint32_t)stageBytes);
+                mbar_expect_tx_elect(full, (uint32_t)(A_STAGE_BYTES + (X3 ? 2 : 1) * bBytes));
                 const uint32_t aDst = tiles + s * stageBytes;
                 if (HALF) {
 #pragma unroll
@@ -110,7 +130,40 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
                     for (int j = 0; j < 4; j++) tma_load_3d_elect(aDst + j * (BK * 128), &mapX, full, p0 + 32 * j, kt * BK, n);
                 }
-                tma_load_3d_elect(aDst + A_STAGE_BYTES, &mapW, full, kt * KST, o0, n);
+                if (X3) {       // weight planes [N][2][O][ldw]: head and tail
+                    tma_load_3d_elect(aDst + A_BYTES, &mapW, full, kt * KST, o0, 2 * n);
+                    tma_load_3d_elect(aDst + A_BYTES + bBytes, &mapW, full, kt * KST, o0, 2 * n + 1);
+                } else {
+                    tma_load_3d_elect(aDst + A_BYTES, &mapW, full, kt * KST, o0, n);
+                }
+            }
+        }
+    } else if (X3 && warp >= 6) {
+        // ---------------- splitter (X3): Xl = X - (top 19 bits of X), elementwise on the landed tile (swizzle-agnostic) ------
+        unsigned char* gen = smem + (tiles - smem_u32(smem));
+        const int tid = (int)threadIdx.x - 192;                   // 0 .. 127
+        uint32_t it = 0;
+        for (long long t = blockIdx.x; t < p.totalTiles; t += gridDim.x) {
+            for (int kt = 0; kt < p.kTiles; kt++, it++) {
+                const uint32_t s = it % p.stages;
+                mbar_wait(smem_u32(&barFull[s]), (it / p.stages) & 1);
+                const float4* a = (const float4*)(gen + (size_t)s * stageBytes);
+                float4* lo = (float4*)(gen + (size_t)s * stageBytes + A_STAGE_BYTES);
+#pragma unroll
+                for (int e = 0; e < A_STAGE_BYTES / 16 / 128; e++) {
+                    const float4 v = a[tid + 128 * e];
+                    // the residual is exact in fp32; it is then ROUNDED to TF32 here (the tensor core would truncate it, a bias
+                    // that grows linearly with the number of input channels)
+                    float4 r;
+                    r.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u));
+                    r.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u));
+                    r.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u));
+                    r.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u));
+                    lo[tid + 128 * e] = r;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&barSplit[s]));
             }
         }
     } else if (warp == 5) {
@@ -124,7 +177,7 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         // A (fp16, MN-major): 16 k-rows per step = two 8-row atoms 1024 B apart (SBO), 64-pixel blocks KST*128 B apart (LBO)
         const uint64_t dA = HALF ? umma_desc(tiles, KST * 128, 1024)
                                  : umma_desc(tiles, BK * 128, 512, kLayoutSw128Base32);
-        const uint64_t dB = umma_desc(tiles + A_STAGE_BYTES, 16, 1024);
+        const uint64_t dB = umma_desc(tiles + A_BYTES, 16, 1024);
         const uint32_t aLo0 = (uint32_t)dA, aHi = (uint32_t)(dA >> 32), bLo0 = (uint32_t)dB, bHi = (uint32_t)(dB >> 32);
         const uint32_t stageStep = (uint32_t)stageBytes >> 4;
         uint32_t it = 0, tc = 0;                                  // k-iterations / tiles consumed so far
@@ -136,9 +189,15 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             for (int kt = 0; kt < p.kTiles; kt++, it++) {
                 const uint32_t s = it % p.stages;
                 mbar_wait(smem_u32(&barFull[s]), (it / p.stages) & 1);
+                if (X3) mbar_wait(smem_u32(&barSplit[s]), (it / p.stages) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (HALF) umma_f16_x4<128, 2>(acc, aLo0 + s * stageStep, aHi, bLo0 + s * stageStep, bHi, idesc, kt > 0 ? 1u : 0u);
                 else umma_tf32_x4<64, 2>(acc, aLo0 + s * stageStep, aHi, bLo0 + s * stageStep, bHi, idesc, kt > 0 ? 1u : 0u);
+                if (X3) {
+                    // + Xh * Wl + Xl * Wh  (descriptor start fields in 16-byte units)
+                    umma_tf32_x4<64, 2>(acc, aLo0 + s * stageStep, aHi, bLo0 + s * stageStep + ((uint32_t)bBytes >> 4), bHi, idesc, 1u);
+                    umma_tf32_x4<64, 2>(acc, aLo0 + s * stageStep + (A_STAGE_BYTES >> 4), aHi, bLo0 + s * stageStep, bHi, idesc, 1u);
+                }
                 umma_commit_elect(smem_u32(&barEmpty[s]));        // frees the smem stage when these MMAs retire
             }
             umma_commit_elect(smem_u32(&barAccFull[as]));         // accumulator of this tile complete
@@ -331,7 +390,7 @@ bool make_map3(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint6
 namespace {
 
 // x [N][I][P], wmod [N][O][ldw] (zero beyond I), y [N][O][P]; k must be 1.  HALF: all three are fp16.
-template <bool HALF>
+template <bool HALF, bool X3>
 int launch_fwd_tc(const void* x, const void* wmod, void* y, int N, int I, int O, int H, int W, int k, int pad, int ldw, cudaStream_t stream)
 {
     if (k != 1 || pad != 0) return SG3_E_NOKERNEL;
@@ -344,7 +403,8 @@ int launch_fwd_tc(const void* x, const void* wmod, void* y, int N, int I, int O,
     TcParams p;
     p.y = y; p.N = N; p.I = I; p.O = O; p.P = (int)P;
     // out-channel tile: split O evenly into the fewest tiles of <= 256, rounded up to the UMMA N granule (16)
-    const int nt = (O + 255) / 256;
+    constexpr int kMaxBN = X3 ? 128 : 256;                  // X3 stages hold two A tiles and two B tiles: 64 KB at BN = 128
+    const int nt = (O + kMaxBN - 1) / kMaxBN;
     int bn = ((O + nt - 1) / nt + 15) & ~15;
     if (bn < 16) bn = 16;
     p.BN = bn;
@@ -368,21 +428,21 @@ int launch_fwd_tc(const void* x, const void* wmod, void* y, int N, int I, int O,
             return SG3_E_NOKERNEL;
     }
     {
-        const uint64_t dims[3] = {(uint64_t)ldw, (uint64_t)O, (uint64_t)N};
+        // X3: the weight tensor is [N][2][O][ldw] (TF32 head and tail planes): third dimension 2N
+        const uint64_t dims[3] = {(uint64_t)ldw, (uint64_t)O, (uint64_t)(X3 ? 2 * N : N)};
         const uint64_t strides[2] = {(uint64_t)ldw * esz, (uint64_t)ldw * O * esz};
         const uint32_t box[3] = {(uint32_t)kst, (uint32_t)bn, 1};
         if (!sg3_make_tensor_map(&mapW, dt, 3, wmod, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return SG3_E_NOKERNEL;
     }
-    p.stages = bn > 128 ? 4 : 6;                            // 4 x 48 KB or 6 x <= 32 KB of operand stages
-    const int smemBytes = p.stages * (A_STAGE_BYTES + bn * BK * 4) + 1024;
+    // operand stages: 4 x 48 KB or 6 x <= 32 KB; X3: 3 x <= 64 KB
+    p.stages = X3 ? 3 : (bn > 128 ? 4 : 6);
+    const int smemBytes = p.stages * ((X3 ? 2 : 1) * (A_STAGE_BYTES + bn * BK * 4)) + 1024;
     static Sg3DeviceOnce once;
     const cudaError_t attrErr = once.run([] {
-        cudaError_t e = cudaFuncSetAttribute(modconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(modconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        return e;
+        return cudaFuncSetAttribute(modconv_tc_kernel<HALF, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     });
     if (attrErr != cudaSuccess) return (int)attrErr;
-    modconv_tc_kernel<HALF><<<(unsigned)ctas, kThreads, smemBytes, stream>>>(mapX, mapW, p);
+    modconv_tc_kernel<HALF, X3><<<(unsigned)ctas, X3 ? kThreadsX3 : kThreads, smemBytes, stream>>>(mapX, mapW, p);
     return sg3_launch_status();
 }
 
@@ -391,13 +451,20 @@ int launch_fwd_tc(const void* x, const void* wmod, void* y, int N, int I, int O,
 int sg3_modconv_fwd_tc(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
                        cudaStream_t stream)
 {
-    return launch_fwd_tc<false>(x, wmod, y, N, I, O, H, W, k, pad, ldw, stream);
+    return launch_fwd_tc<false, false>(x, wmod, y, N, I, O, H, W, k, pad, ldw, stream);
+}
+
+// 3xTF32: wmod is [N][2][O][ldw] (sg3_modconv_weights with round_tf32 = 3)
+int sg3_modconv_fwd_tc_x3(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
+                          cudaStream_t stream)
+{
+    return launch_fwd_tc<false, true>(x, wmod, y, N, I, O, H, W, k, pad, ldw, stream);
 }
 
 int sg3_modconv_fwd_tc_f16(const void* x, const void* wmod, void* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
                            cudaStream_t stream)
 {
-    return launch_fwd_tc<true>(x, wmod, y, N, I, O, H, W, k, pad, ldw, stream);
+    return launch_fwd_tc<true, false>(x, wmod, y, N, I, O, H, W, k, pad, ldw, stream);
 }
 
 // dy [N][O][P], x [N][I][P], dw [N][O][ldw] (zeroed by the caller; ldw >= I).

@@ -43,6 +43,7 @@ constexpr int kAccPitchAlign = 32;      // accumulator pitch granularity in TMEM
 struct Tc3Params {
     float* y;
     int N, I, O, H, W, OH, OW, pad;
+    int yPitch;                // floats between output rows (>= OW): a 16-byte multiple lets the stencil that follows use TMA
     int NPX, R, CW;            // pixels per MMA (multiple of 32), output rows per tile, accumulator pitch (>= NPX + 4)
     int S;                     // valid output columns per tile = NPX - 4
     int xoff, colBase;         // box start = tileX * S - xoff;  output ox = tileX * S + (col - colBase)
@@ -187,7 +188,7 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             const bool mine = (p.m64 ? 16 * warp : 32 * warp) < nrows;
             float* st = stage + laneRow * STAGE_PITCH;
             const int colEnd = p.colBase + p.S;
-            const size_t chStep = (size_t)p.OH * p.OW;
+            const size_t chStep = (size_t)p.OH * p.yPitch;
             for (int oyl = 0; oyl < p.R; oyl++) {
                 const int oy = oy0 + oyl;
                 if (oy >= p.OH) break;
@@ -212,7 +213,7 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                     const int col = c0 + lane;
                     const int ox = tx * p.S + col - p.colBase;
                     if (col >= p.colBase && col < colEnd && ox < p.OW) {
-                        float* yp = p.y + (((size_t)n * p.O + o0 + warp) * p.OH + oy) * (size_t)p.OW + ox;
+                        float* yp = p.y + (((size_t)n * p.O + o0 + warp) * p.OH + oy) * (size_t)p.yPitch + ox;
                         const float* sp = stage + warp * STAGE_PITCH + lane;
                         for (int r = warp; r < nrows; r += 4) {
                             *yp = *sp;
@@ -293,8 +294,8 @@ int sg3_modconv_tc3_supported(int I, int O, int H, int W, int k, int pad)
     return 0;
 }
 
-// x [N][I][H][W]; wtap [N][9][O][ldw] (tap = ky * 3 + kx, i contiguous, ldw % 4 == 0, ldw >= I); y [N][O][OH][OW].
-int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw,
+// x [N][I][H][W]; wtap [N][9][O][ldw] (tap = ky * 3 + kx, i contiguous, ldw % 4 == 0, ldw >= I); y [N][O][OH][yPitch >= OW].
+int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw, int yPitch,
                         cudaStream_t stream)
 {
     if (sg3_modconv_tc3_supported(I, O, H, W, 3, pad) != 0) return SG3_E_NOKERNEL;
@@ -303,6 +304,8 @@ int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int 
     Tc3Params p;
     p.y = y; p.N = N; p.I = I; p.O = O; p.H = H; p.W = W; p.pad = pad;
     p.OH = H + 2 * pad - 2; p.OW = W + 2 * pad - 2;
+    p.yPitch = yPitch > 0 ? yPitch : p.OW;
+    if (p.yPitch < p.OW) return SG3_E_INVALID;
     p.kChunks = (I + BK3 - 1) / BK3;
     p.xoff = pad == 2 ? 4 : 0;
     p.colBase = pad == 2 ? 4 : 2;

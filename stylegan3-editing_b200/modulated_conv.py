@@ -4,8 +4,10 @@ Mirror of `modulated_conv2d()` in `models/stylegan3/networks_stylegan3.py:24-63`
 and semantics).  The reference materialises [N,O,I,k,k] weights with ~10 eager kernels and calls a
 cuDNN grouped convolution; here the weight chain is one fused prologue kernel
 (`sg3_modconv_weights`) and the contraction is `sg3_modconv_fwd`:
-  math='fp32'  exact FP32 SIMT contraction (parity mode, <= 1e-5 of the reference's fp32 result)
-  math='tf32'  TF32 tcgen05/TMEM implicit GEMM (the reference's default cuDNN path also allows TF32)
+  math='fp32'    exact FP32 SIMT contraction (parity mode, <= 1e-5 of the reference's fp32 result)
+  math='tf32'    TF32 tcgen05/TMEM implicit GEMM (the reference's default cuDNN path also allows TF32)
+  math='fp32x3'  3xTF32 on the tensor cores: both operands split into a TF32 head and tail, three MMAs per K step --
+                 fp32-accurate (~1e-6) at tensor-core speed; 1x1 kernels (config R), other shapes run 'fp32' 
 The default follows `torch.backends.cudnn.allow_tf32`, like the reference's F.conv2d call.
 """
 import torch
@@ -13,12 +15,13 @@ import torch
 from . import capi
 
 _default_math = None      # None -> follow torch.backends.cudnn.allow_tf32
+_pitched_output = True    # 3x3 tensor-core convs write a 16-byte row pitch (see conv_forward); False: contiguous outputs
 
 
 def set_math(mode):
     """Force 'fp32' / 'tf32' for all modulated_conv2d calls, or None to follow cudnn.allow_tf32."""
     global _default_math
-    assert mode in (None, 'fp32', 'tf32')
+    assert mode in (None, 'fp32', 'tf32', 'fp32x3')
     _default_math = mode
 
 
@@ -28,11 +31,13 @@ def _math_mode():
     return 'tf32' if torch.backends.cudnn.allow_tf32 else 'fp32'
 
 
-def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, transpose=False, tap_major=False, half=False):
+def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, transpose=False, tap_major=False, half=False,
+                    split=False):
     """[N, O, ldw >= I*k*k] float32 modulated (+demodulated, +input-gain) weights, rows zero padded  (:39-56).
     transpose=True (1x1 only): [N, I, ldw >= O], the weight operand of the input-gradient GEMM.
     tap_major=True: [N, k*k, O, ldw >= I], the operand of the 3x3 tensor-core kernel.
-    half=True: float16 [N, O, ldw] (what `w.to(x.dtype)` of :61 produces for fp16 layers), operand of the fp16 tensor-core kernel."""
+    half=True: float16 [N, O, ldw] (what `w.to(x.dtype)` of :61 produces for fp16 layers), operand of the fp16 tensor-core kernel.
+    split=True: [N, 2, O, ldw], TF32 head and TF32 tail of every weight, operand of the 3xTF32 kernel (math='fp32x3')."""
     capi.require_cuda(w, 'modulated_conv2d')
     O, I, kh, kw = w.shape
     assert kh == kw
@@ -49,7 +54,11 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, tr
         else:
             mode, g = 3, g.expand(N, I).contiguous()               # per (sample, input channel), broadcast like :55
     layout = 1 if transpose else (2 if tap_major else 0)
-    if half:
+    if split:
+        assert not transpose and not tap_major and not half
+        ldw = (I * kh * kw + 31) // 32 * 32
+        wmod = torch.empty([N, 2, O, ldw], dtype=torch.float32, device=w.device)
+    elif half:
         assert not transpose and not tap_major
         ldw = (I * kh * kw + 63) // 64 * 64
         wmod = torch.empty([N, O, ldw], dtype=torch.float16, device=w.device)
@@ -68,20 +77,27 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, tr
     with torch.cuda.device(w.device):
         rc = capi.lib().sg3_modconv_weights(w.data_ptr(), s.data_ptr(), g.data_ptr() if g is not None else None, mode,
                                             wmod.data_ptr(), scratch.data_ptr(), N, I, O, kh, ldw, int(bool(demodulate)),
-                                            2 if half else int(bool(round_tf32)), layout, capi.stream_ptr(w.device))
+                                            3 if split else (2 if half else int(bool(round_tf32))), layout, capi.stream_ptr(w.device))
     capi.check(rc, 'sg3_modconv_weights')
     return wmod
 
 
 def conv_forward(x, wmod, O, k, padding, math):
-    """y[n,o] = sum_i wmod[n,o,i] (*) x[n,i] with zero padding; x float32 (or float16 with float16 weights) contiguous."""
+    """y[n,o] = sum_i wmod[n,o,i] (*) x[n,i] with zero padding; x float32 (or float16 with float16 weights) contiguous.
+
+    The 3x3 tensor-core kernel writes its output with a row pitch rounded up to 16 bytes (returned as a [N, O, OH, OW] view of a
+    [N, O, OH, pitch] buffer): the filtered_lrelu that consumes it can then stage its input by TMA although OW * 4 is not a
+    16-byte multiple (all 3x3 layers of config T)."""
     N, I, H, W = x.shape
     OH, OW = H + 2 * padding - k + 1, W + 2 * padding - k + 1
-    y = torch.empty([N, O, OH, OW], dtype=x.dtype, device=x.device)
+    pitch = (OW + 3) // 4 * 4 if (math == 'tf32' and k == 3 and x.dtype == torch.float32 and _pitched_output) else OW
+    ybuf = torch.empty([N, O, OH, pitch], dtype=x.dtype, device=x.device)
+    y = ybuf if pitch == OW else ybuf[..., :OW]
     with torch.cuda.device(x.device):
         ldw = wmod.shape[-1]
-        rc = capi.lib().sg3_modconv_fwd(x.data_ptr(), wmod.data_ptr(), y.data_ptr(), N, I, O, H, W, k, padding, ldw,
-                                        1 if math == 'tf32' else 0, capi.dtype_code(x.dtype), capi.stream_ptr(x.device))
+        rc = capi.lib().sg3_modconv_fwd_pitched(x.data_ptr(), wmod.data_ptr(), ybuf.data_ptr(), N, I, O, H, W, k, padding, ldw,
+                                                0 if pitch == OW else pitch, {'fp32': 0, 'tf32': 1, 'fp32x3': 2}[math],
+                                                capi.dtype_code(x.dtype), capi.stream_ptr(x.device))
     if rc == capi.SG3_E_NOKERNEL:
         return None             # e.g. a base pointer off the 16-byte TMA alignment: the caller reruns the SIMT contraction
     capi.check(rc, 'sg3_modconv_fwd')
@@ -131,12 +147,14 @@ class _ModConv(torch.autograd.Function):
                 return y
             math = 'fp32'                  # no fp16 tensor-core launch for this tensor (alignment): upcast + SIMT below
         x32 = xin if xin.dtype == torch.float32 else xin.float()
-        if math == 'tf32' and not tc_supported(I, O, x32.shape[2], x32.shape[3], k, padding):
+        if math == 'fp32x3' and (k != 1 or xin.dtype != torch.float32):
+            math = 'fp32'                  # the operand-split kernel exists for fp32 1x1 convs
+        if math in ('tf32', 'fp32x3') and not tc_supported(I, O, x32.shape[2], x32.shape[3], k, padding):
             math = 'fp32'                  # shapes without a tensor-core kernel run the exact SIMT contraction
         wmod = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, round_tf32=(math == 'tf32'),
-                               tap_major=(math == 'tf32' and k > 1))
+                               tap_major=(math == 'tf32' and k > 1), split=(math == 'fp32x3'))
         y = conv_forward(x32, wmod, O, k, padding, math)
-        if y is None and math == 'tf32':
+        if y is None and math in ('tf32', 'fp32x3'):
             # the shape has a tensor-core kernel but this tensor does not (unaligned view, tensor-map encode failure):
             # rebuild the weights in the plain fp32 layout and run the exact SIMT contraction
             math = 'fp32'

@@ -462,3 +462,45 @@ def test_modconv_weights_backward_kernel(pkg, demod):
         dw, ds = pkg.modulated_conv._weights_backward(dWn, w, s, gain, demod, ldw)
         assert rel_err(dw.cpu().numpy(), dw_ref.reshape(O, I).cpu().numpy()) < 2e-5
         assert rel_err(ds.cpu().numpy(), ds_ref.cpu().numpy()) < 2e-5
+
+
+@pytest.mark.parametrize('case', golden('modconv.npz').cases('modconv'))
+def test_modulated_conv2d_fp32x3_golden(pkg, case):
+    """3xTF32 contraction (math='fp32x3'): tensor cores with both operands split into TF32 head + tail -- must hold the fp32
+    parity tolerance (2e-5), not the TF32 one.  3x3 cases run the exact SIMT kernel under this mode."""
+    c = golden('modconv.npz').case('modconv', case)
+    k = c['w'].shape[-1]
+    g = cu(c['input_gain']) if 'input_gain' in c else None
+    y = pkg.modulated_conv.modulated_conv2d(cu(c['x']), cu(c['w']), cu(c['s']), demodulate=bool(c['demodulate']), padding=k - 1,
+                                            input_gain=g, math='fp32x3')
+    assert rel_err(y.cpu().numpy(), c['y']) < 2e-5
+
+
+def test_fp32x3_layer_shapes_vs_oracle(pkg):
+    """The operand-split kernel at awkward shapes (ragged I / O / P, several N tiles) against the oracle, and that it really is
+    the tensor-core launch (launch counter of the library: weights prologue 2 + contraction 1)."""
+    from oracle import sg3_oracle as orc
+    rng = np.random.RandomState(17)
+    for (N, I, O, H) in ((2, 96, 300, 20), (1, 161, 102, 36), (3, 33, 17, 12), (1, 1024, 645, 16)):
+        x = rng.randn(N, I, H, H).astype(np.float32) * 3
+        w = rng.randn(O, I, 1, 1).astype(np.float32)
+        s = (rng.randn(N, I) + 1).astype(np.float32)
+        ref = orc.modulated_conv2d(x, w, s)
+        n0 = pkg.capi.lib().sg3_launch_count()
+        y = pkg.modulated_conv.modulated_conv2d(cu(x), cu(w), cu(s), math='fp32x3')
+        assert pkg.capi.lib().sg3_launch_count() - n0 == 3
+        assert rel_err(y.cpu().numpy(), ref) < 1e-5, (N, I, O, H)           # fp32 parity tolerance of this suite: 2e-5
+        ytf = pkg.modulated_conv.modulated_conv2d(cu(x), cu(w), cu(s), math='tf32')
+        assert rel_err(ytf.cpu().numpy(), ref) > rel_err(y.cpu().numpy(), ref)
+
+
+def test_tiny_generator_fp32x3(pkg):
+    """Whole tiny R generator with the 3xTF32 convs: the fp32 network tolerance (1e-4), where TF32 needs 1e-2."""
+    G, g = _build(pkg, 'tinyR')
+    ws = cu(g.z['tinyR/ws'])
+    pkg.modulated_conv.set_math('fp32x3')
+    try:
+        img = G.synthesis(ws, noise_mode='const', force_fp32=True)
+    finally:
+        pkg.modulated_conv.set_math(None)
+    assert rel_err(img.cpu().numpy(), g.z['tinyR/img']) < 1e-4
