@@ -44,12 +44,12 @@ class _FlreluTimer:
         self.mod, self.orig, self.on, self.events = fl_mod, fl_mod._fused, False, []
         fl_mod._fused = self._call
 
-    def _call(self, x, fu, fd, b, si, sx, sy, cfg, write_signs, ysum=None):
+    def _call(self, x, fu, fd, b, si, sx, sy, cfg, write_signs, **kw):
         if not self.on:
-            return self.orig(x, fu, fd, b, si, sx, sy, cfg, write_signs, ysum=ysum)
+            return self.orig(x, fu, fd, b, si, sx, sy, cfg, write_signs, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res = self.orig(x, fu, fd, b, si, sx, sy, cfg, write_signs, ysum=ysum)
+        res = self.orig(x, fu, fd, b, si, sx, sy, cfg, write_signs, **kw)
         e1.record()
         if res is not None:
             y, so = res

@@ -169,7 +169,9 @@ int sg3_modconv_weights(const float* w, const float* s, const float* input_gain,
 /* Weight layouts (`transpose` argument): 0 = [N][O][ldw >= I*k*k] (index i*k*k + tap), read by mathMode 0 and by the
  * 1x1 tensor-core kernel;  1 (1x1 kernels) = transposed [N][I][ldw >= O], the weight operand of the input-gradient GEMM
  * dX = sg3_modconv_fwd(dY, wmodT, ...) with the roles of I and O swapped;  2 = tap-major [N][k*k][O][ldw >= I]
- * (tap = ky*k + kx, i contiguous), the operand sg3_modconv_fwd reads when mathMode = 1 and k > 1.
+ * (tap = ky*k + kx, i contiguous), the operand sg3_modconv_fwd reads when mathMode = 1 and k > 1;  3 = the same with flipped taps
+ * and transposed channels, [N][k*k][I][ldw >= O] with wmod[n][k*k-1-tap][i][o] = W[n][o][i][tap] (buffer zeroed by the caller):
+ * the weight operand of the k x k input-gradient conv (roles of I and O swapped).
  *
  * sg3_modconv_tc_supported: 0 if sg3_modconv_fwd(mathMode = 1) has a tensor-core kernel for this shape
  * (k = 1: pad 0, H*W % 4 == 0;  k = 3: pad 0 or 2, W % 4 == 0), SG3_E_NOKERNEL otherwise -- ask before choosing the
@@ -191,12 +193,14 @@ int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
                     int N, int I, int O, int H, int W, int k, int pad, int ldw,
                     int mathMode, int dtype, void* stream);
 
-/* Same contraction, output rows `yPitch` floats apart (y is [N][O][OH][yPitch >= OW]; 0 = contiguous).  First step of the
- * conv -> filtered_lrelu fusion: with a 16-byte-multiple pitch the stencil that consumes y stages its input
- * by TMA even when OW * 4 is not a multiple of 16 (every 3x3 layer of config T: OW = 38 ... 1046).  Implemented by the 3x3
- * tensor-core kernel (mathMode 1, k = 3); other paths answer SG3_E_NOKERNEL unless yPitch is 0 or OW. */
+/* Same contraction with padded row pitches: x is [N][I][H][xPitch >= W], y is [N][O][OH][yPitch >= OW] (0 = contiguous).
+ * yPitch: first step of the conv -> filtered_lrelu fusion: with a 16-byte-multiple pitch the stencil that
+ * consumes y stages its input by TMA even when OW * 4 is not a multiple of 16 (every 3x3 layer of config T: OW = 38 ... 1046).
+ * xPitch: lets the same kernel compute the 3x3 INPUT GRADIENT from a dy whose width is not a multiple of 4 (dy comes out of the
+ * filtered_lrelu backward kernel with a padded pitch): dX = sg3_modconv_fwd_pitched(dY, wmod in layout 3, pad' = 2 - pad).
+ * Implemented by the 3x3 tensor-core kernel (mathMode 1, k = 3); other paths answer SG3_E_NOKERNEL for real pitches. */
 int sg3_modconv_fwd_pitched(const void* x, const float* wmod, void* y,
-                            int N, int I, int O, int H, int W, int k, int pad, int ldw, int yPitch,
+                            int N, int I, int O, int H, int W, int k, int pad, int ldw, int xPitch, int yPitch,
                             int mathMode, int dtype, void* stream);
 
 #ifdef __cplusplus

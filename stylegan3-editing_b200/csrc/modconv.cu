@@ -9,8 +9,8 @@
 #include "common.cuh"
 
 int sg3_modconv_wgrad_tc(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, cudaStream_t stream);
-int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw, int yPitch,
-                        cudaStream_t stream);
+int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw,
+                        int xPitch, int yPitch, cudaStream_t stream);
 int sg3_modconv_tc3_supported(int I, int O, int H, int W, int k, int pad);
 int sg3_modconv_fwd_tc_f16(const void* x, const void* wmod, void* y, int N, int I, int O, int H, int W, int k, int pad, int ldw, cudaStream_t stream);
 int sg3_modconv_fwd_tc_x3(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
@@ -82,8 +82,11 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
         }
         // layout 1 (1x1 kernels only): transposed, wmod is [N][I][ldw >= O], the operand of the dgrad GEMM
         // layout 2: tap-major, wmod is [N][kk][O][ldw >= I], the operand of the 3x3 tensor-core kernel
+        // layout 3: tap-major with flipped taps and transposed channels, wmod is [N][kk][I][ldw >= O] with
+        //           wmod[n][kk-1-tap][i][o] = W[n][o][i][tap] -- the operand of the 3x3 INPUT-GRADIENT conv (same kernel, roles of I / O swapped)
         float* dst = transpose == 1 ? wmod + (size_t)n * I * ldw + o
                    : transpose == 2 ? wmod + ((size_t)n * kk * O + o) * ldw
+                   : transpose == 3 ? wmod + (size_t)n * kk * I * ldw + o
                                     : wmod + ((size_t)n * O + o) * ldw;
         const size_t dstStep = transpose == 1 ? (size_t)ldw : 1;
         const size_t tapStep = (size_t)O * ldw;
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
             if (roundTf32 == 2) { dstH[q] = __float2half_rn(v); continue; }       // what the reference's w.to(x.dtype) does (:61)
             v = roundTf32 ? round_tf32(v) : v;
             if (transpose == 2) dst[(size_t)(q - i * kk) * tapStep + i] = v;
+            else if (transpose == 3) dst[((size_t)(kk - 1 - (q - i * kk)) * I + i) * ldw] = v;
             else dst[q * dstStep] = v;
         }
     }
@@ -297,9 +301,9 @@ SG3_EXPORT int sg3_modconv_weights(const float* w, const float* s, const float* 
                                    int N, int I, int O, int k, int ldw, int demodulate, int round_tf32_flag, int transpose, void* stream)
 {
     if (!w || !s || !wmod || !scratch || N < 1 || I < 1 || O < 1 || k < 1) return SG3_E_INVALID;
-    if (transpose < 0 || transpose > 2 || round_tf32_flag < 0 || round_tf32_flag > 3) return SG3_E_INVALID;
+    if (transpose < 0 || transpose > 3 || round_tf32_flag < 0 || round_tf32_flag > 3) return SG3_E_INVALID;
     if (round_tf32_flag >= 2 && transpose != 0) return SG3_E_INVALID;
-    if (transpose == 1 ? (k != 1 || ldw < O) : transpose == 2 ? (ldw < I) : (ldw < I * k * k)) return SG3_E_INVALID;
+    if (transpose == 1 ? (k != 1 || ldw < O) : transpose == 2 ? (ldw < I) : transpose == 3 ? (ldw < O) : (ldw < I * k * k)) return SG3_E_INVALID;
     if (gainMode < 0 || gainMode > 3 || (gainMode && !input_gain)) return SG3_E_INVALID;
     if ((int64_t)N * I > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -314,17 +318,17 @@ SG3_EXPORT int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
                                int N, int I, int O, int H, int W, int k, int pad, int ldw,
                                int mathMode, int dtype, void* stream)
 {
-    return sg3_modconv_fwd_pitched(x, wmod, y, N, I, O, H, W, k, pad, ldw, 0, mathMode, dtype, stream);
+    return sg3_modconv_fwd_pitched(x, wmod, y, N, I, O, H, W, k, pad, ldw, 0, 0, mathMode, dtype, stream);
 }
 
 SG3_EXPORT int sg3_modconv_fwd_pitched(const void* x, const float* wmod, void* y,
-                                       int N, int I, int O, int H, int W, int k, int pad, int ldw, int yPitch,
+                                       int N, int I, int O, int H, int W, int k, int pad, int ldw, int xPitch, int yPitch,
                                        int mathMode, int dtype, void* stream)
 {
     if (!x || !wmod || !y || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || k < 1 || pad < 0) return SG3_E_INVALID;
     const bool tapMajor = mathMode == 1 && k > 1;             // the tensor-core kernels for k > 1 read tap-major weights
     if (ldw < (tapMajor ? I : I * k * k)) return SG3_E_INVALID;
-    if (dtype == SG3_F16 && yPitch != 0) return SG3_E_NOKERNEL;
+    if (dtype == SG3_F16 && (yPitch != 0 || xPitch != 0)) return SG3_E_NOKERNEL;
     if (dtype == SG3_F16)        // fp16 activations and fp16 weights (prologue format 2): tensor cores only, 1x1 kernels
         return mathMode == 1 ? sg3_modconv_fwd_tc_f16(x, wmod, y, N, I, O, H, W, k, pad, ldw, (cudaStream_t)stream) : SG3_E_NOKERNEL;
     if (dtype != SG3_F32) return SG3_E_NOKERNEL;
@@ -334,8 +338,9 @@ SG3_EXPORT int sg3_modconv_fwd_pitched(const void* x, const float* wmod, void* y
     cudaStream_t st = (cudaStream_t)stream;
     if (mathMode == 2)          // 3xTF32: 1x1 kernels (the 3x3 tensor-core kernel has no split variant yet)
         return k == 1 ? sg3_modconv_fwd_tc_x3((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, ldw, st) : SG3_E_NOKERNEL;
-    if (mathMode == 1 && k == 3) return sg3_modconv_fwd_tc3((const float*)x, wmod, (float*)y, N, I, O, H, W, pad, ldw, yPitch, st);
-    if (yPitch != 0 && yPitch != OW) return SG3_E_NOKERNEL;      // only the 3x3 tensor-core kernel writes a padded row pitch
+    if (mathMode == 1 && k == 3) return sg3_modconv_fwd_tc3((const float*)x, wmod, (float*)y, N, I, O, H, W, pad, ldw, xPitch, yPitch, st);
+    // only the 3x3 tensor-core kernel reads / writes padded row pitches
+    if ((yPitch != 0 && yPitch != OW) || (xPitch != 0 && xPitch != W)) return SG3_E_NOKERNEL;
     if (mathMode == 1) return sg3_modconv_fwd_tc((const float*)x, wmod, (float*)y, N, I, O, H, W, k, pad, ldw, st);
     if (mathMode != 0) return SG3_E_INVALID;
     const int P = OH * OW;

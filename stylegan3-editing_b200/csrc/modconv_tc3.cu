@@ -294,11 +294,15 @@ int sg3_modconv_tc3_supported(int I, int O, int H, int W, int k, int pad)
     return 0;
 }
 
-// x [N][I][H][W]; wtap [N][9][O][ldw] (tap = ky * 3 + kx, i contiguous, ldw % 4 == 0, ldw >= I); y [N][O][OH][yPitch >= OW].
-int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw, int yPitch,
-                        cudaStream_t stream)
+// x [N][I][H][xPitch >= W]; wtap [N][9][O][ldw] (tap = ky * 3 + kx, i contiguous, ldw % 4 == 0, ldw >= I); y [N][O][OH][yPitch >= OW].
+// The kernel only sees x through its tensor map, so a padded input row pitch costs nothing: TMA needs the PITCH to be a
+// 16-byte multiple, not W (columns >= W are outside the map's extent and read as zero like any other out-of-image column).
+int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw,
+                        int xPitch, int yPitch, cudaStream_t stream)
 {
-    if (sg3_modconv_tc3_supported(I, O, H, W, 3, pad) != 0) return SG3_E_NOKERNEL;
+    const int xp = xPitch > 0 ? xPitch : W;
+    if (xp < W || xp % 4 != 0) return SG3_E_NOKERNEL;
+    if (sg3_modconv_tc3_supported(I, O, H, xp, 3, pad) != 0 || W + 2 * pad - 2 < 1) return SG3_E_NOKERNEL;
     if (ldw % 4 != 0 || ldw < I) return SG3_E_NOKERNEL;
     if (((uintptr_t)x & 15) || ((uintptr_t)wtap & 15)) return SG3_E_NOKERNEL;
     Tc3Params p;
@@ -322,7 +326,7 @@ int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int 
     alignas(64) CUtensorMap mapX, mapW;
     {
         const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)I, (uint64_t)N};
-        const uint64_t strides[3] = {(uint64_t)W * 4, (uint64_t)W * H * 4, (uint64_t)W * H * I * 4};
+        const uint64_t strides[3] = {(uint64_t)xp * 4, (uint64_t)xp * H * 4, (uint64_t)xp * H * I * 4};
         const uint32_t box[4] = {32, 1, BK3, 1};
         if (!sg3_make_tensor_map(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
             return SG3_E_NOKERNEL;

@@ -70,9 +70,11 @@ def _act_inplace(y, si, sx, sy, gain, slope, clamp, write_signs):
     return s if write_signs else None
 
 
-def _fused(x, fu, fd, b, si, sx, sy, cfg, write_signs, ysum=None):
+def _fused(x, fu, fd, b, si, sx, sy, cfg, write_signs, ysum=None, pitched_out=False):
     """Try the fused kernel.  Returns (y, signs_written) or None when no specialisation exists.
-    `ysum` (float32 [C], zeroed): the kernel adds the per-channel sum of y -- the bias gradient when y = dx."""
+    `ysum` (float32 [C], zeroed): the kernel adds the per-channel sum of y -- the bias gradient when y = dx.
+    `pitched_out`: fp32 outputs whose width is not a multiple of 4 are written with a 16-byte row pitch (returned as a view):
+    the gradient wrt a 3x3 conv's output then feeds the tensor-core input-gradient conv without a re-pitching copy."""
     up, down, px0, px1, py0, py1, gain, slope, clamp, flip = cfg
     if x.dtype not in (torch.float16, torch.float32):
         return None
@@ -88,7 +90,11 @@ def _fused(x, fu, fd, b, si, sx, sy, cfg, write_signs, ysum=None):
     if rc != 0:
         raise RuntimeError('filtered_lrelu: upsampled buffer must be at least the size of the downsampling filter '
                            'and the output at least 1x1')
-    y = torch.empty([n, c, oh.value, ow.value], dtype=x.dtype, device=x.device)
+    if pitched_out and x.dtype == torch.float32 and ow.value % 4 != 0:
+        from .modulated_conv import empty_row_pitched
+        y = empty_row_pitched([n, c, oh.value, ow.value], x.dtype, x.device)
+    else:
+        y = torch.empty([n, c, oh.value, ow.value], dtype=x.dtype, device=x.device)
     d = capi.FlreluDesc()
     d.x, d.y = x.data_ptr(), y.data_ptr()
     d.b = b.data_ptr() if b is not None else None
@@ -189,7 +195,7 @@ class _FilteredLRelu(torch.autograd.Function):
                 # first-order backward: the backward kernel also accumulates db = sum(dx) per channel (fp32 atomics),
                 # which saves the separate reduction pass over dx of filtered_lrelu.py:268
                 ysum = torch.zeros([dy.shape[1]], dtype=torch.float32, device=dy.device)
-                res = _fused(dy, fd, fu, None, signs, s_ofs[0], s_ofs[1], adj, False, ysum=ysum)
+                res = _fused(dy, fd, fu, None, signs, s_ofs[0], s_ofs[1], adj, False, ysum=ysum, pitched_out=True)
                 if res is not None:
                     dx, db = res[0], ysum.to(dy.dtype)
             if dx is None:

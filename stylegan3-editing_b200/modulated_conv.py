@@ -32,12 +32,13 @@ def _math_mode():
 
 
 def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, transpose=False, tap_major=False, half=False,
-                    split=False):
+                    split=False, dgrad_taps=False):
     """[N, O, ldw >= I*k*k] float32 modulated (+demodulated, +input-gain) weights, rows zero padded  (:39-56).
     transpose=True (1x1 only): [N, I, ldw >= O], the weight operand of the input-gradient GEMM.
     tap_major=True: [N, k*k, O, ldw >= I], the operand of the 3x3 tensor-core kernel.
     half=True: float16 [N, O, ldw] (what `w.to(x.dtype)` of :61 produces for fp16 layers), operand of the fp16 tensor-core kernel.
-    split=True: [N, 2, O, ldw], TF32 head and TF32 tail of every weight, operand of the 3xTF32 kernel (math='fp32x3')."""
+    split=True: [N, 2, O, ldw], TF32 head and TF32 tail of every weight, operand of the 3xTF32 kernel (math='fp32x3').
+    dgrad_taps=True: [N, k*k, I, ldw >= O], taps flipped and channels transposed: the operand of the k x k input-gradient conv."""
     capi.require_cuda(w, 'modulated_conv2d')
     O, I, kh, kw = w.shape
     assert kh == kw
@@ -53,8 +54,12 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, tr
             mode, g = 2, g.contiguous()                            # per input channel
         else:
             mode, g = 3, g.expand(N, I).contiguous()               # per (sample, input channel), broadcast like :55
-    layout = 1 if transpose else (2 if tap_major else 0)
-    if split:
+    layout = 1 if transpose else (2 if tap_major else (3 if dgrad_taps else 0))
+    if dgrad_taps:
+        assert not transpose and not tap_major and not half and not split
+        ldw = (O + 31) // 32 * 32
+        wmod = torch.zeros([N, kh * kw, I, ldw], dtype=torch.float32, device=w.device)     # padding columns must be zero
+    elif split:
         assert not transpose and not tap_major and not half
         ldw = (I * kh * kw + 31) // 32 * 32
         wmod = torch.empty([N, 2, O, ldw], dtype=torch.float32, device=w.device)
@@ -90,18 +95,37 @@ def conv_forward(x, wmod, O, k, padding, math):
     16-byte multiple (all 3x3 layers of config T)."""
     N, I, H, W = x.shape
     OH, OW = H + 2 * padding - k + 1, W + 2 * padding - k + 1
+    xpitch = 0
+    if not x.is_contiguous():           # a row-pitched view [N, I, H, W] of a [N, I, H, pitch] buffer (see _row_pitched)
+        assert _row_pitched(x)
+        xpitch = x.stride(2)
     pitch = (OW + 3) // 4 * 4 if (math == 'tf32' and k == 3 and x.dtype == torch.float32 and _pitched_output) else OW
     ybuf = torch.empty([N, O, OH, pitch], dtype=x.dtype, device=x.device)
     y = ybuf if pitch == OW else ybuf[..., :OW]
     with torch.cuda.device(x.device):
         ldw = wmod.shape[-1]
         rc = capi.lib().sg3_modconv_fwd_pitched(x.data_ptr(), wmod.data_ptr(), ybuf.data_ptr(), N, I, O, H, W, k, padding, ldw,
-                                                0 if pitch == OW else pitch, {'fp32': 0, 'tf32': 1, 'fp32x3': 2}[math],
+                                                xpitch, 0 if pitch == OW else pitch, {'fp32': 0, 'tf32': 1, 'fp32x3': 2}[math],
                                                 capi.dtype_code(x.dtype), capi.stream_ptr(x.device))
     if rc == capi.SG3_E_NOKERNEL:
         return None             # e.g. a base pointer off the 16-byte TMA alignment: the caller reruns the SIMT contraction
     capi.check(rc, 'sg3_modconv_fwd')
     return y
+
+
+def _row_pitched(t):
+    """True for a [N, C, H, W] view of a dense [N, C, H, pitch] buffer (unit pixel stride, rows `pitch` apart)."""
+    n, c, h, w = t.shape
+    p = t.stride(2)
+    return t.stride(3) == 1 and p >= w and t.stride(1) == h * p and t.stride(0) == c * h * p
+
+
+def empty_row_pitched(shape, dtype, device, align=4):
+    """[N, C, H, W] tensor whose rows are padded to a multiple of `align` elements (a view when W is not one already)."""
+    n, c, h, w = shape
+    p = (w + align - 1) // align * align
+    buf = torch.empty([n, c, h, p], dtype=dtype, device=device)
+    return buf if p == w else buf[..., :w]
 
 
 def tc_supported(I, O, H, W, k, padding):
@@ -176,6 +200,11 @@ class _ModConv(torch.autograd.Function):
                 and x.dtype == torch.float32 and dy.dtype == torch.float32
                 and (x.shape[2] * x.shape[3]) % 4 == 0):        # TMA needs 16-byte aligned plane pitches
             return _native_backward_1x1(x, w, s, input_gain, dy, demodulate, need) + (None, None, None, None)
+        if (math == 'tf32' and w.shape[-1] == 3 and padding in (0, 2) and not higher_order
+                and x.dtype == torch.float32 and dy.dtype == torch.float32):
+            res = _native_backward_3x3(x, w, s, input_gain, dy, demodulate, padding, need)
+            if res is not None:
+                return res + (None, None, None, None)
         with torch.enable_grad(), torch.backends.cudnn.flags(allow_tf32=(math == 'tf32')):
             xs = x.detach().requires_grad_(need[0])
             ws = w.detach().requires_grad_(need[1])
@@ -270,6 +299,61 @@ def _native_backward_1x1(x, w, s, input_gain, dy, demodulate, need):
             ds = (dW * w2.unsqueeze(0)).sum(dim=1)
         dw = dw.reshape(w.shape).to(w.dtype) if need[1] else None
         ds = ds.to(s.dtype) if need[2] else None
+    return dx, dw, ds
+
+
+def _weights_formula(w, s, demodulate, input_gain, N):
+    """Per-sample weights [N, O, I, k, k] as a differentiable torch expression (networks_stylegan3.py:39-56)."""
+    I = w.shape[1]
+    if demodulate:
+        w = w * w.square().mean([1, 2, 3], keepdim=True).rsqrt()
+        s = s * s.square().mean().rsqrt()
+    w = w.unsqueeze(0) * s.unsqueeze(1).unsqueeze(3).unsqueeze(4)
+    if demodulate:
+        w = w * (w.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt().unsqueeze(2).unsqueeze(3).unsqueeze(4)
+    if input_gain is not None:
+        w = w * input_gain.expand(N, I).unsqueeze(1).unsqueeze(3).unsqueeze(4)
+    return w
+
+
+def _native_backward_3x3(x, w, s, input_gain, dy, demodulate, padding, need):
+    """dx of the 3x3 modulated conv on the tcgen05 kernel: the input gradient of a stride-1 convolution is the convolution of
+    dy with the flipped, channel-transposed taps and padding 2 - pad -- the SAME implicit-GEMM kernel with the weight prologue
+    writing layout 3.  dy arrives from the filtered_lrelu backward kernel as a row-pitched view (its width, e.g. 1046, is not a
+    TMA pitch), otherwise it is copied into one.  dw / ds: the per-sample weight gradient is one library (cuDNN) grouped
+    weight-gradient call, then autograd through the small weight expression.  None when the kernel has no plan for the shape."""
+    N, I, H, W = x.shape
+    O = w.shape[0]
+    dx = dw = ds = None
+    if need[0]:
+        if not (_row_pitched(dy) and dy.stride(2) % 4 == 0 and dy.data_ptr() % 16 == 0):
+            buf = empty_row_pitched(dy.shape, dy.dtype, dy.device)
+            buf.copy_(dy)
+            dy_p = buf
+        else:
+            dy_p = dy
+        wT = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, round_tf32=True, dgrad_taps=True)
+        global _pitched_output
+        keep, _pitched_output = _pitched_output, False            # dx feeds the previous layer's stencil backward as a plain tensor
+        try:
+            dx = conv_forward(dy_p, wT, I, 3, 2 - padding, 'tf32')
+        finally:
+            _pitched_output = keep
+        if dx is None:
+            return None
+    if need[1] or need[2]:
+        dyc = dy.contiguous()
+        with torch.backends.cudnn.flags(allow_tf32=True):
+            dW = torch.nn.grad.conv2d_weight(x.reshape(1, N * I, H, W), [N * O, I, 3, 3], dyc.reshape(1, N * O, *dyc.shape[2:]),
+                                             padding=padding, groups=N).reshape(N, O, I, 3, 3)
+        with torch.enable_grad():
+            ws = w.detach().requires_grad_(need[1])
+            ss = s.detach().requires_grad_(need[2])
+            Wn = _weights_formula(ws, ss, demodulate, input_gain, N)
+            ins = [t for t, n in zip((ws, ss), need[1:]) if n]
+            grads = list(torch.autograd.grad(Wn, ins, dW))
+        dw = grads.pop(0) if need[1] else None
+        ds = grads.pop(0) if need[2] else None
     return dx, dw, ds
 
 

@@ -504,3 +504,30 @@ def test_tiny_generator_fp32x3(pkg):
     finally:
         pkg.modulated_conv.set_math(None)
     assert rel_err(img.cpu().numpy(), g.z['tinyR/img']) < 1e-4
+
+
+def test_native_3x3_input_gradient(pkg):
+    """dx of the 3x3 modulated conv on the tcgen05 kernel (flipped / transposed taps, padding 2 - pad, row-pitched dy) vs the
+    oracle's input gradient; both forward paddings; dy handed over contiguous (re-pitched by a copy) and as a row-pitched view."""
+    from oracle import sg3_oracle as orc
+    rng = np.random.RandomState(23)
+    for (N, I, O, H, pad) in ((2, 40, 24, 24, 2), (1, 96, 130, 20, 2), (2, 33, 64, 20, 0)):        # W % 4 == 0 as in every config-T layer
+        x = rng.randn(N, I, H, H).astype(np.float32)
+        w = rng.randn(O, I, 3, 3).astype(np.float32)
+        s = (rng.randn(N, I) + 1).astype(np.float32)
+        OH = H + 2 * pad - 2
+        dy = rng.randn(N, O, OH, OH).astype(np.float32)
+        dx_ref, dw_ref, ds_ref = orc.modulated_conv2d_bwd(x, w, s, dy, padding=pad)
+        for pitched in (False, True):
+            xt, wt, st = cu(x, True), cu(w, True), cu(s, True)
+            y = pkg.modulated_conv.modulated_conv2d(xt, wt, st, padding=pad, math='tf32')
+            if pitched:
+                g = pkg.modulated_conv.empty_row_pitched(dy.shape, torch.float32, 'cuda')
+                g.copy_(cu(dy))
+            else:
+                g = cu(dy)
+            n0 = pkg.capi.lib().sg3_launch_count()
+            dx, dw, ds = torch.autograd.grad(y, [xt, wt, st], g)
+            assert pkg.capi.lib().sg3_launch_count() - n0 == 3          # weight prologue (2) + the tensor-core conv (1)
+            assert rel_err(dx.cpu().numpy(), dx_ref) < 2e-3, (N, I, O, H, pad, pitched)
+            assert rel_err(dw.cpu().numpy(), dw_ref) < 2e-3 and rel_err(ds.cpu().numpy(), ds_ref) < 2e-3
