@@ -13,8 +13,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OBJ = os.path.join(CSRC, 'build')
-LIB = os.path.join(HERE, 'libsg3_b200.so')
+# Tuning experiments: SG3_NVCC_EXTRA="-DSG3_FL_WARPS=1 ..." builds a variant library next to the default one
+# (SG3_LIB_SUFFIX names it, e.g. "_w1" -> libsg3_b200_w1.so; load it with SG3_B200_LIB=<path>, see capi.py).
+_EXTRA = os.environ.get('SG3_NVCC_EXTRA', '').split()
+_SUFFIX = os.environ.get('SG3_LIB_SUFFIX', '')
+OBJ = os.path.join(CSRC, 'build' + _SUFFIX)
+LIB = os.path.join(HERE, f'libsg3_b200{_SUFFIX}.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
 CFLAGS = ['-O3', '-std=c++17', '-lineinfo', '-Xcompiler', '-fPIC,-fvisibility=hidden', '-Xptxas', '-v',
@@ -57,7 +61,7 @@ def _compile(src, force, verbose):
             force = True
     if not force and os.path.exists(obj) and os.path.getmtime(obj) >= newest:
         return obj, False
-    cmd = [NVCC] + ARCH + CFLAGS + extra + ['-c', path, '-o', obj]
+    cmd = [NVCC] + ARCH + CFLAGS + _EXTRA + extra + ['-c', path, '-o', obj]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(obj + '.log', 'w') as f:
         f.write(' '.join(cmd) + '\n' + res.stdout)

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libsg3_b200.so')
+LIB_PATH = os.environ.get('SG3_B200_LIB') or os.path.join(_HERE, 'libsg3_b200.so')      # the override is for tuning builds (build.py)
 
 SG3_F32, SG3_F16, SG3_F64 = 0, 1, 2
 SG3_E_INVALID, SG3_E_NOKERNEL, SG3_E_TOOLARGE = -1, -2, -3

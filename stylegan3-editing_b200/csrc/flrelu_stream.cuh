@@ -49,7 +49,19 @@ namespace flrelu_stream {
 
 constexpr int kTapsPerPhase = 6;      // up filter taps per polyphase branch
 constexpr int kDownTaps = 12;         // down filter taps (per axis)
-constexpr int kWarpsPerCta = 4;
+// Tuning knobs (build.py: SG3_NVCC_EXTRA / SG3_LIB_SUFFIX build a variant library).  Measured on B200, round 2: one-warp CTAs at
+// 96 registers (21 warps / SM instead of 16) are 11-15 % SLOWER on the dense layers, and a rolled `half` loop in stage D
+// (108 registers) 15-17 % slower: the kernel is bound by the FP32 pipe, not by occupancy.
+#ifndef SG3_FL_WARPS
+#define SG3_FL_WARPS 4
+#endif
+#ifndef SG3_FL_MINCTAS
+#define SG3_FL_MINCTAS 4
+#endif
+#ifndef SG3_FL_HALFLOOP
+#define SG3_FL_HALFLOOP 0
+#endif
+constexpr int kWarpsPerCta = SG3_FL_WARPS;
 constexpr int kStages = 4;            // TMA landing buffers (pairs of input rows in flight) per warp
 // Groups per unrolled period of the main loop.  Inside a period everything that cycles is a compile-time constant: the tap
 // rotation of stage D (period 3), the transpose-buffer parity (2), the cadence of input pairs for UP = 4 (2), and the rows of
@@ -169,7 +181,7 @@ __device__ __forceinline__ float2 act2(float2 v, const Params& p, unsigned rc0, 
 // image comes from the tensor map; the bias enters as the initial value of the stage-B accumulators).  Needs fp32,
 // unit pixel stride and 16-byte aligned row/plane strides; otherwise the register-prefetch path (TMA = false) runs.
 template <class T, int UP, int FD, int MODE, bool TMA>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, TMA ? 4 : 3) kernel(const __grid_constant__ Params p)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, TMA ? SG3_FL_MINCTAS : (3 * 4) / kWarpsPerCta) kernel(const __grid_constant__ Params p)
 {
     typedef Geo<UP> G;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -528,7 +540,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TMA ? 4 : 3) kernel(const _
             // x-symmetric dense filter: per row pair, add mirrored pixels first (12 FADD2), then 6 taps per filter row.
             const float2* pE = (const float2*)sC;
             const float2* pO = (const float2*)(sC + G::XHP);
+#if SG3_FL_HALFLOOP
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int half = 0; half < 2; half++) {          // half 0: rows (4g, 4g+2); half 1: rows (4g+1, 4g+3)
                 float2 px[kDownTaps + 2];
 #pragma unroll
