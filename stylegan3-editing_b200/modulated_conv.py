@@ -101,7 +101,10 @@ def conv_forward(x, wmod, O, k, padding, math):
         xpitch = x.stride(2)
     pitch = (OW + 3) // 4 * 4 if (math == 'tf32' and k == 3 and x.dtype == torch.float32 and _pitched_output) else OW
     ybuf = torch.empty([N, O, OH, pitch], dtype=x.dtype, device=x.device)
-    y = ybuf if pitch == OW else ybuf[..., :OW]
+    y = ybuf
+    if pitch != OW:
+        ybuf[..., OW:].zero_()        # padding columns: defined contents, never written by the kernel, never read by the stencil's TMA
+        y = ybuf[..., :OW]
     with torch.cuda.device(x.device):
         ldw = wmod.shape[-1]
         rc = capi.lib().sg3_modconv_fwd_pitched(x.data_ptr(), wmod.data_ptr(), ybuf.data_ptr(), N, I, O, H, W, k, padding, ldw,
@@ -125,7 +128,10 @@ def empty_row_pitched(shape, dtype, device, align=4):
     n, c, h, w = shape
     p = (w + align - 1) // align * align
     buf = torch.empty([n, c, h, p], dtype=dtype, device=device)
-    return buf if p == w else buf[..., :w]
+    if p == w:
+        return buf
+    buf[..., w:].zero_()              # the <= 3 padding columns of every row: defined contents (no kernel ever writes them)
+    return buf[..., :w]
 
 
 def tc_supported(I, O, H, W, k, padding):
