@@ -199,7 +199,7 @@ def run_pti(args, ClockSampler):
     with torch.no_grad():
         ws = G.mapping(z[b0:b1].to(dev), None).contiguous()
     frames = frames_host.to(dev)
-    trainer = workloads.PTITrainer(G, frames, ws, batch=B, world=world)
+    trainer = workloads.PTITrainer(G, frames, ws, batch=B, world=world, use_graph=not args.eager)
     ws_host = ws.cpu().pin_memory()
 
     def step_resident():
@@ -207,18 +207,13 @@ def run_pti(args, ClockSampler):
 
     def step_e2e():
         # frames and latents of the step come from pinned host memory; the loss value goes back (the reference prints it)
-        n = frames_host.shape[0]
-        idx = [(trainer.cursor + i) % n for i in range(B)]
-        trainer.cursor = (trainer.cursor + B) % n
-        tgt = frames_host[idx[0]:idx[0] + B].to(dev, non_blocking=True) if idx[-1] == idx[0] + B - 1 else torch.stack([frames_host[i] for i in idx]).to(dev)
-        w = ws_host[idx].to(dev, non_blocking=True)
-        trainer.bucket.zero()
-        img = G.synthesis(w, noise_mode='const', force_fp32=True)
-        loss = torch.nn.functional.mse_loss(img, tgt) + trainer.lpips(img, tgt)
-        loss.backward()
-        trainer.bucket.all_reduce_mean()
-        trainer.opt.step()
-        return float(loss)                                   # D2H of the loss: synchronises the step
+        idx = trainer._next_batch()
+        if idx[-1] == idx[0] + B - 1:
+            tgt = frames_host[idx[0]:idx[0] + B]
+        else:
+            tgt = torch.stack([frames_host[i] for i in idx])
+        trainer.load_batch(tgt, ws_host[idx])
+        return float(trainer.run_loaded())                   # D2H of the loss: synchronises the step
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -227,8 +222,8 @@ def run_pti(args, ClockSampler):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    timer.on = args.eager                                    # a graph replay hides the per-call wrapper: see below
     launches0 = capi.lib().sg3_launch_count()
-    timer.on = True
     _barrier(world)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -241,6 +236,22 @@ def run_pti(args, ClockSampler):
     launches = capi.lib().sg3_launch_count() - launches0
     ms_total = sharding.max_over_ranks(e0.elapsed_time(e1), device=dev)
     clocks = sampler.stop() if rank == 0 else None
+    fl_steps = args.steps
+    if not args.eager:
+        # kernel time of filtered_lrelu and the launch count: two eager steps of the same computation with events around every launch
+        for _ in range(2):                                   # untimed: the eager allocations (the graphs own a private pool)
+            trainer.load_batch(frames[:B], ws[:B])
+            trainer._fwd_bwd()
+        torch.cuda.synchronize()
+        timer.on = True
+        l0 = capi.lib().sg3_launch_count()
+        fl_steps = 2
+        for _ in range(fl_steps):
+            trainer.load_batch(frames[:B], ws[:B])
+            trainer._fwd_bwd()
+        torch.cuda.synchronize()
+        timer.on = False
+        launches = (capi.lib().sg3_launch_count() - l0) // fl_steps * args.steps
     fl_ms, fl_bytes, n_calls = timer.close()
 
     for _ in range(2):
@@ -277,11 +288,13 @@ def run_pti(args, ClockSampler):
         e2e=dict(value=world * B * args.steps / (e2e_ms * 1e-3), unit='frames/s',
                  h2d_bytes_per_step=int(B * 3 * 1024 * 1024 * 4 + B * ws.shape[1] * 512 * 4), d2h_bytes_per_step=4),
         gpu_launches=int(launches),
-        roofline=_roofline(fl_ms, fl_bytes, n_calls, args.steps,
-                           f'filtered_lrelu forward with sign write + backward ({n_calls // max(args.steps, 1)} launches per step, CUDA events)'),
+        roofline=_roofline(fl_ms, fl_bytes, n_calls, fl_steps,
+                           f'filtered_lrelu forward with sign write + backward ({n_calls // max(fl_steps, 1)} launches per step, CUDA events'
+                           + ('' if args.eager else ' on eager steps; the timed steps replay the same launches from CUDA graphs') + ')'),
         loss_first=losses[0], loss_last=losses[-1], rank_parameter_divergence=dev_max,
         cpu_baseline=None)
-    out['roofline']['share_of_step'] = (fl_ms / args.steps) / (ms_total / args.steps)
+    out['roofline']['share_of_step'] = (fl_ms / fl_steps) / (ms_total / args.steps)
+    out['config']['step'] = 'eager' if args.eager else 'two CUDA graphs per step (zero + forward + loss + backward | Adam) around the eager NCCL all-reduce'
     print(json.dumps(out))
     assert dev_max == 0.0, f'ranks diverged by {dev_max}'
     if world > 1:

@@ -197,9 +197,15 @@ class LPIPSAlex(nn.Module):
 
 class PTITrainer:
     """Data-parallel PTI over frames.  Every rank owns a contiguous shard of the frames and walks it in batches of
-    `batch` frames; one `step()` = forward, loss, backward, ONE flat all-reduce, Adam."""
+    `batch` frames; one `step()` = forward, loss, backward, ONE flat all-reduce, Adam.
 
-    def __init__(self, G, frames, latents, batch=4, lr=3e-4, l2_lambda=1.0, lpips_lambda=1.0, world=1):
+    `use_graph=True`: a PTI step at batch 4 is ~800 kernel launches (autograd through 15 layers, ~60 parameter tensors), and the
+    Python / launch overhead of the small ones leaves the GPU idle for a third of the step.  The step is therefore captured ONCE
+    into two CUDA graphs -- (zero the gradient bucket, forward, loss, backward) and (Adam) -- around the eager NCCL all-reduce, and
+    replayed on static input buffers.  Every sg3_b200 kernel launches on the capturing stream, taps and tensor maps travel in the
+    launch parameters, nothing synchronises with the host."""
+
+    def __init__(self, G, frames, latents, batch=4, lr=3e-4, l2_lambda=1.0, lpips_lambda=1.0, world=1, use_graph=False):
         from sg3_b200 import sharding
         self.G, self.frames, self.latents, self.batch, self.world = G, frames, latents, batch, world
         self.l2_lambda, self.lpips_lambda = l2_lambda, lpips_lambda
@@ -210,18 +216,64 @@ class PTITrainer:
         for p in params:
             p.requires_grad_(True)
         self.bucket = sharding.FlatGradBucket(params)
-        self.opt = torch.optim.Adam(params, lr=lr)
+        self.opt = torch.optim.Adam(params, lr=lr, capturable=use_graph)
         self.cursor = 0
+        self.use_graph = use_graph
+        self._graphs = None
+        dev = frames.device
+        self.s_tgt = torch.empty([batch] + list(frames.shape[1:]), device=dev)       # static inputs of the captured step
+        self.s_ws = torch.empty([batch] + list(latents.shape[1:]), device=dev)
+        self.s_loss = torch.zeros([], device=dev)
 
-    def step(self):
+    def _next_batch(self):
         n = self.frames.shape[0]
         idx = [(self.cursor + i) % n for i in range(self.batch)]
         self.cursor = (self.cursor + self.batch) % n
-        tgt, ws = self.frames[idx], self.latents[idx]
+        return idx
+
+    def _fwd_bwd(self):
         self.bucket.zero()
-        img = self.G.synthesis(ws, noise_mode='const', force_fp32=True)
-        loss = self.l2_lambda * F.mse_loss(img, tgt) + self.lpips_lambda * self.lpips(img, tgt)
+        img = self.G.synthesis(self.s_ws, noise_mode='const', force_fp32=True)
+        loss = self.l2_lambda * F.mse_loss(img, self.s_tgt) + self.lpips_lambda * self.lpips(img, self.s_tgt)
         loss.backward()
-        self.bucket.all_reduce_mean()
-        self.opt.step()
-        return loss.detach()
+        self.s_loss.copy_(loss.detach())
+
+    def _capture(self):
+        side = torch.cuda.Stream(self.s_tgt.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                          # warm-up off the default stream: allocator pools, tap caches, Adam state
+            for _ in range(3):
+                self._fwd_bwd()
+                self.bucket.all_reduce_mean()
+                self.opt.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self._fwd_bwd()
+        with torch.cuda.graph(g2):
+            self.opt.step()
+        self._graphs = (g1, g2)
+
+    def load_batch(self, tgt, ws):
+        self.s_tgt.copy_(tgt, non_blocking=True)
+        self.s_ws.copy_(ws, non_blocking=True)
+
+    def run_loaded(self):
+        """One optimisation step on the batch currently in the static buffers; returns the (device) loss."""
+        if self.use_graph:
+            if self._graphs is None:
+                self._capture()
+            self._graphs[0].replay()
+            self.bucket.all_reduce_mean()
+            self._graphs[1].replay()
+        else:
+            self._fwd_bwd()
+            self.bucket.all_reduce_mean()
+            self.opt.step()
+        return self.s_loss
+
+    def step(self):
+        idx = self._next_batch()
+        self.load_batch(self.frames[idx], self.latents[idx])
+        return self.run_loaded().clone()

@@ -203,6 +203,13 @@ int sg3_modconv_fwd_pitched(const void* x, const float* wmod, void* y,
                             int N, int I, int O, int H, int W, int k, int pad, int ldw, int xPitch, int yPitch,
                             int mathMode, int dtype, void* stream);
 
+/* Co-scheduling knob (no reference counterpart; networks.PipelinedSynthesis uses it).  The tensor-core conv kernels are persistent,
+ * one CTA per SM with a deep TMA ring (up to ~200 KB of dynamic shared memory), so nothing else fits on an SM while they run.  With a
+ * budget of `bytes` (> 0) they shrink the ring to fit, which leaves room for three of the four resident filtered_lrelu CTAs of an SM:
+ * launched on two streams, the HBM/tensor-bound contraction of one micro-batch then overlaps the FP32-pipe-bound stencil of another.
+ * 0 restores the default.  Process-wide; returns the previous value. */
+int sg3_modconv_set_smem_budget(int bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,20 @@ int sg3_sm_count()
     return cached[dev];
 }
 
+static std::atomic<int> g_convSmemBudget{0};
+int sg3_conv_smem_budget() { return g_convSmemBudget.load(std::memory_order_relaxed); }
+SG3_EXPORT int sg3_modconv_set_smem_budget(int bytes)
+{
+    if (bytes < 0) bytes = 0;
+    return g_convSmemBudget.exchange(bytes, std::memory_order_relaxed);
+}
+
+#ifdef SG3_TRACE
+static std::atomic<unsigned long long*> g_trace{nullptr};
+unsigned long long* sg3_trace_buffer() { return g_trace.load(std::memory_order_relaxed); }
+SG3_EXPORT void sg3_debug_set_trace(void* buf) { g_trace.store((unsigned long long*)buf, std::memory_order_relaxed); }
+#endif
+
 SG3_EXPORT int sg3_abi_version(void) { return SG3_ABI_VERSION; }
 
 SG3_EXPORT int sg3_sizeof_flrelu_desc(void) { return (int)sizeof(sg3_flrelu_desc); }

@@ -47,6 +47,9 @@ __host__ __device__ __forceinline__ int pos_mod(int a, int b)
     return r < 0 ? r + b : r;
 }
 
+// Dynamic shared memory the persistent tensor-core conv kernels may use per CTA (0 = no limit); see sg3_modconv_set_smem_budget.
+int sg3_conv_smem_budget();
+
 // Cached SM count of the current device (grid sizing in multiples of the SM count).
 int sg3_sm_count();
 
@@ -65,3 +68,30 @@ struct Sg3DeviceOnce {
         return e;
     }
 };
+
+// ---- CTA residency trace (debug builds only: -DSG3_TRACE, see tools/overlap_probe.py) ---------------------------------------
+// buf[0] = record counter, buf[1] = capacity in records, records of 3 x u64 from buf[2]: (kind << 32 | smid), id, globaltimer.
+#ifdef SG3_TRACE
+unsigned long long* sg3_trace_buffer();
+__device__ __forceinline__ void sg3_trace(unsigned long long* buf, unsigned kind, unsigned long long id)
+{
+    if (!buf) return;
+    unsigned smid;
+    unsigned long long t;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned long long slot = atomicAdd(buf, 1ull);
+    if (slot < buf[1]) {
+        buf[2 + 3 * slot] = ((unsigned long long)kind << 32) | smid;
+        buf[3 + 3 * slot] = id;
+        buf[4 + 3 * slot] = t;
+    }
+}
+#define SG3_TRACE_FIELD unsigned long long* trace;
+#define SG3_TRACE_SET(p) (p).trace = sg3_trace_buffer()
+#define SG3_TRACE_EVENT(p, kind, id) sg3_trace((p).trace, kind, id)
+#else
+#define SG3_TRACE_FIELD
+#define SG3_TRACE_SET(p) ((void)0)
+#define SG3_TRACE_EVENT(p, kind, id) ((void)0)
+#endif

@@ -223,6 +223,7 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
     p.chunkRows = (d->outH + chunks - 1) / chunks;
     p.chunksY = (d->outH + p.chunkRows - 1) / p.chunkRows;
     p.totalStrips = base * p.chunksY;
+    SG3_TRACE_SET(p);
 
     // Dense filters that are mirror-symmetric along x (the radial jinc filters are) take the variant that
     // pre-adds mirrored pixels.  Exact tap equality is required; anything else runs the general dense path.

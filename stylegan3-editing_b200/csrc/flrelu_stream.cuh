@@ -109,6 +109,7 @@ struct Params {
     int stripsX, chunksY, chunkRows;
     int vecStore;                      // y has unit pixel stride and 8-byte (fp32) / 4-byte (fp16) aligned rows: paired stores
     long long totalStrips;
+    SG3_TRACE_FIELD
     // tap tables are laid out for 128-bit uniform loads (LDCU.128): rows of 8 / 12 floats, 16-byte aligned
     alignas(16) float tu[4][8];        // tu[p][k]: up taps of phase p, pre-scaled by UP (horizontal pass); k < 6
     alignas(16) float tv[4][8];        // vertical pass: tu * gain (the activation gain rides on the taps)
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TMA ? SG3_FL_MINCTAS : (3 *
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const long long strip = (long long)blockIdx.x * kWarpsPerCta + warp;
     if (strip >= p.totalStrips) return;
+    if (lane == 0) SG3_TRACE_EVENT(p, 1, (unsigned long long)strip);
 
     unsigned char* wsm = smem_raw + warp * G::WARP_BYTES;
     float2* sIn = (float2*)wsm;                                        // register path: [TIW] (row 2t, row 2t+1)
@@ -684,6 +686,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TMA ? SG3_FL_MINCTAS : (3 *
         for (int o = 16; o > 0; o >>= 1) ySum += __shfl_xor_sync(0xffffffffu, ySum, o);
         if (lane == 0) atomicAdd(p.ysum + c, ySum);
     }
+    if (lane == 0) SG3_TRACE_EVENT(p, 2, (unsigned long long)strip);
 }
 
 }  // namespace flrelu_stream

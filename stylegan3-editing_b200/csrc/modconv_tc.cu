@@ -50,6 +50,7 @@ struct TcParams {
     int kTiles;
     int stages;            // smem pipeline depth (4 for 48 KB stages, 6 for <= 32 KB stages)
     long long totalTiles;
+    SG3_TRACE_FIELD
 };
 
 // Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The TMA producer runs
@@ -78,6 +79,7 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     // warp index through a shuffle: the role dispatch is then provably warp-uniform and the producer / MMA loops run on the
     // uniform datapath (see tc_common.cuh, "warp-uniform issue")
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) SG3_TRACE_EVENT(p, 3, blockIdx.x);
     // stage layout: A (X^T tile) [| A tail (X3)] | B (W tile) [| B tail (X3)]
     constexpr int A_BYTES = X3 ? 2 * A_STAGE_BYTES : A_STAGE_BYTES;
     const int bBytes = p.BN * BK * 4;
@@ -236,6 +238,7 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     if (warp == 5) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)p.tmemCols) : "memory");
+        if (lane == 0) SG3_TRACE_EVENT(p, 4, blockIdx.x);
     }
 }
 
@@ -436,10 +439,22 @@ int launch_fwd_tc(const void* x, const void* wmod, void* y, int N, int I, int O,
     }
     // operand stages: 4 x 48 KB or 6 x <= 32 KB; X3: 3 x <= 64 KB
     p.stages = X3 ? 3 : (bn > 128 ? 4 : 6);
-    const int smemBytes = p.stages * ((X3 ? 2 : 1) * (A_STAGE_BYTES + bn * BK * 4)) + 1024;
+    SG3_TRACE_SET(p);
+    const int stageBytes = (X3 ? 2 : 1) * (A_STAGE_BYTES + bn * BK * 4);
+    if (const int budget = sg3_conv_smem_budget()) {
+        // co-scheduling with the stencil kernel (sg3_modconv_set_smem_budget): a shallower ring so that this CTA fits NEXT TO three
+        // resident stencil CTAs; the contraction is HBM-bound and 2-4 stages of 32-48 KB still cover the DRAM latency
+        const int fit = (budget - 1024) / stageBytes;
+        if (fit < p.stages) p.stages = fit < 2 ? 2 : fit;
+    }
+    const int smemBytes = p.stages * stageBytes + 1024;
     static Sg3DeviceOnce once;
     const cudaError_t attrErr = once.run([] {
-        return cudaFuncSetAttribute(modconv_tc_kernel<HALF, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(modconv_tc_kernel<HALF, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        // the same (maximal) shared-memory carve-out as the stencil kernels: an SM cannot hold CTAs of two kernels that were
+        // launched with different carve-outs, and PipelinedSynthesis wants this CTA next to three stencil CTAs
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(modconv_tc_kernel<HALF, X3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        return e;
     });
     if (attrErr != cudaSuccess) return (int)attrErr;
     modconv_tc_kernel<HALF, X3><<<(unsigned)ctas, X3 ? kThreadsX3 : kThreads, smemBytes, stream>>>(mapX, mapW, p);

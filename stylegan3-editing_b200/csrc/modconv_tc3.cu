@@ -241,7 +241,7 @@ constexpr int kSmemLimit3 = 224 * 1024;       // + 2 KB of static barriers stays
 
 // Pick (NPX, R, accumulator stages, W slots) for a layer: minimise an estimate of the per-layer time
 // max(MMA clocks, operand bytes / 40 B/clk) over the tile shapes that fit TMEM (512 columns) and shared memory.
-bool plan_tc3(Tc3Params& p)
+bool plan_tc3(Tc3Params& p, int smemLimit)
 {
     // Per-tile time model fitted on B200 (tools/run_tc3_sweep.sh): a fixed 1700 clk of pipeline hand-over, the K loop
     // (tensor core or operand stream, whichever is slower) and -- the accumulator is single-buffered -- the serial
@@ -256,7 +256,7 @@ bool plan_tc3(Tc3Params& p)
             const int need = (2 * r - 1) * cw + ((cw + 31) & ~31);
             if (need > 512) continue;
             const int xGroup = (r + 2) * npx * 128;
-            int wSlots = (kSmemLimit3 - 1024 - 4 * 32 * STAGE_PITCH * 4 - 2 * xGroup) / p.wSlotBytes;
+            int wSlots = (smemLimit - 1024 - 4 * 32 * STAGE_PITCH * 4 - 2 * xGroup) / p.wSlotBytes;
             if (wSlots > kMaxWSlots) wSlots = kMaxWSlots;
             if (wSlots < 3) continue;
             const bool resident = wSlots >= 9 * p.kChunks;
@@ -316,7 +316,9 @@ int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int 
     p.m64 = O <= 64 ? 1 : 0;
     p.wRows = O >= 128 ? 128 : (O + 7) & ~7;
     p.wSlotBytes = p.wRows * BK3 * 4;
-    if (!plan_tc3(p)) return SG3_E_NOKERNEL;
+    // co-scheduling with the stencil kernel (sg3_modconv_set_smem_budget): plan inside a smaller shared-memory budget
+    const int budget = sg3_conv_smem_budget();
+    if (!plan_tc3(p, budget > 0 && budget < kSmemLimit3 ? budget : kSmemLimit3)) return SG3_E_NOKERNEL;
     p.tilesX = (p.OW + p.S - 1) / p.S;
     p.tilesY = (p.OH + p.R - 1) / p.R;
     p.tilesO = (O + 127) / 128;
@@ -340,7 +342,12 @@ int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int 
     }
     const int smemBytes = 2 * p.xGroupBytes + p.wSlots * p.wSlotBytes + 4 * 32 * STAGE_PITCH * 4 + 1024;
     static Sg3DeviceOnce once;
-    const cudaError_t attrErr = once.run([] { return cudaFuncSetAttribute(modconv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3); });
+    const cudaError_t attrErr = once.run([] {
+        cudaError_t e = cudaFuncSetAttribute(modconv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
+        // same carve-out as the stencil kernels, so that both can be resident on one SM (see modconv_tc.cu)
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(modconv_tc3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        return e;
+    });
     if (attrErr != cudaSuccess) return (int)attrErr;
     modconv_tc3_kernel<<<(unsigned)ctas, kThreads3, smemBytes, stream>>>(mapX, mapW, p);
     return sg3_launch_status();

@@ -20,7 +20,7 @@ from . import bias_act, filtered_lrelu
 from .modulated_conv import modulated_conv2d
 
 __all__ = ['FullyConnectedLayer', 'MappingNetwork', 'SynthesisInput', 'SynthesisLayer', 'SynthesisNetwork',
-           'Generator', 'modulated_conv2d', 'CONFIG_R', 'CONFIG_T']
+           'Generator', 'GraphedSynthesis', 'PipelinedSynthesis', 'modulated_conv2d', 'CONFIG_R', 'CONFIG_T']
 
 # Keyword sets of the reference's SG3Generator wrapper (models/stylegan3/model.py:29-54).
 CONFIG_R = dict(channel_base=65536, channel_max=1024, conv_kernel=1, use_radial_filters=True)
@@ -203,6 +203,12 @@ class SynthesisLayer(torch.nn.Module):
         self.padding = [int(lo[0]), int(hi[0]), int(lo[1]), int(hi[1])]
 
     def forward(self, x, w, styles=None, noise_mode='random', force_fp32=False, update_emas=False):
+        x = self.conv_part(x, w, styles=styles, noise_mode=noise_mode, force_fp32=force_fp32, update_emas=update_emas)
+        return self.act_part(x)
+
+    # The two halves of forward(), separately callable so that `PipelinedSynthesis` can launch them on different streams.
+    def conv_part(self, x, w, styles=None, noise_mode='random', force_fp32=False, update_emas=False):
+        """EMA gain -> affine -> modulated_conv2d   (reference :335-358)."""
         assert noise_mode in ['random', 'const', 'none']
         _shape_is(x, [None, self.in_channels, int(self.in_size[1]), int(self.in_size[0])])
         if update_emas:
@@ -216,8 +222,12 @@ class SynthesisLayer(torch.nn.Module):
             if self.is_torgb:
                 styles = styles * (1 / np.sqrt(self.in_channels * (self.conv_kernel ** 2)))
         dtype = torch.float16 if (self.use_fp16 and not force_fp32 and x.device.type == 'cuda') else torch.float32
-        x = modulated_conv2d(x=x.to(dtype), w=self.weight, s=styles, padding=self.conv_kernel - 1,
-                             demodulate=(not self.is_torgb), input_gain=input_gain)
+        return modulated_conv2d(x=x.to(dtype), w=self.weight, s=styles, padding=self.conv_kernel - 1,
+                                demodulate=(not self.is_torgb), input_gain=input_gain)
+
+    def act_part(self, x):
+        """bias -> filtered leaky ReLU at the temporary sampling rate   (reference :361-368)."""
+        dtype = x.dtype
         x = filtered_lrelu.filtered_lrelu(
             x=x, fu=self.up_filter, fd=self.down_filter, b=self.bias.to(x.dtype), up=self.up_factor, down=self.down_factor,
             padding=self.padding, gain=(1 if self.is_torgb else np.sqrt(2)), slope=(1 if self.is_torgb else 0.2),
@@ -369,3 +379,102 @@ class GraphedSynthesis:
         self.ws.copy_(ws, non_blocking=True)
         self.graph.replay()
         return self.img
+
+
+class PipelinedSynthesis:
+    """`SynthesisNetwork.forward` with the two halves of every layer OVERLAPPED on the GPU.
+
+    A synthesis layer is a modulated convolution (tcgen05 tensor cores, bound by HBM in config R and by the tensor pipe in config
+    T; its FP32 pipe idles) followed by the fused filtered_lrelu stencil (bound by the FP32 pipe; HBM at ~20 %, tensor pipe idle).
+    Run back to back, each leaves the other's resource unused.  Here the batch is split into micro-batches and the network is
+    software-pipelined over two streams: the convolutions go to a HIGH-priority stream, the stencils to a normal one, chained per
+    micro-batch by events -- while the stencil of layer k works on micro-batch m, the convolution of micro-batch m+1 (or of layer
+    k+1 on micro-batch m-1) runs on the same SMs.  Co-residency is arranged, not hoped for: the conv kernels are persistent (one CTA
+    per SM) and are given a shared-memory budget (`sg3_modconv_set_smem_budget`) that lets one conv CTA (192 threads, 64 registers)
+    sit next to three of the four stencil CTAs an SM holds (4 warps, 128 registers, 28 KB each), and the block scheduler serves the
+    high-priority stream first, so a pending conv CTA takes the first stencil slot that retires.
+
+    Every op is per sample, so the result equals the plain forward up to the batch-global style RMS of networks_stylegan3.py:42,
+    which cancels under demodulation except for its 1e-8 epsilon (same statement as for batch sharding across GPUs).
+    Inference only (`torch.no_grad`)."""
+
+    CONV_SMEM_BUDGET = 138 * 1024       # 228 KB per SM - 3 x (28 KB + 1 KB reserved) stencil CTAs - 1 KB reserved - barriers
+
+    def __init__(self, synthesis, micro_batches=2, conv_smem_budget=None):
+        self.synthesis = synthesis
+        self.micro_batches = int(micro_batches)
+        self.budget = self.CONV_SMEM_BUDGET if conv_smem_budget is None else int(conv_smem_budget)
+        self._streams = {}
+
+    def _get_streams(self, device):
+        key = torch.device(device).index
+        if key not in self._streams:
+            try:
+                lo_pri, hi_pri = torch.cuda.Stream.priority_range()        # (least, greatest) = (0, -5) on B200
+            except Exception:
+                lo_pri, hi_pri = 0, -1
+            self._streams[key] = (torch.cuda.Stream(device, priority=hi_pri), torch.cuda.Stream(device, priority=lo_pri))
+        return self._streams[key]
+
+    @torch.no_grad()
+    def __call__(self, ws, out=None, **layer_kwargs):
+        from . import capi
+        syn = self.synthesis
+        _shape_is(ws, [None, syn.num_ws, syn.w_dim])
+        N, dev = ws.shape[0], ws.device
+        M = max(1, min(self.micro_batches, N))
+        if M == 1:
+            img = syn(ws, **layer_kwargs)
+            if out is not None:
+                out.copy_(img)
+                return out
+            return img
+        if out is None:
+            out = torch.empty([N, syn.img_channels, syn.img_resolution, syn.img_resolution], dtype=torch.float32, device=dev)
+        bounds = [(N * m // M, N * (m + 1) // M) for m in range(M)]
+        conv_s, act_s = self._get_streams(dev)
+        main = torch.cuda.current_stream(dev)
+        conv_s.wait_stream(main)
+        act_s.wait_stream(main)
+        layers = [getattr(syn, name) for name in syn.layer_names]
+        prev = capi.lib().sg3_modconv_set_smem_budget(self.budget)
+        try:
+            # Tensor lifetimes across the two streams are ordered by hand instead of `Tensor.record_stream` (which parks a freed
+            # block until the GPU has caught up -- the host runs a whole forward ahead, so every activation of the network would
+            # be live at once): a conv output t is allocated on the conv stream and read by the stencil stream; it is released only
+            # after the conv stream has waited for that stencil (the wait the next layer needs anyway), so any later conv-stream
+            # allocation that reuses the block is ordered behind the read.  Symmetrically for the stencil outputs.
+            wsm, x, t_prev, ev = [], [None] * M, [None] * M, [None] * M
+            with torch.cuda.stream(conv_s):
+                for m, (b0, b1) in enumerate(bounds):
+                    w = ws[b0:b1].to(torch.float32).unbind(dim=1)
+                    wsm.append(w)
+                    x[m] = syn.input(w[0])
+            for k, layer in enumerate(layers):
+                for m in range(M):
+                    with torch.cuda.stream(conv_s):
+                        if ev[m] is not None:
+                            conv_s.wait_event(ev[m])                     # the stencil of the previous layer on this micro-batch ...
+                            t_prev[m] = None                             # ... which was the last reader of that layer's conv output
+                        t = layer.conv_part(x[m], wsm[m][k + 1], **layer_kwargs)
+                        done = torch.cuda.Event()
+                        done.record(conv_s)
+                    with torch.cuda.stream(act_s):
+                        act_s.wait_event(done)
+                        x[m] = None                                      # the conv that read it is complete as far as act_s is concerned
+                        y = layer.act_part(t)
+                        if k == len(layers) - 1:                         # output scale and fp32 cast of SynthesisNetwork.forward
+                            b0, b1 = bounds[m]
+                            torch.mul(y, syn.output_scale, out=out[b0:b1])
+                        ev[m] = torch.cuda.Event()
+                        ev[m].record(act_s)
+                    x[m], t_prev[m] = y, t
+                    del t, y
+            conv_s.wait_stream(act_s)                                    # orders the release of the last conv outputs (below)
+            act_s.wait_stream(conv_s)
+            del x, t_prev
+        finally:
+            capi.lib().sg3_modconv_set_smem_budget(prev)
+        main.wait_stream(act_s)
+        main.wait_stream(conv_s)
+        return out
