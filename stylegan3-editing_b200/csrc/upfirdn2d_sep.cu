@@ -9,6 +9,7 @@
 // Up / down factor (the same on both axes, one of them 1) and the taps per polyphase branch (KP) are compile-time;
 // lanes run along x: global loads / stores are contiguous segments, the x pass keeps the taps of a lane's branch in
 // registers, the y pass reads its taps with a warp-uniform index.
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -223,6 +224,17 @@ int dispatch_sep(const SepParams& p, int up, int down, cudaStream_t stream)
 
 }  // namespace
 
+int sg3_upfirdn2d_stream(const float* x, float* y, int N, int C, int inH, int inW, int outH, int outW,
+                         const int64_t xs[4], const int64_t ys[4], const float* fx, const float* fy, int fW, int fH,
+                         int up, int down, int padx0, int pady0, float gain, cudaStream_t stream);
+
+// SG3_UPFIRDN_TILED=1 in the environment keeps the tiled kernel for everything (A/B timing, tools/prof_ops.py)
+static bool stream_kernel_disabled()
+{
+    static const bool off = [] { const char* e = getenv("SG3_UPFIRDN_TILED"); return e && e[0] == '1'; }();
+    return off;
+}
+
 // Separable filter, same factors on both axes.  fx [fW], fy [fH] host taps (NULL = single 1); other arguments as sg3_upfirdn2d.
 SG3_EXPORT int sg3_upfirdn2d_sep(const void* x, void* y, const float* fx, const float* fy,
                                  int N, int C, int inH, int inW, int outH, int outW,
@@ -244,5 +256,12 @@ SG3_EXPORT int sg3_upfirdn2d_sep(const void* x, void* y, const float* fx, const 
     for (int b = 0; b < fW; b++) p.fx[b] = fx ? fx[flip ? b : fW - 1 - b] : 1.0f;
     for (int a = 0; a < fH; a++) p.fy[a] = fy ? fy[flip ? a : fH - 1 - a] : 1.0f;
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == SG3_F32 && !stream_kernel_disabled()) {
+        // warp-streaming kernel first (upfirdn2d_stream.cu: up 2 / down 2 / neither, <= 12 taps per branch); the tiled kernel
+        // below covers the rest (factors of 4, longer filters, fp16)
+        const int rc = sg3_upfirdn2d_stream((const float*)x, (float*)y, N, C, inH, inW, outH, outW, xStride, yStride, p.fx, p.fy, fW, fH,
+                                            up, down, padx0, pady0, gain, st);
+        if (rc != SG3_E_NOKERNEL) return rc;
+    }
     return dtype == SG3_F32 ? dispatch_sep<float>(p, up, down, st) : dispatch_sep<__half>(p, up, down, st);
 }

@@ -123,13 +123,14 @@ def upfirdn2d_raw(x, taps2d, upx, upy, downx, downy, padx0, padx1, pady0, pady1,
     return y
 
 
-def upfirdn2d_sep_raw(x, taps1d, up, down, padx0, padx1, pady0, pady1, flip, gain):
-    """Separable filter in one launch (sg3_upfirdn2d_sep).  Returns None when the library has no kernel for the shape."""
+def upfirdn2d_sep_raw(x, taps_x, taps_y, up, down, padx0, padx1, pady0, pady1, flip, gain):
+    """Separable filter (1-D numpy taps per axis) in one launch (sg3_upfirdn2d_sep): the warp-streaming kernel for fp32 with
+    up 2 / down 2 / neither, the tiled one-pass kernel otherwise.  Returns None when the library has no kernel for the shape."""
     capi.require_cuda(x, 'upfirdn2d')
-    ft = int(taps1d.shape[0])
+    fw, fh = int(taps_x.shape[0]), int(taps_y.shape[0])
     n, c, ih, iw = x.shape
-    ow = (iw * up + padx0 + padx1 - ft + down) // down
-    oh = (ih * up + pady0 + pady1 - ft + down) // down
+    ow = (iw * up + padx0 + padx1 - fw + down) // down
+    oh = (ih * up + pady0 + pady1 - fh + down) // down
     if ow < 1 or oh < 1:
         raise RuntimeError('upfirdn2d: output must be at least 1x1')
     if x.numel() == 0 or x.dtype not in (torch.float16, torch.float32) or x.stride(3) != 1:
@@ -139,13 +140,38 @@ def upfirdn2d_sep_raw(x, taps1d, up, down, padx0, padx1, pady0, pady1, flip, gai
     ys = capi.c_i64x4(*y.stride())
     with torch.cuda.device(x.device):
         rc = capi.lib().sg3_upfirdn2d_sep(
-            x.data_ptr(), y.data_ptr(), taps1d.ctypes.data, taps1d.ctypes.data, n, c, ih, iw, oh, ow,
-            ctypes.byref(xs), ctypes.byref(ys), ft, ft, up, down, padx0, pady0,
+            x.data_ptr(), y.data_ptr(), taps_x.ctypes.data, taps_y.ctypes.data, n, c, ih, iw, oh, ow,
+            ctypes.byref(xs), ctypes.byref(ys), fw, fh, up, down, padx0, pady0,
             int(bool(flip)), float(gain), capi.dtype_code(x.dtype), capi.stream_ptr(x.device))
     if rc == capi.SG3_E_NOKERNEL:
         return None
     capi.check(rc, 'sg3_upfirdn2d_sep')
     return y
+
+
+_rank1 = {}
+
+
+def _rank1_factors(taps2d):
+    """(taps_x, taps_y) when the dense filter is an outer product to fp32 rounding, else None.  `setup_filter` turns short 1-D
+    filters (fewer than 8 taps, e.g. the [1, 3, 3, 1] blur) into their dense outer product (upfirdn2d.py:103-105): running those as
+    two 1-D passes in one kernel costs 2 * taps instead of taps^2 multiply-adds per output and the same bytes."""
+    key = (taps2d.shape, taps2d.tobytes())
+    hit = _rank1.get(key)
+    if hit is None:
+        hit = False
+        fh, fw = taps2d.shape
+        if fh > 1 and fw > 1:
+            a = taps2d.astype(np.float64)
+            i, j = np.unravel_index(np.argmax(np.abs(a)), a.shape)
+            if a[i, j] != 0:
+                ty, tx = a[:, j], a[i, :] / a[i, j]
+                if np.max(np.abs(np.outer(ty, tx) - a)) <= 4e-7 * np.abs(a[i, j]):
+                    hit = (np.ascontiguousarray(tx, dtype=np.float32), np.ascontiguousarray(ty, dtype=np.float32))
+        if len(_rank1) > 256:
+            _rank1.clear()
+        _rank1[key] = hit
+    return hit or None
 
 
 _ONE = np.ones((1, 1), np.float32)
@@ -160,9 +186,14 @@ def _run(x, f, upx, upy, downx, downy, pads, flip, gain):
     if taps.ndim == 1 and taps.shape[0] == 1:
         taps = (taps * taps).reshape(1, 1)
     if taps.ndim == 2:
+        sep = _rank1_factors(taps) if (upx == upy and downx == downy) else None
+        if sep is not None:                    # a dense outer product (setup_filter of a short 1-D filter): two 1-D passes, one launch
+            y = upfirdn2d_sep_raw(x, sep[0], sep[1], upx, downx, px0, px1, py0, py1, flip, gain)
+            if y is not None:
+                return y
         return upfirdn2d_raw(x, taps, upx, upy, downx, downy, px0, px1, py0, py1, flip, gain)
     if upx == upy and downx == downy:          # one pass over HBM instead of the reference's two launches
-        y = upfirdn2d_sep_raw(x, taps, upx, downx, px0, px1, py0, py1, flip, gain)
+        y = upfirdn2d_sep_raw(x, taps, taps, upx, downx, px0, px1, py0, py1, flip, gain)
         if y is not None:
             return y
     y = upfirdn2d_raw(x, taps.reshape(1, -1), upx, 1, downx, 1, px0, px1, 0, 0, flip, 1.0)

@@ -382,6 +382,77 @@ def test_upfirdn2d_fast_paths(ops, case, dtype):
         assert rel_err(y2.float().cpu().numpy(), ref) < (TOL32 if dtype == torch.float32 else 4e-3)
 
 
+# ---------------------------------------------------------------------------------------------
+# The warp-streaming separable kernel (csrc/upfirdn2d_stream.cu): every alignment case is folded into its tap tables, so sweep
+# the padding residues (both parities / all four residues mod 4 per axis), row alignments (16- and 8-byte rows), tap counts of every
+# instantiation, crops, more than one strip (128 output columns) and more than one row chunk, views with a plane / row pitch.
+
+UPFIRDN_STREAM = [
+    # name, taps, up, down, padding, flip, shape, (row pitch, column offset) of the input view
+    ('up2_t12', 12, 2, 1, [11, 10, 11, 10], False, (2, 3, 36, 44), None),
+    ('up2_t12_odd_pad', 12, 2, 1, [10, 11, 12, 9], True, (1, 2, 40, 152), None),        # 304 output columns: 3 strips
+    ('up2_t4', 4, 2, 1, [2, 1, 2, 1], False, (2, 2, 70, 36), None),
+    ('up2_t8_crop', 8, 2, 1, [-3, 7, 5, -4], False, (1, 2, 300, 40), None),             # 5 row chunks of 128
+    ('up2_t24', 24, 2, 1, [23, 22, 21, 20], False, (1, 2, 34, 38), None),
+    ('up2_t11_8byte_rows', 11, 2, 1, [5, 5, 6, 4], False, (1, 3, 33, 42), None),         # rows 8-byte aligned only
+    ('down2_t12', 12, 1, 2, 0, False, (2, 3, 70, 88), None),
+    ('down2_t12_pads', 12, 1, 2, [1, 2, 3, 0], True, (1, 2, 90, 600), None),             # 296 output columns
+    ('down2_t12_pad2', 12, 1, 2, [2, 3, 1, 5], False, (1, 2, 64, 72), None),
+    ('down2_t12_pad3', 12, 1, 2, [3, 0, 2, 2], False, (1, 2, 64, 72), None),
+    ('down2_t4', 4, 1, 2, [1, 1, 1, 1], True, (2, 3, 64, 72), None),
+    ('down2_t8_rows', 8, 1, 2, [4, 3, 4, 3], False, (1, 2, 700, 36), None),              # 3 row chunks
+    ('down2_t12_2098', 12, 1, 2, 0, False, (1, 1, 150, 2098), None),                     # the reference-path shape: 8-byte rows
+    ('same_t12', 12, 1, 1, [6, 5, 6, 5], False, (2, 2, 33, 64), None),
+    ('same_t8_flip', 8, 1, 1, [4, 3, 4, 3], True, (2, 2, 33, 68), None),
+    ('same_t4_crop', 4, 1, 1, [-2, 4, 3, -1], False, (1, 2, 40, 260), None),
+    ('same_t5', 5, 1, 1, [2, 2, 2, 2], False, (1, 2, 40, 48), None),
+    ('up2_t12_pitched_view', 12, 2, 1, [11, 10, 11, 10], False, (2, 3, 36, 44), (52, 4)),
+    ('down2_t12_pitched_view', 12, 1, 2, [0, 0, 0, 0], False, (2, 2, 70, 86), (96, 2)),   # 8-byte aligned view
+]
+
+
+@pytest.mark.parametrize('case', UPFIRDN_STREAM, ids=[c[0] for c in UPFIRDN_STREAM])
+def test_upfirdn2d_stream_kernel(ops, case):
+    from oracle import sg3_oracle as orc
+    name, taps, up, down, padding, flip, shape, view = case
+    rng = np.random.RandomState(len(name) + taps)
+    f = rng.randn(taps).astype(np.float32)
+    x = rng.randn(*shape).astype(np.float32)
+    xt = cu(x)
+    if view is not None:                       # [N, C, H, W] window of a wider buffer: row pitch != W, base off the buffer start
+        pitch, ofs = view
+        buf = torch.full([shape[0], shape[1], shape[2], pitch], float('nan'), device='cuda')
+        buf[..., ofs:ofs + shape[3]] = xt
+        xt = buf[..., ofs:ofs + shape[3]]
+    before = ops.capi.lib().sg3_launch_count()
+    y = ops.upfirdn2d.upfirdn2d(xt, cu(f), up=up, down=down, padding=padding, flip_filter=flip, gain=up * up)
+    assert ops.capi.lib().sg3_launch_count() - before == 1
+    ref = orc.upfirdn2d(x, f, up=up, down=down, padding=padding, flip_filter=flip, gain=up * up)
+    assert y.shape == ref.shape
+    assert rel_err(y.cpu().numpy(), ref) < TOL32
+
+
+def test_upfirdn2d_rank1_dense_filters_run_separable(ops):
+    """`setup_filter([1, 3, 3, 1])` returns the dense 4 x 4 outer product (upfirdn2d.py:103-105); the op factors it back and runs
+    the separable kernel: filter2d / upsample2d / downsample2d with their default paddings, against the oracle's dense evaluation."""
+    from oracle import sg3_oracle as orc
+    f = ops.upfirdn2d.setup_filter([1, 3, 3, 1], device='cuda')
+    assert f.ndim == 2
+    assert ops.upfirdn2d._rank1_factors(ops.upfirdn2d.host_taps(f)) is not None
+    rng = np.random.RandomState(5)
+    x = rng.randn(2, 3, 48, 56).astype(np.float32)
+    fh = f.cpu().numpy()
+    for fn, kw, okw in ((ops.upfirdn2d.filter2d, {}, dict(up=1, down=1, padding=[2, 1, 2, 1])),
+                        (ops.upfirdn2d.upsample2d, dict(up=2), dict(up=2, down=1, padding=[2, 1, 2, 1], gain=4)),
+                        (ops.upfirdn2d.downsample2d, dict(down=2), dict(up=1, down=2, padding=[1, 1, 1, 1]))):
+        y = fn(cu(x), f, **kw)
+        ref = orc.upfirdn2d(x, fh, **okw)
+        assert y.shape == ref.shape
+        assert rel_err(y.cpu().numpy(), ref) < TOL32
+    g = rng.randn(4, 4).astype(np.float32)                     # a full-rank filter stays dense
+    assert ops.upfirdn2d._rank1_factors(g) is None
+
+
 def test_fused_backward_accumulates_bias_gradient(ops):
     """desc.ysum: the sign-READ kernels add the per-channel sum of their output (db of the backward pass) with fp32 atomics;
     the autograd path then skips the reduction over dx.  Compared with dx.sum of the create_graph path (torch reduction)."""
