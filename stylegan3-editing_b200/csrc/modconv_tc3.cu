@@ -318,7 +318,8 @@ int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int 
     p.wSlotBytes = p.wRows * BK3 * 4;
     // co-scheduling with the stencil kernel (sg3_modconv_set_smem_budget): plan inside a smaller shared-memory budget
     const int budget = sg3_conv_smem_budget();
-    if (!plan_tc3(p, budget > 0 && budget < kSmemLimit3 ? budget : kSmemLimit3)) return SG3_E_NOKERNEL;
+    // (a budget too small for any tile plan is ignored: the kernel then simply does not share its SM)
+    if (!(budget > 0 && budget < kSmemLimit3 && plan_tc3(p, budget)) && !plan_tc3(p, kSmemLimit3)) return SG3_E_NOKERNEL;
     p.tilesX = (p.OW + p.S - 1) / p.S;
     p.tilesY = (p.OH + p.R - 1) / p.R;
     p.tilesO = (O + 127) / 128;

@@ -7,7 +7,7 @@
 //   * one WARP owns a strip of 128 output columns (lane = 4 adjacent columns: one 128-bit store per lane and row, a warp
 //     writes 512 contiguous bytes) and streams down a chunk of rows; warps never synchronise with each other;
 //   * input rows arrive in a per-warp shared-memory ring by cp.async (16-byte copies when the rows allow it, else 8-byte;
-//     columns and rows outside the image are zero-filled by the copy itself), five rows in flight per warp;
+//     columns and rows outside the image are zero-filled by the copy itself), 4-12 rows in flight per warp;
 //   * the x pass reads the lane's window with 128-bit (64-bit for up 2) shared-memory loads and leaves 4 values in registers;
 //   * the y pass keeps a sliding window of x-filtered rows in REGISTERS (static slots: the loop body is unrolled over one
 //     rotation of the window), so the intermediate image of the reference never exists anywhere.
@@ -22,55 +22,92 @@
 
 namespace ufs {
 
-constexpr int kWarps = 4;
-constexpr int kRing = 6;             // staged input rows per warp (kRing - 1 copies in flight)
+// Tuning knobs (tools/build_ufs_variants.sh builds variants of this file only).  Defaults = the measured optimum on B200:
+// 4 CTAs of 4 warps per SM -- more resident warps mean more concurrent row streams in DRAM and measured SLOWER (12-tap up 2:
+// 0.69 of HBM at 6 CTAs / SM, 0.85 at 4) -- enforced through a lower bound on the dynamic shared memory of a CTA.
+#ifndef UFS_WARPS
+#define UFS_WARPS 4
+#endif
+#ifndef UFS_SMEM_MIN
+#define UFS_SMEM_MIN 46000
+#endif
+#ifndef UFS_CG16
+#define UFS_CG16 1
+#endif
+constexpr int kWarps = UFS_WARPS;
 constexpr int kV = 4;                // output columns per lane
-constexpr int kMaxNT = 16, kMaxWin = 16;
+constexpr int kMaxNT = 16, kMaxWin = 16;       // taps per output (even), y window rows
 
 template <int UP, int DOWN, int KP> struct Geo {
     static_assert((UP == 1 || UP == 2) && (DOWN == 1 || DOWN == 2) && !(UP == 2 && DOWN == 2), "factors");
     static constexpr int T = UP * KP;                                    // taps, zero padded
     static constexpr int XSTRIDE = 128 * DOWN / UP;                      // input columns between strips
     static constexpr int LSTEP = kV * DOWN / UP;                         // input columns between lanes (2 / 8 / 4)
-    static constexpr int NT = UP == 2 ? KP + 2 : T + 3;                  // static tap range per output (filter + alignment slack)
-    static constexpr int wlo(int v) { return UP == 2 ? v / 2 : v * DOWN; }          // first window position output v can touch
+    // Static tap range of output v over the lane window: positions w0(v) .. w0(v) + NT - 1.  It covers the filter plus the
+    // alignment slack (the 0-3 columns between the staged row's origin and the strip's first column, the polyphase branch) and
+    // starts on an EVEN position with an even length, so that a packed FMA takes two adjacent window values (one 64-bit half
+    // of a shared-memory load) times two adjacent taps: out = sum of the two halves of the packed accumulator.
+    static constexpr int w0(int v) { return UP == 2 ? 0 : (v * DOWN) & ~1; }
+    static constexpr int NT = UP == 2 ? ((KP + 3 + 1) / 2) * 2 : ((T + 3 + (DOWN == 1 ? 1 : 0) + 1) / 2) * 2;
     static constexpr int LG = UP == 2 ? 2 : 4;                           // floats per shared-memory load of the window
-    static constexpr int NWH = ((wlo(kV - 1) + NT + LG - 1) / LG) * LG;  // lane window (floats)
-    static constexpr int NINP = ((31 * LSTEP + (UP == 2 ? 2 : 0) + NWH + 3) / 4) * 4;   // staged floats per row
+    static constexpr int NWH = ((w0(kV - 1) + NT + LG - 1) / LG) * LG;   // lane window (floats)
+    static constexpr int NIN = ((31 * LSTEP + (UP == 2 ? 2 : 0) + NWH + 7) / 8) * 8;    // staged floats per row (even number of chunks)
+    // Down 2: lanes read their window 8 floats = two 16-byte chunks apart, so a 128-bit shared-memory load of a warp would touch
+    // every other chunk (bank conflicts).  The staged row is therefore DE-INTERLEAVED: even chunks first, odd chunks behind them.
+    // Load j of lane L wants chunk 2 L + j, which sits at position L + j / 2 of its half: consecutive lanes read consecutive
+    // 16-byte chunks, every load is one contiguous 512-byte access.  pidx() maps a float index of the row to its place; the
+    // copies that fill the row use it too (pieces are at most one chunk and chunk-aligned).
+    static constexpr bool SPLIT = DOWN == 2;
+    static __host__ __device__ constexpr int pidx(int i)
+    {
+        return SPLIT ? 4 * ((i >> 3) + ((i >> 2) & 1) * (NIN / 8)) + (i & 3) : i;
+    }
     static constexpr int WIN = UP == 2 ? KP + 1 : T;                     // y window (rows of x-filtered values)
     static constexpr int RPI = DOWN;                                     // input rows consumed per iteration
     static constexpr int PRIME = WIN - RPI;                              // rows consumed before the first output
     static constexpr int PERIOD = WIN / RPI;                             // iterations per rotation of the window
-    static_assert(WIN % RPI == 0 && NT <= kMaxNT && WIN <= kMaxWin, "window geometry");
+    // The loop body is unrolled over KU rotations of the window = ROWS_U input rows, and the ring of staged rows has RING slots
+    // with RING | ROWS_U: window slot AND ring slot of every row are then compile-time constants (no index arithmetic, the
+    // slot offsets are immediates of the shared-memory instructions).
+    static constexpr int KU = WIN < 5 ? 2 : 1;
+    static constexpr int ROWS_U = WIN * KU;
+    static constexpr int RING = ROWS_U <= 8 ? ROWS_U : (ROWS_U % 6 == 0 ? 6 : ROWS_U);
+    static constexpr int SLOT = NIN;                                     // floats per ring slot
+    static_assert(WIN % RPI == 0 && ROWS_U % RING == 0 && NT <= kMaxNT && WIN <= kMaxWin, "window geometry");
 };
 
 struct Params {
     const float* x; float* y;
     int N, C, inH, inW, outH, outW;
     long long xs0, xs1, xs2, ys0, ys1, ys2;      // element strides (unit stride along x)
-    float gain;
+    float gain;                                  // folded into tv by the host
     int stripsX, chunksY, chunkRows;
     long long totalWarps;
     int jA0;          // first staged input column of strip 0 (multiple of 4, may be negative)
     int c0;           // offset of lane 0's window inside the staged row (up 2: 0 or 2)
     int iBase0;       // input row at window position 0 of the chunk that starts at output row 0
-    int vecStore;     // output rows are 16-byte aligned: one 128-bit store per lane
-    float th[kV][kMaxNT];      // x pass: taps of output v over window positions wlo(v) .. wlo(v) + NT - 1
+    int vecStore;     // 2: output rows are 16-byte aligned (one 128-bit store per lane); 1: 8-byte aligned (two 64-bit stores); 0: scalar
+    float2 th[kV][kMaxNT / 2]; // x pass: taps of output v over window positions w0(v) .. w0(v) + NT - 1, in pairs
     float tv[2][kMaxWin];      // y pass: taps over the window rows (up 2: one table per output row of a pair)
 };
 
-template <int BYTES>
-__device__ __forceinline__ void cp_async(float* dst, const float* src, int srcBytes)
+// 16- or 8-byte global -> shared copy; `zero`: write zeros instead and do not touch the source (the ignore-src form of cp.async).
+// CG: 16-byte copies bypass L1 (.cg).  Measured on B200 (tools/build_ufs_variants.sh): .cg is worth 0.75 -> 0.91 of HBM for filter2d and
+// 0.76 -> 0.85 for the 12-tap up 2, but costs the down-2 kernels 0.77 -> 0.63 (their strips re-read the row halo from L1).
+template <int BYTES, bool CG>
+__device__ __forceinline__ void cp_async(float* dst, const float* src, bool zero)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    if (BYTES == 16)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(srcBytes) : "memory");
+    if (BYTES == 16 && CG)
+        asm volatile("{\n\t.reg .pred z;\n\tsetp.ne.b32 z, %2, 0;\n\tcp.async.cg.shared.global [%0], [%1], 16, z;\n\t}" ::"r"(d), "l"(src), "r"((int)zero) : "memory");
+    else if (BYTES == 16)
+        asm volatile("{\n\t.reg .pred z;\n\tsetp.ne.b32 z, %2, 0;\n\tcp.async.ca.shared.global [%0], [%1], 16, z;\n\t}" ::"r"(d), "l"(src), "r"((int)zero) : "memory");
     else
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(srcBytes) : "memory");
+        asm volatile("{\n\t.reg .pred z;\n\tsetp.ne.b32 z, %2, 0;\n\tcp.async.ca.shared.global [%0], [%1], 8, z;\n\t}" ::"r"(d), "l"(src), "r"((int)zero) : "memory");
 }
 
 template <int UP, int DOWN, int KP, int COPY>
-__global__ void __launch_bounds__(kWarps * 32) kernel(const __grid_constant__ Params p)
+__global__ void __launch_bounds__(kWarps * 32, (KP <= 6 ? 4 : 3) * 4 / kWarps) kernel(const __grid_constant__ Params p)
 {
     typedef Geo<UP, DOWN, KP> G;
     extern __shared__ __align__(16) float smem[];
@@ -91,47 +128,54 @@ __global__ void __launch_bounds__(kWarps * 32) kernel(const __grid_constant__ Pa
     const int iBase = p.iBase0 + chunk * (p.chunkRows * DOWN / UP);
     const int nIt = UP == 2 ? (chs + 1) >> 1 : chs;
     const int nRows = G::PRIME + G::RPI * nIt;
-    float* ring = smem + warp * (kRing * G::NINP);
+    float* ring = smem + warp * (G::RING * G::SLOT);
 
-    // ---- stage input row iBase + r into ring slot `slot` (one commit group per call, empty past the last row) ----
-    // Per lane and 16- / 8-byte piece of the row, everything that does not depend on the row is computed once: the column
-    // (clamped into the image so that the source address is always valid and aligned) and the bytes of the piece that lie
-    // inside the image; a row outside the image copies 0 bytes (cp.async zero-fills the rest of the piece).
+    // ---- staging: input row iBase + r -> ring slot r % RING, one commit group per row (empty past the last row) ----
+    // Per lane and 16- / 8-byte piece of the row, everything that does not depend on the row is computed once: where the piece
+    // lands (pidx), its source column (clamped into the image so that the address is always valid and aligned) and how many of its
+    // bytes lie inside the image; a row outside the image copies 0 bytes (cp.async zero-fills the rest of a piece).  Lanes
+    // without a piece copy 0 bytes into the scratch chunk of the slot, so the copy instructions need no predicate.
     constexpr int CE = COPY / 4;                                  // floats per piece
-    constexpr int NF = (G::NINP / CE + 31) / 32;                  // pieces per lane
-    int colC[NF], nbC[NF];
+    constexpr int NF = (G::NIN / CE + 31) / 32;                   // pieces per lane
+    float* dstC[NF];
+    unsigned srcC[NF];
+    unsigned inside = 0;                                          // bit f: piece f of this lane lies inside the image (inW % CE == 0: never partly)
 #pragma unroll
     for (int f = 0; f < NF; f++) {
         const int e = CE * (lane + 32 * f), j = jA + e;
-        nbC[f] = (e < G::NINP && j >= 0) ? min(max(p.inW - j, 0), CE) * 4 : 0;
-        colC[f] = nbC[f] ? j : 0;
-        if (e >= G::NINP) nbC[f] = -1;                            // this lane has no piece f
+        const bool in = e < G::NIN && j >= 0 && j < p.inW;
+        inside |= in ? 1u << f : 0u;
+        srcC[f] = in ? 4u * (unsigned)j : 0u;
+        dstC[f] = ring + (e < G::NIN ? G::pidx(e) : 0);
     }
-    auto issue = [&](int r, int slot) {
-        if (r < nRows) {
-            const int i = iBase + r;
-            const int rowMask = (i >= 0 && i < p.inH) ? -1 : 0;
-            const float* src = xp + (long long)min(max(i, 0), p.inH - 1) * p.xs2;
-            float* dst = ring + slot * G::NINP + CE * lane;
+    // only the last piece index can be missing for some lanes (32 (NF - 1) CE < NIN by construction)
+    const bool hasLast = CE * (lane + 32 * (NF - 1)) < G::NIN;
+    int rI = 0;                                                   // next row to stage; rows are staged strictly in order
+    const char* pI = reinterpret_cast<const char*>(xp + (long long)iBase * p.xs2);      // its address (not dereferenced outside the image)
+    const long long rowBytes = p.xs2 * 4;
+    auto issue = [&](int slot) {
+        if (rI < nRows) {
+            const bool ok = (unsigned)(iBase + rI) < (unsigned)p.inH;
+            const unsigned live = ok ? inside : 0u;
+            const char* src = ok ? pI : reinterpret_cast<const char*>(xp);
 #pragma unroll
             for (int f = 0; f < NF; f++)
-                if (nbC[f] >= 0) cp_async<COPY>(dst + CE * 32 * f, src + colC[f], nbC[f] & rowMask);
+                if (f < NF - 1 || hasLast)
+                    cp_async<COPY, UFS_CG16 != 0 && DOWN == 1>(dstC[f] + slot * G::SLOT, reinterpret_cast<const float*>(src + srcC[f]), !((live >> f) & 1u));
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
+        rI++;
+        pI += rowBytes;
     };
+#pragma unroll
+    for (int r = 0; r < G::RING - 1; r++) issue(r);
 
-    int rNext = 0, slotIssue = 0, slotUse = 0;
-#pragma unroll 1
-    for (; rNext < kRing - 1; rNext++) {
-        issue(rNext, slotIssue);
-        slotIssue = slotIssue + 1 == kRing ? 0 : slotIssue + 1;
-    }
-
-    // ---- x pass of the next staged row: 4 values per lane ----
-    auto xrow = [&](float (&h)[kV]) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(kRing - 2) : "memory");
+    // ---- x pass of the next staged row (ring slot `slot`): 4 values per lane; then refill the slot read one row ago ----
+    const float* lds0 = ring + (UP == 2 ? p.c0 + G::LSTEP * lane : (G::SPLIT ? 4 * lane : G::LSTEP * lane));
+    auto xrow = [&](float (&h)[kV], int slot) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(G::RING - 2) : "memory");
         __syncwarp();
-        const float* row = ring + slotUse * G::NINP + p.c0 + G::LSTEP * lane;
+        const float* row = lds0 + slot * G::SLOT;
         float xin[G::NWH];
         if (UP == 2) {
 #pragma unroll
@@ -142,75 +186,79 @@ __global__ void __launch_bounds__(kWarps * 32) kernel(const __grid_constant__ Pa
         } else {
 #pragma unroll
             for (int w = 0; w < G::NWH; w += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(row + w);
+                // split layout: chunk 2 L + w / 4 of the row sits at position L + w / 8 of its half (pidx with the lane part in lds0)
+                const float4 t = *reinterpret_cast<const float4*>(row + (G::SPLIT ? G::pidx(w) : w));
                 xin[w] = t.x; xin[w + 1] = t.y; xin[w + 2] = t.z; xin[w + 3] = t.w;
             }
         }
-        slotUse = slotUse + 1 == kRing ? 0 : slotUse + 1;
-        // the slot read one row ago is free now (every lane has passed the __syncwarp above): refill it
-        issue(rNext, slotIssue);
-        rNext++;
-        slotIssue = slotIssue + 1 == kRing ? 0 : slotIssue + 1;
+        // every lane has passed the __syncwarp above, so the slot read one row ago is free: refill it
+        issue((slot + G::RING - 1) % G::RING);
 #pragma unroll
         for (int v = 0; v < kV; v++) {
-            float acc = 0.f;
+            float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int t = 0; t < G::NT; t++) acc = fmaf(xin[G::wlo(v) + t], p.th[v][t], acc);
-            h[v] = acc;
+            for (int t = 0; t < G::NT; t += 2)
+                acc = __ffma2_rn(make_float2(xin[G::w0(v) + t], xin[G::w0(v) + t + 1]), p.th[v][t >> 1], acc);
+            h[v] = acc.x + acc.y;
         }
     };
 
-    auto store = [&](int oy, const float (&o)[kV]) {
-        if (oy >= p.outH || ox >= p.outW) return;
-        float* q = yp + (long long)oy * p.ys2 + ox;
-        if (p.vecStore && ox + 3 < p.outW) {
-            *reinterpret_cast<float4*>(q) = make_float4(o[0], o[1], o[2], o[3]);
-        } else {
+    // ---- output rows leave in order; how a lane stores is decided once ----
+    //   0: nothing (column outside the image), 1: one 128-bit store, 2: two 64-bit stores (rows aligned to 8 bytes only, e.g. 2098
+    //   columns), 3: scalar stores with a bound check (image edge, or rows without alignment)
+    const int storeMode = ox >= p.outW ? 0 : (ox + 3 < p.outW && p.vecStore == 2) ? 1 : (ox + 3 < p.outW && p.vecStore == 1) ? 2 : 3;
+    // The address of every row is computed afresh from a row counter: a running pointer updated in place right after the store
+    // waits for the store to release its address register (measured: the largest single stall of the kernel).
+    float* const y0 = yp + (long long)oy0 * p.ys2 + ox;
+    int orow = 0;
+    auto store = [&](const float2 (&o)[2]) {
+        float* yq = y0 + (long long)orow * p.ys2;
+        if (storeMode == 1) {
+            *reinterpret_cast<float4*>(yq) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+        } else if (storeMode == 2) {
+            *reinterpret_cast<float2*>(yq) = o[0];
+            *reinterpret_cast<float2*>(yq + 2) = o[1];
+        } else if (storeMode == 3) {
+            const float e[kV] = {o[0].x, o[0].y, o[1].x, o[1].y};
 #pragma unroll
             for (int v = 0; v < kV; v++)
-                if (ox + v < p.outW) q[v] = o[v];
+                if (ox + v < p.outW) yq[v] = e[v];
         }
+        orow++;
     };
 
+    // ---- main loop.  Iteration t consumes RPI input rows into static window slots and, once the window is full (t >= LEAD),
+    //      produces the output row(s) m = t - LEAD.  The y taps carry the gain.
+    constexpr int LEAD = G::PRIME / G::RPI;
+    constexpr int ITS_U = G::ROWS_U / G::RPI;                    // iterations per unrolled body
+    static_assert(G::PRIME % G::RPI == 0, "lead-in");
     float win[G::WIN][kV];
-#pragma unroll
-    for (int r = 0; r < G::PRIME; r++) xrow(win[r]);
-
+    const int nT = nIt + LEAD;
 #pragma unroll 1
-    for (int m0 = 0; m0 < nIt; m0 += G::PERIOD) {
+    for (int tb = 0; tb < nT; tb += ITS_U) {
 #pragma unroll
-        for (int q = 0; q < G::PERIOD; q++) {
-            const int m = m0 + q;
-            if (m < nIt) {
+        for (int q = 0; q < ITS_U; q++) {
+            const int t = tb + q;
+            if (t < nT) {
 #pragma unroll
-                for (int j = 0; j < G::RPI; j++) xrow(win[(G::RPI * q + G::PRIME + j) % G::WIN]);
-                if (UP == 2) {
-                    float a[kV], b[kV];
-#pragma unroll
-                    for (int v = 0; v < kV; v++) { a[v] = 0.f; b[v] = 0.f; }
+                for (int j = 0; j < G::RPI; j++)
+                    xrow(win[(G::RPI * q + j) % G::WIN], (G::RPI * q + j) % G::RING);
+                if (t >= LEAD) {
+                    // y pass: packed FMAs over column pairs (v, v + 1), the tap broadcast to both halves.  Window row w of this
+                    // output sits in slot (RPI q + RPI + w) % WIN (the rows just written are its last ones).
+                    float2 a[2], b[2];
+                    a[0] = a[1] = b[0] = b[1] = make_float2(0.f, 0.f);
 #pragma unroll
                     for (int w = 0; w < G::WIN; w++)
 #pragma unroll
-                        for (int v = 0; v < kV; v++) {
-                            const float hv = win[(q + w) % G::WIN][v];
-                            a[v] = fmaf(hv, p.tv[0][w], a[v]);
-                            b[v] = fmaf(hv, p.tv[1][w], b[v]);
+                        for (int h = 0; h < 2; h++) {
+                            const float* r = win[(G::RPI * q + G::RPI + w) % G::WIN];
+                            const float2 hv = make_float2(r[2 * h], r[2 * h + 1]);
+                            a[h] = __ffma2_rn(hv, make_float2(p.tv[0][w], p.tv[0][w]), a[h]);
+                            if (UP == 2) b[h] = __ffma2_rn(hv, make_float2(p.tv[1][w], p.tv[1][w]), b[h]);
                         }
-#pragma unroll
-                    for (int v = 0; v < kV; v++) { a[v] *= p.gain; b[v] *= p.gain; }
-                    store(oy0 + 2 * m, a);
-                    if (2 * m + 1 < chs) store(oy0 + 2 * m + 1, b);
-                } else {
-                    float a[kV];
-#pragma unroll
-                    for (int v = 0; v < kV; v++) a[v] = 0.f;
-#pragma unroll
-                    for (int w = 0; w < G::WIN; w++)
-#pragma unroll
-                        for (int v = 0; v < kV; v++) a[v] = fmaf(win[(G::RPI * q + w) % G::WIN][v], p.tv[0][w], a[v]);
-#pragma unroll
-                    for (int v = 0; v < kV; v++) a[v] *= p.gain;
-                    store(oy0 + m, a);
+                    store(a);
+                    if (UP == 2 && 2 * (t - LEAD) + 1 < chs) store(b);
                 }
             }
         }
@@ -234,7 +282,7 @@ int launch(Params& p, const float* fx, const float* fy, int padx0, int pady0, cu
         for (int t = 0; t < kMaxNT; t++) {
             float tap = 0.f;
             if (t < G::NT) {
-                const int w = G::wlo(v) + t;                   // window position
+                const int w = G::w0(v) + t;                    // window position
                 if (UP == 2) {
                     const int mid = midS + v, a0 = pos_mod(-mid, 2);
                     const int off = (mid + a0) / 2 - jFirst0 + s;        // exact division: mid + a0 is even
@@ -245,7 +293,7 @@ int launch(Params& p, const float* fx, const float* fy, int padx0, int pady0, cu
                     if (k >= 0 && k < G::T) tap = fx[k];
                 }
             }
-            p.th[v][t] = tap;
+            if (t & 1) p.th[v][t >> 1].y = tap; else p.th[v][t >> 1].x = tap;
         }
     // ---- y pass ----
     for (int a = 0; a < 2; a++)
@@ -263,18 +311,22 @@ int launch(Params& p, const float* fx, const float* fy, int padx0, int pady0, cu
         p.iBase0 = -pady0;
         for (int k = 0; k < G::T; k++) p.tv[0][k] = fy[k];
     }
+    for (int a = 0; a < 2; a++)
+        for (int w = 0; w < kMaxWin; w++) p.tv[a][w] *= p.gain;           // the gain rides on the y taps
     // ---- work split: strips of 128 columns x chunks of rows; shrink the chunks until the GPU is covered ----
     p.stripsX = (p.outW + 127) / 128;
     const long long planes = (long long)p.N * p.C;
+    // chunks of 128 output rows; smaller ones (down to a y halo of ~10 %) until the warps fill several waves of the GPU
     int chunkRows = 128;
-    const long long want = (long long)sg3_sm_count() * 16 * 2;
-    while (chunkRows > 32 && planes * p.stripsX * ((p.outH + chunkRows - 1) / chunkRows) < want) chunkRows >>= 1;
+    const int minRows = G::T >= 8 ? 64 : 32;
+    const long long want = (long long)sg3_sm_count() * 24 * 4;
+    while (chunkRows > minRows && planes * p.stripsX * ((p.outH + chunkRows - 1) / chunkRows) < want) chunkRows >>= 1;
     p.chunkRows = chunkRows;
     p.chunksY = (p.outH + chunkRows - 1) / chunkRows;
     p.totalWarps = planes * p.stripsX * p.chunksY;
     const long long ctas = (p.totalWarps + kWarps - 1) / kWarps;
     if (ctas > 0x7fffffffLL) return SG3_E_TOOLARGE;
-    const int smemBytes = kWarps * kRing * G::NINP * 4;
+    const int smemBytes = kWarps * G::RING * G::SLOT * 4 > UFS_SMEM_MIN ? kWarps * G::RING * G::SLOT * 4 : UFS_SMEM_MIN;
     auto kern = kernel<UP, DOWN, KP, COPY>;
     static Sg3DeviceOnce once;
     const cudaError_t attrErr = once.run([&] {
@@ -312,9 +364,10 @@ int sg3_upfirdn2d_stream(const float* x, float* y, int N, int C, int inH, int in
         const int e = bytes / 4;
         return ((uintptr_t)base % bytes) == 0 && st[0] % e == 0 && st[1] % e == 0 && st[2] % e == 0;
     };
-    const int copyBytes = aligned(x, xs, 16) ? 16 : aligned(x, xs, 8) ? 8 : 0;     // granularity of the global -> shared copies
+    // granularity of the global -> shared copies: rows aligned to it and made of whole pieces
+    const int copyBytes = (aligned(x, xs, 16) && inW % 4 == 0) ? 16 : (aligned(x, xs, 8) && inW % 2 == 0) ? 8 : 0;
     if (!copyBytes) return SG3_E_NOKERNEL;                                          // odd row pitch: the tiled kernel
-    p.vecStore = aligned(y, ys, 16) ? 1 : 0;
+    p.vecStore = aligned(y, ys, 16) ? 2 : aligned(y, ys, 8) ? 1 : 0;
 #define SG3_UFS(U, D, K) return copyBytes == 16 ? ufs::launch<U, D, K, 16>(p, fx, fy, padx0, pady0, stream) \
                                                 : ufs::launch<U, D, K, 8>(p, fx, fy, padx0, pady0, stream)
     if (up == 2) {

@@ -380,6 +380,61 @@ def test_graphed_synthesis_matches_eager(pkg):
     assert torch.equal(gs(ws2), ref2)
 
 
+@pytest.mark.parametrize('math', ['fp32', 'tf32'])
+@pytest.mark.parametrize('name', ['tinyR', 'tinyT'])
+def test_pipelined_synthesis_matches_plain_forward(pkg, name, math):
+    """networks.PipelinedSynthesis (micro-batches on two streams: convs on a high-priority stream with the shared-memory budget,
+    stencils on a normal one): the image equals the plain forward.  Every op is per sample; the only cross-sample term is the
+    batch-global style RMS (networks_stylegan3.py:42), which cancels under demodulation up to its 1e-8 epsilon -- so fp32 math agrees
+    to rounding, and with TF32 the few weights whose rounding flips stay inside the TF32 network tolerance.  Also: the golden image,
+    ragged micro-batches, `out=`, and the budget being restored."""
+    from sg3_b200 import capi, modulated_conv, networks
+    G, g = _build(pkg, name)
+    ws1 = cu(g.z[name + '/ws'])
+    ws = torch.cat([ws1, ws1.flip(0) * 0.9, ws1 * 1.1])[:5].contiguous()            # batch 5: ragged micro-batches
+    modulated_conv.set_math(math)
+    try:
+        with torch.no_grad():
+            ref = G.synthesis(ws, noise_mode='const', force_fp32=True)
+        tol = 1e-5 if math == 'fp32' else 1e-2
+        for M in (2, 3, 8):
+            pipe = networks.PipelinedSynthesis(G.synthesis, micro_batches=M)
+            img = pipe(ws, noise_mode='const', force_fp32=True)
+            torch.cuda.synchronize()
+            assert img.shape == ref.shape and img.dtype == torch.float32
+            assert rel_err(img.cpu().numpy(), ref.cpu().numpy()) < tol, (M, math)
+        out = torch.full_like(ref, float('nan'))
+        res = networks.PipelinedSynthesis(G.synthesis, micro_batches=2)(ws, out=out, noise_mode='const', force_fp32=True)
+        assert res is out and rel_err(out.cpu().numpy(), ref.cpu().numpy()) < tol
+        if math == 'fp32':
+            n = ws1.shape[0]
+            assert rel_err(out[:n].cpu().numpy(), g.z[name + '/img']) < 1e-4        # the golden image of the reference
+        assert capi.lib().sg3_modconv_set_smem_budget(0) == 0                         # restored after every call
+    finally:
+        modulated_conv.set_math(None)
+
+
+def test_conv_smem_budget_keeps_results(pkg):
+    """sg3_modconv_set_smem_budget only changes the depth of the operand ring / the tile plan: same numbers for 1x1 and 3x3 convs."""
+    from sg3_b200 import capi, modulated_conv
+    rng = np.random.RandomState(3)
+    for (I, O, H, k, pad) in ((96, 80, 36, 1, 0), (200, 300, 20, 1, 0), (40, 48, 36, 3, 2), (64, 130, 20, 3, 2)):
+        x = cu(rng.randn(2, I, H, H).astype(np.float32))
+        w = cu(rng.randn(O, I, k, k).astype(np.float32))
+        s = cu(rng.randn(2, I).astype(np.float32))
+        modulated_conv.set_math('tf32')
+        try:
+            y0 = modulated_conv.modulated_conv2d(x, w, s, padding=pad)
+            prev = capi.lib().sg3_modconv_set_smem_budget(100 * 1024)
+            assert prev == 0
+            y1 = modulated_conv.modulated_conv2d(x, w, s, padding=pad)
+            assert capi.lib().sg3_modconv_set_smem_budget(0) == 100 * 1024
+        finally:
+            modulated_conv.set_math(None)
+            capi.lib().sg3_modconv_set_smem_budget(0)
+        assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 1e-6, (I, O, H, k)
+
+
 @pytest.mark.parametrize('shape', TC_CASES, ids=['x'.join(map(str, s)) for s in TC_CASES])
 def test_modconv_tc_f16_vs_oracle(pkg, shape):
     """fp16 tensor-core contraction (fp16 activations and weights, fp32 accumulate, fp16 store) vs the oracle on the same
