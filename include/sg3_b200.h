@@ -134,7 +134,8 @@ int sg3_upfirdn2d(const void* x, void* y, const float* f,
 /* Separable filter with the same up / down factor on both axes in ONE pass over HBM (the reference and sg3_upfirdn2d run
  * it as two launches with an intermediate image, upfirdn2d.py:241-246).  fx [fW], fy [fH]: host taps (NULL = 1);
  * power-of-two factor 1 / 2 / 4 on one side, <= 24 taps per polyphase branch, W-contiguous f32 / f16 tensors; otherwise
- * SG3_E_NOKERNEL (call sg3_upfirdn2d twice). */
+ * SG3_E_NOKERNEL (call sg3_upfirdn2d twice).  f32 tensors with factor 1 or 2, <= 12 taps per branch and rows aligned to 8 bytes run the
+ * warp-streaming kernel (upfirdn2d_stream.cu: every byte of x and y crosses HBM once, 0.68-0.94 of the copy bandwidth); the rest a CTA-tile kernel. */
 int sg3_upfirdn2d_sep(const void* x, void* y, const float* fx, const float* fy,
                       int N, int C, int inH, int inW, int outH, int outW,
                       const int64_t xStride[4], const int64_t yStride[4],
