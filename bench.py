@@ -332,6 +332,29 @@ def run_ours(args):
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
 
+    # ---- extra (not the headline): the same step through networks.PipelinedSynthesis (convs and stencils of two micro-batches
+    #      co-scheduled on the SMs, profiles/r02_overlap.md); a few steps, CUDA events, max over ranks ----
+    pipelined = None
+    try:
+        pipe2 = networks.PipelinedSynthesis(G.synthesis, micro_batches=2)
+        out_img = torch.empty([B, 3, 1024, 1024], dtype=torch.float32, device=dev)
+        for _ in range(2):
+            pipe2(ws, out=out_img, noise_mode='const', force_fp32=True)
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_pipe = min(args.steps, 5)
+        p0.record()
+        for _ in range(n_pipe):
+            pipe2(ws, out=out_img, noise_mode='const', force_fp32=True)
+        p1.record()
+        barrier()
+        pipe_ms = max_over_ranks(p0.elapsed_time(p1))
+        pipelined = dict(value=world * B * n_pipe / (pipe_ms * 1e-3), unit='images/s', ms_per_step=pipe_ms / n_pipe, steps=n_pipe, micro_batches=2,
+                         note='opt-in networks.PipelinedSynthesis; the headline `value` is the plain forward')
+        del out_img
+    except Exception as e:            # never lose the bench line over the secondary figure
+        pipelined = dict(error=repr(e))
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -404,6 +427,7 @@ def run_ours(args):
                  h2d_bytes_per_step=int(ws_host.numel() * 4), d2h_bytes_per_step=int(img_host[0].numel() * 4)),
         gpu_launches=int(launches),
         conv=conv,
+        pipelined=pipelined,
         # `bound` names the roof `achieved` / `peak` / `frac` are quoted against (the contract's HBM roof); the roof that actually
         # binds this kernel with fp32 SIMT math is the FP32 pipe: `binds` + the flat fp32_pipe_* keys
         roofline=dict(bound='hbm', achieved=achieved, peak=hbm_peak, unit='GB/s', frac=achieved / hbm_peak,

@@ -21,6 +21,8 @@ except Exception as e:
     print(sys.argv[1], 'unparsed', e)
 PY
 done
+python tools/prof_ops.py > $O/r02_final_streaming_ops.txt 2>&1; tail -6 $O/r02_final_streaming_ops.txt
+[ -n "$SKIP_NCU" ] && exit 0
 cap() { ncu --set full --import-source on --clock-control none -k kernel -s $3 -c 1 -o $O/r02_final_$1 python tools/prof_flrelu.py $2 2 bwd > /dev/null 2>&1; }
 cap L11_fwd L11 3; cap L10_fwd L10 3; cap L12_fwd L12 3; cap L11_write L11 4; cap L11_bwd L11 5; cap L10_bwd L10 5
 ls $O/r02_final_*.ncu-rep
