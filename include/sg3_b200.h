@@ -59,6 +59,8 @@ unsigned long long sg3_launch_count(void);    /* kernels launched by this librar
  * signs: uint8 [N][C][sH][sWb], 4 pixels per byte along x, pixel k at bits 2k..2k+1,
  * code 1 = negative (scaled by slope), 2 = clamped (gradient 0)   (.cu:494-519).
  * ---------------------------------------------------------------------- */
+#define SG3_FLRELU_ROUND_TF32 1
+
 typedef struct sg3_flrelu_desc {
     const void* x;   void* y;   const void* b;   uint8_t* signs;
     const float* fu; const float* fd;            /* host */
@@ -75,7 +77,10 @@ typedef struct sg3_flrelu_desc {
     int32_t sH, sWb;                             /* sign tensor height, width in BYTES */
     int32_t sx, sy;                              /* sign offset added to upsampled coords */
     int32_t dtype;                               /* SG3_F32 / SG3_F16 */
-    int32_t reserved;
+    int32_t flags;                               /* bit 0 (SG3_FLRELU_ROUND_TF32, f32 only): round every output to the nearest TF32 value
+                                                    (ties away, as cvt.rna).  For outputs that feed a TF32 tensor-core convolution: the
+                                                    tensor core TRUNCATES fp32 operands to TF32, rounding in the producer halves that
+                                                    error (what cuDNN's TF32 kernels do on load).  Honoured by the fused forward kernels. */
     float*  ysum;                                /* optional f32 [C]: the kernel ADDS sum_{n,h,w} y[n][c][h][w] (fp32 atomics;
                                                     zero it first).  In the backward pass y = dx and this is the bias gradient
                                                     (filtered_lrelu.py:268 computes dx.sum([0,2,3]) in a second pass).  NULL = off;

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get('SG3_B200_LIB') or os.path.join(_HERE, 'libsg3_b200.so
 SG3_F32, SG3_F16, SG3_F64 = 0, 1, 2
 SG3_E_INVALID, SG3_E_NOKERNEL, SG3_E_TOOLARGE = -1, -2, -3
 SIGNS_NONE, SIGNS_WRITE, SIGNS_READ = 0, 1, 2
+FLRELU_ROUND_TF32 = 1
 
 c_i64x4 = ctypes.c_int64 * 4
 
@@ -31,7 +32,7 @@ class FlreluDesc(ctypes.Structure):
         ('gain', ctypes.c_float), ('slope', ctypes.c_float), ('clamp', ctypes.c_float),
         ('flip', ctypes.c_int32), ('signMode', ctypes.c_int32),
         ('sH', ctypes.c_int32), ('sWb', ctypes.c_int32), ('sx', ctypes.c_int32), ('sy', ctypes.c_int32),
-        ('dtype', ctypes.c_int32), ('reserved', ctypes.c_int32),
+        ('dtype', ctypes.c_int32), ('flags', ctypes.c_int32),
         ('ysum', ctypes.c_void_p),
     ]
 

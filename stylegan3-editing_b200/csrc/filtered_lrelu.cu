@@ -204,6 +204,7 @@ SG3_EXPORT int sg3_filtered_lrelu(const sg3_flrelu_desc* d, void* stream)
         const long long es = d->dtype == SG3_F32 ? 4 : 2;
         p.vecStore = d->yStride[3] == es && ((uintptr_t)d->y % (2 * es)) == 0 && d->yStride[2] % (2 * es) == 0 &&
                      d->yStride[1] % (2 * es) == 0 && d->yStride[0] % (2 * es) == 0;
+        if ((d->flags & SG3_FLRELU_ROUND_TF32) && d->dtype == SG3_F32) p.vecStore |= 2;      // bit 1: outputs rounded to TF32
     }
 
     // Strip decomposition: TW-column strips (58 / 56 outputs for up 2 / 4); rows are chunked only when there are too few strips to

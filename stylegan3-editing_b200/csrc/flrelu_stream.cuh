@@ -107,7 +107,7 @@ struct Params {
     float gain, slope, clamp;
     int sH, sWb, sx, sy;
     int stripsX, chunksY, chunkRows;
-    int vecStore;                      // y has unit pixel stride and 8-byte (fp32) / 4-byte (fp16) aligned rows: paired stores
+    int vecStore;                      // bit 0: y has unit pixel stride and 8-byte (fp32) / 4-byte (fp16) aligned rows: paired stores; bit 1: round outputs to TF32
     long long totalStrips;
     SG3_TRACE_FIELD
     // tap tables are laid out for 128-bit uniform loads (LDCU.128): rows of 8 / 12 floats, 16-byte aligned
@@ -133,6 +133,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+
+// nearest TF32 value, ties away from zero (= cvt.rna.tf32.f32) as two integer operations: the FMA pipe is the busy one
+__device__ __forceinline__ float round_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 
 __device__ __forceinline__ float2 ffma2(float2 a, float t, float2 c) { return __ffma2_rn(a, make_float2(t, t), c); }
 __device__ __forceinline__ float2 fmul2(float2 a, float t) { return __fmul2_rn(a, make_float2(t, t)); }
@@ -603,8 +606,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TMA ? SG3_FL_MINCTAS : (3 *
             acc[S4][0] = acc[S4][1] = acc[S5][0] = acc[S5][1] = make_float2(0.f, 0.f);
         }
         const int oA = 2 * g - 5;                         // rows oA and oA + 1 retire; both valid except at the chunk's ends
+        if (sizeof(T) == 4 && (p.vecStore & 2)) {         // SG3_FLRELU_ROUND_TF32: the consumer is a TF32 tensor-core conv
+            a0 = round_tf32(a0); a1 = round_tf32(a1); b0 = round_tf32(b0); b1 = round_tf32(b1);
+        }
         if (laneStores) {
-            if (p.vecStore && two) {
+            if ((p.vecStore & 1) && two) {
                 if (oA >= 0 && oA < chs) {
                     if (sizeof(T) == 4) *(float2*)outRow = make_float2(a0, a1);
                     else *(__half2*)outRow = __floats2half2_rn(a0, a1);

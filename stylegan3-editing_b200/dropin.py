@@ -114,4 +114,9 @@ def patch_modulated_conv(target=None):
             m._sg3_b200_original_modulated_conv2d = m.modulated_conv2d
             m.modulated_conv2d = modulated_conv2d
             done.append(m.__name__)
+    if done:
+        # the patched layers' convolutions now read their inputs with TF32 tensor cores (when the math mode is 'tf32'): have the
+        # stencils that produce those inputs round them to nearest (filtered_lrelu.tf32_rounded_outputs)
+        from . import filtered_lrelu
+        filtered_lrelu.round_for_tf32_convs = True
     return done

@@ -70,11 +70,12 @@ def _act_inplace(y, si, sx, sy, gain, slope, clamp, write_signs):
     return s if write_signs else None
 
 
-def _fused(x, fu, fd, b, si, sx, sy, cfg, write_signs, ysum=None, pitched_out=False):
+def _fused(x, fu, fd, b, si, sx, sy, cfg, write_signs, ysum=None, pitched_out=False, round_tf32=False):
     """Try the fused kernel.  Returns (y, signs_written) or None when no specialisation exists.
     `ysum` (float32 [C], zeroed): the kernel adds the per-channel sum of y -- the bias gradient when y = dx.
     `pitched_out`: fp32 outputs whose width is not a multiple of 4 are written with a 16-byte row pitch (returned as a view):
-    the gradient wrt a 3x3 conv's output then feeds the tensor-core input-gradient conv without a re-pitching copy."""
+    the gradient wrt a 3x3 conv's output then feeds the tensor-core input-gradient conv without a re-pitching copy.
+    `round_tf32`: fp32 outputs are rounded to the nearest TF32 value (see `tf32_rounded_outputs`)."""
     up, down, px0, px1, py0, py1, gain, slope, clamp, flip = cfg
     if x.dtype not in (torch.float16, torch.float32):
         return None
@@ -120,6 +121,7 @@ def _fused(x, fu, fd, b, si, sx, sy, cfg, write_signs, ysum=None, pitched_out=Fa
     d.sH, d.sWb = (s.shape[2], s.shape[3]) if s is not None else (0, 0)
     d.sx, d.sy = int(sx), int(sy)
     d.dtype = capi.dtype_code(x.dtype)
+    d.flags = capi.FLRELU_ROUND_TF32 if (round_tf32 and x.dtype == torch.float32) else 0
     d.ysum = ysum.data_ptr() if ysum is not None else None
     with torch.cuda.device(x.device):
         rc = L.sg3_filtered_lrelu(ctypes.byref(d), capi.stream_ptr(x.device))
@@ -155,7 +157,7 @@ class _FilteredLRelu(torch.autograd.Function):
         strides = [x.stride(i) for i in range(x.ndim) if x.size(i) > 1]
         if any(a < c for a, c in zip(strides[:-1], strides[1:])):
             warnings.warn('low-performance memory layout detected in filtered_lrelu input', RuntimeWarning)
-        res = _fused(x, fu, fd, b, si, sx, sy, cfg, write_signs)
+        res = _fused(x, fu, fd, b, si, sx, sy, cfg, write_signs, round_tf32=(si is None and _rounding_wanted()))
         if res is None:
             if not _quiet_fallback:
                 warnings.warn('filtered_lrelu called with parameters that have no fused sm_100a kernel, '
@@ -206,6 +208,45 @@ class _FilteredLRelu(torch.autograd.Function):
 
 
 _quiet_fallback = False
+
+# ---------------------------------------------------------------------------------------------
+# Outputs that feed a TF32 tensor-core convolution.  The tensor core TRUNCATES its fp32 operands to TF32 (10 mantissa bits);
+# cuDNN's TF32 kernels round them to nearest when they load them, which halves the operand error.  The modulated-conv kernels of
+# this package read activations straight from HBM by TMA, so the rounding is done where the activation is produced: inside
+# `tf32_rounded_outputs(True)` the fused forward kernel rounds every fp32 output to the nearest TF32 value (two integer
+# operations per value, hidden under the FMA pipe).  `networks.SynthesisLayer` switches it on for the layers whose consumer is
+# a TF32 conv; `round_for_tf32_convs = True` (set by `sg3_b200.patch_modulated_conv()`) does the same for the reference's own
+# layer code whenever the conv math mode is 'tf32'.  Never applied in the backward pass (gradients pass straight through).
+
+_round_tf32 = False
+round_for_tf32_convs = False
+
+
+class tf32_rounded_outputs:
+    """Context manager: `filtered_lrelu` forward outputs (fp32, fused kernel) are rounded to the nearest TF32 value."""
+
+    def __init__(self, enable=True):
+        self.enable = bool(enable)
+
+    def __enter__(self):
+        global _round_tf32
+        self.prev, _round_tf32 = _round_tf32, self.enable
+        return self
+
+    def __exit__(self, *exc):
+        global _round_tf32
+        _round_tf32 = self.prev
+        return False
+
+
+def _rounding_wanted():
+    if _round_tf32:
+        return True
+    if round_for_tf32_convs:
+        from .modulated_conv import _math_mode
+        return _math_mode() == 'tf32'
+    return False
+
 
 
 def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=np.sqrt(2), slope=0.2, clamp=None,

@@ -17,7 +17,7 @@ import scipy.special
 import torch
 
 from . import bias_act, filtered_lrelu
-from .modulated_conv import modulated_conv2d
+from .modulated_conv import modulated_conv2d, _math_mode
 
 __all__ = ['FullyConnectedLayer', 'MappingNetwork', 'SynthesisInput', 'SynthesisLayer', 'SynthesisNetwork',
            'Generator', 'GraphedSynthesis', 'PipelinedSynthesis', 'modulated_conv2d', 'CONFIG_R', 'CONFIG_T']
@@ -228,10 +228,13 @@ class SynthesisLayer(torch.nn.Module):
     def act_part(self, x):
         """bias -> filtered leaky ReLU at the temporary sampling rate   (reference :361-368)."""
         dtype = x.dtype
-        x = filtered_lrelu.filtered_lrelu(
-            x=x, fu=self.up_filter, fd=self.down_filter, b=self.bias.to(x.dtype), up=self.up_factor, down=self.down_factor,
-            padding=self.padding, gain=(1 if self.is_torgb else np.sqrt(2)), slope=(1 if self.is_torgb else 0.2),
-            clamp=self.conv_clamp)
+        # the next layer's convolution reads this output with TF32 tensor cores (which truncate): round to nearest here
+        rnd = (not self.is_torgb) and dtype == torch.float32 and _math_mode() == 'tf32'
+        with filtered_lrelu.tf32_rounded_outputs(rnd):
+            x = filtered_lrelu.filtered_lrelu(
+                x=x, fu=self.up_filter, fd=self.down_filter, b=self.bias.to(x.dtype), up=self.up_factor, down=self.down_factor,
+                padding=self.padding, gain=(1 if self.is_torgb else np.sqrt(2)), slope=(1 if self.is_torgb else 0.2),
+                clamp=self.conv_clamp)
         _shape_is(x, [None, self.out_channels, int(self.out_size[1]), int(self.out_size[0])])
         assert x.dtype == dtype
         return x
