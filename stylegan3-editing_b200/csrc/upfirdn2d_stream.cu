@@ -16,9 +16,13 @@
 // each of a lane's 4 outputs, just shift the taps inside a slightly longer static tap range (zero taps outside the filter), and
 // the taps are kernel parameters, i.e. constant-bank operands of the FFMAs.  Same arithmetic as the two passes of the
 // reference (fp32 accumulation, gain applied once at the end).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
+#include "tensor_map.h"
 
 namespace ufs {
 
@@ -58,9 +62,10 @@ template <int UP, int DOWN, int KP> struct Geo {
     // 16-byte chunks, every load is one contiguous 512-byte access.  pidx() maps a float index of the row to its place; the
     // copies that fill the row use it too (pieces are at most one chunk and chunk-aligned).
     static constexpr bool SPLIT = DOWN == 2;
+    static constexpr int HALFC = ((NIN / 8 + 7) / 8) * 8;               // 16-byte chunks per half, padded to 128 bytes
     static __host__ __device__ constexpr int pidx(int i)
     {
-        return SPLIT ? 4 * ((i >> 3) + ((i >> 2) & 1) * (NIN / 8)) + (i & 3) : i;
+        return SPLIT ? 4 * ((i >> 3) + ((i >> 2) & 1) * HALFC) + (i & 3) : i;
     }
     static constexpr int WIN = UP == 2 ? KP + 1 : T;                     // y window (rows of x-filtered values)
     static constexpr int RPI = DOWN;                                     // input rows consumed per iteration
@@ -72,11 +77,12 @@ template <int UP, int DOWN, int KP> struct Geo {
     static constexpr int KU = WIN < 5 ? 2 : 1;
     static constexpr int ROWS_U = WIN * KU;
     static constexpr int RING = ROWS_U <= 8 ? ROWS_U : (ROWS_U % 6 == 0 ? 6 : ROWS_U);
-    static constexpr int SLOT = NIN;                                     // floats per ring slot
+    static constexpr int SLOT = SPLIT ? 8 * HALFC : ((NIN + 31) / 32) * 32;   // floats per ring slot (a multiple of 128 bytes)
     static_assert(WIN % RPI == 0 && ROWS_U % RING == 0 && NT <= kMaxNT && WIN <= kMaxWin, "window geometry");
 };
 
 struct Params {
+    alignas(64) CUtensorMap mapX;   // TMA staging (COPY = 0): x as {W, H, C, N}, box {NIN, 1, 1, 1}
     const float* x; float* y;
     int N, C, inH, inW, outH, outW;
     long long xs0, xs1, xs2, ys0, ys1, ys2;      // element strides (unit stride along x)
@@ -106,11 +112,29 @@ __device__ __forceinline__ void cp_async(float* dst, const float* src, bool zero
         asm volatile("{\n\t.reg .pred z;\n\tsetp.ne.b32 z, %2, 0;\n\tcp.async.ca.shared.global [%0], [%1], 8, z;\n\t}" ::"r"(d), "l"(src), "r"((int)zero) : "memory");
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
+
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// COPY: how the input rows reach the ring.  0 = TMA (cp.async.bulk.tensor behind one mbarrier per ring slot: one elected lane starts
+// a row, the async proxy writes whole 128-byte lines and zero-fills everything outside the image) -- the up-2 and same-rate kernels
+// on tensors TMA can address (12-tap up 2: 0.85 -> 0.88 of HBM).  16 / 8 = per-lane cp.async pieces of that many bytes: rows or
+// planes that are not 16-byte multiples (e.g. 2098 columns), and every down-2 kernel -- its strips re-read a 12-column halo that
+// .ca copies find in L1 while TMA goes to L2 each time (measured: downsample2d 0.76 with cp.async.ca, 0.63 with TMA).
 template <int UP, int DOWN, int KP, int COPY>
 __global__ void __launch_bounds__(kWarps * 32, (KP <= 6 ? 4 : 3) * 4 / kWarps) kernel(const __grid_constant__ Params p)
 {
     typedef Geo<UP, DOWN, KP> G;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * kWarps + warp;
     if (wid >= p.totalWarps) return;
@@ -128,44 +152,66 @@ __global__ void __launch_bounds__(kWarps * 32, (KP <= 6 ? 4 : 3) * 4 / kWarps) k
     const int iBase = p.iBase0 + chunk * (p.chunkRows * DOWN / UP);
     const int nIt = UP == 2 ? (chs + 1) >> 1 : chs;
     const int nRows = G::PRIME + G::RPI * nIt;
-    float* ring = smem + warp * (G::RING * G::SLOT);
+    constexpr int WARP_FLOATS = G::RING * G::SLOT + (COPY == 0 ? 2 * G::RING + 2 : 0);     // ring (+ one mbarrier per slot, 16-byte padded)
+    float* ring = smem + warp * (((WARP_FLOATS + 31) / 32) * 32);
 
-    // ---- staging: input row iBase + r -> ring slot r % RING, one commit group per row (empty past the last row) ----
-    // Per lane and 16- / 8-byte piece of the row, everything that does not depend on the row is computed once: where the piece
-    // lands (pidx), its source column (clamped into the image so that the address is always valid and aligned) and how many of its
-    // bytes lie inside the image; a row outside the image copies 0 bytes (cp.async zero-fills the rest of a piece).  Lanes
-    // without a piece copy 0 bytes into the scratch chunk of the slot, so the copy instructions need no predicate.
-    constexpr int CE = COPY / 4;                                  // floats per piece
-    constexpr int NF = (G::NIN / CE + 31) / 32;                   // pieces per lane
+    // ---- staging: input row iBase + r -> ring slot r % RING, strictly in order ----
+    int rI = 0;                                                   // next row to stage
+    // cp.async path: per lane and 16- / 8-byte piece of the row, everything that does not depend on the row is computed once:
+    // where the piece lands (pidx), its source column (clamped into the image so that the address is always valid and aligned) and
+    // whether it lies inside the image; pieces and rows outside the image are written as zeros (the ignore-src form of cp.async).
+    constexpr int CE = COPY ? COPY / 4 : 4;                       // floats per piece
+    constexpr int NF = COPY ? (G::NIN / CE + 31) / 32 : 1;        // pieces per lane
     float* dstC[NF];
     unsigned srcC[NF];
     unsigned inside = 0;                                          // bit f: piece f of this lane lies inside the image (inW % CE == 0: never partly)
-#pragma unroll
-    for (int f = 0; f < NF; f++) {
-        const int e = CE * (lane + 32 * f), j = jA + e;
-        const bool in = e < G::NIN && j >= 0 && j < p.inW;
-        inside |= in ? 1u << f : 0u;
-        srcC[f] = in ? 4u * (unsigned)j : 0u;
-        dstC[f] = ring + (e < G::NIN ? G::pidx(e) : 0);
-    }
-    // only the last piece index can be missing for some lanes (32 (NF - 1) CE < NIN by construction)
-    const bool hasLast = CE * (lane + 32 * (NF - 1)) < G::NIN;
-    int rI = 0;                                                   // next row to stage; rows are staged strictly in order
-    const char* pI = reinterpret_cast<const char*>(xp + (long long)iBase * p.xs2);      // its address (not dereferenced outside the image)
+    bool hasLast = false;                                         // only the last piece index can be missing for some lanes
+    const char* pI = nullptr;                                     // address of row rI (not dereferenced outside the image)
     const long long rowBytes = p.xs2 * 4;
-    auto issue = [&](int slot) {
-        if (rI < nRows) {
-            const bool ok = (unsigned)(iBase + rI) < (unsigned)p.inH;
-            const unsigned live = ok ? inside : 0u;
-            const char* src = ok ? pI : reinterpret_cast<const char*>(xp);
+    // TMA path: one mbarrier per slot; `phases` holds the parity the next wait on each slot expects
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + G::RING * G::SLOT);
+    unsigned phases = 0;
+    if (COPY != 0) {
 #pragma unroll
-            for (int f = 0; f < NF; f++)
-                if (f < NF - 1 || hasLast)
-                    cp_async<COPY, UFS_CG16 != 0 && DOWN == 1>(dstC[f] + slot * G::SLOT, reinterpret_cast<const float*>(src + srcC[f]), !((live >> f) & 1u));
+        for (int f = 0; f < NF; f++) {
+            const int e = CE * (lane + 32 * f), j = jA + e;
+            const bool in = e < G::NIN && j >= 0 && j < p.inW;
+            inside |= in ? 1u << f : 0u;
+            srcC[f] = in ? 4u * (unsigned)j : 0u;
+            dstC[f] = ring + (e < G::NIN ? G::pidx(e) : 0);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        hasLast = CE * (lane + 32 * (NF - 1)) < G::NIN;
+        pI = reinterpret_cast<const char*>(xp + (long long)iBase * p.xs2);
+    } else {
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < G::RING; q++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bars[q])) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    auto issue = [&](int slot) {
+        if (COPY != 0) {
+            if (rI < nRows) {
+                const bool ok = (unsigned)(iBase + rI) < (unsigned)p.inH;
+                const unsigned live = ok ? inside : 0u;
+                const char* src = ok ? pI : reinterpret_cast<const char*>(xp);
+#pragma unroll
+                for (int f = 0; f < NF; f++)
+                    if (f < NF - 1 || hasLast)
+                        cp_async<COPY ? COPY : 16, UFS_CG16 != 0 && DOWN == 1>(dstC[f] + slot * G::SLOT, reinterpret_cast<const float*>(src + srcC[f]),
+                                                                             !((live >> f) & 1u));
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            pI += rowBytes;
+        } else if (rI < nRows && lane == 0) {
+            const uint32_t bar = smem_u32(&bars[slot]);
+            const uint32_t dst = smem_u32(ring + slot * G::SLOT);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(G::NIN * 4)) : "memory");
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                         ::"r"(dst), "l"((uint64_t)&p.mapX), "r"(bar), "r"(jA), "r"(iBase + rI), "r"(c), "r"(n) : "memory");
+        }
         rI++;
-        pI += rowBytes;
     };
 #pragma unroll
     for (int r = 0; r < G::RING - 1; r++) issue(r);
@@ -173,7 +219,14 @@ __global__ void __launch_bounds__(kWarps * 32, (KP <= 6 ? 4 : 3) * 4 / kWarps) k
     // ---- x pass of the next staged row (ring slot `slot`): 4 values per lane; then refill the slot read one row ago ----
     const float* lds0 = ring + (UP == 2 ? p.c0 + G::LSTEP * lane : (G::SPLIT ? 4 * lane : G::LSTEP * lane));
     auto xrow = [&](float (&h)[kV], int slot) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(G::RING - 2) : "memory");
+        if (COPY != 0) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(G::RING - 2) : "memory");
+        } else {
+            const uint32_t bar = smem_u32(&bars[slot]);
+            for (uint32_t spins = 0; !mbar_try_wait(bar, (phases >> slot) & 1u); spins++)
+                if (spins > (1u << 24)) __trap();                 // bounded: trap, never hang
+            phases ^= 1u << slot;
+        }
         __syncwarp();
         const float* row = lds0 + slot * G::SLOT;
         float xin[G::NWH];
@@ -263,7 +316,7 @@ __global__ void __launch_bounds__(kWarps * 32, (KP <= 6 ? 4 : 3) * 4 / kWarps) k
             }
         }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (COPY != 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 template <int UP, int DOWN, int KP, int COPY>
@@ -313,6 +366,20 @@ int launch(Params& p, const float* fx, const float* fy, int padx0, int pady0, cu
     }
     for (int a = 0; a < 2; a++)
         for (int w = 0; w < kMaxWin; w++) p.tv[a][w] *= p.gain;           // the gain rides on the y taps
+    static_assert(COPY != 0 || DOWN == 1, "TMA staging is built for the up-2 / same-rate kernels");
+    if (COPY == 0) {
+        // TMA staging: x as a tiled tensor map (out-of-image columns / rows read as zero).  Extent-1 dimensions get a synthetic stride.
+        const uint64_t sW = 4, sH = (uint64_t)p.xs2 * 4, sC = (uint64_t)p.xs1 * 4, sN = (uint64_t)p.xs0 * 4;
+        auto pad16 = [](uint64_t v) { return (v + 15) / 16 * 16; };
+        const uint64_t rowS = p.inH > 1 ? sH : pad16((uint64_t)p.inW * sW);
+        const uint64_t chS = p.C > 1 ? sC : pad16(rowS * (uint64_t)p.inH);
+        const uint64_t smS = p.N > 1 ? sN : pad16(chS * (uint64_t)p.C);
+        const uint64_t dims[4] = {(uint64_t)p.inW, (uint64_t)p.inH, (uint64_t)p.C, (uint64_t)p.N};
+        const uint64_t strides[3] = {rowS, chS, smS};
+        const uint32_t box[4] = {(uint32_t)G::NIN, 1, 1, 1};
+        const bool ok = sg3_make_tensor_map(&p.mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p.x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+        if (!ok) return SG3_E_NOKERNEL;
+    }
     // ---- work split: strips of 128 columns x chunks of rows; shrink the chunks until the GPU is covered ----
     p.stripsX = (p.outW + 127) / 128;
     const long long planes = (long long)p.N * p.C;
@@ -326,7 +393,9 @@ int launch(Params& p, const float* fx, const float* fy, int padx0, int pady0, cu
     p.totalWarps = planes * p.stripsX * p.chunksY;
     const long long ctas = (p.totalWarps + kWarps - 1) / kWarps;
     if (ctas > 0x7fffffffLL) return SG3_E_TOOLARGE;
-    const int smemBytes = kWarps * G::RING * G::SLOT * 4 > UFS_SMEM_MIN ? kWarps * G::RING * G::SLOT * 4 : UFS_SMEM_MIN;
+    constexpr int WARP_FLOATS = G::RING * G::SLOT + (COPY == 0 ? 2 * G::RING + 2 : 0);
+    constexpr int need = kWarps * (((WARP_FLOATS + 31) / 32) * 32) * 4;
+    const int smemBytes = need > UFS_SMEM_MIN ? need : UFS_SMEM_MIN;
     auto kern = kernel<UP, DOWN, KP, COPY>;
     static Sg3DeviceOnce once;
     const cudaError_t attrErr = once.run([&] {
@@ -339,7 +408,21 @@ int launch(Params& p, const float* fx, const float* fy, int padx0, int pady0, cu
     return sg3_launch_status();
 }
 
+template <int UP, int DOWN, int KP>
+int launch_tma(Params& p, const float* fx, const float* fy, int padx0, int pady0, cudaStream_t stream)
+{
+    if constexpr (DOWN == 1) return launch<UP, DOWN, KP, 0>(p, fx, fy, padx0, pady0, stream);
+    else return SG3_E_NOKERNEL;
+}
+
 }  // namespace ufs
+
+// SG3_UPFIRDN_NO_TMA=1 in the environment keeps the cp.async staging for every tensor (A/B timing)
+static bool ufs_tma_disabled()
+{
+    static const bool off = [] { const char* e = getenv("SG3_UPFIRDN_NO_TMA"); return e && e[0] == '1'; }();
+    return off;
+}
 
 // fp32 separable upfirdn2d through the streaming kernel.  fx / fy: correlation-ordered taps, zero padded to >= up * 12 entries
 // (the table upfirdn2d_sep.cu builds).  SG3_E_NOKERNEL when the shape is not covered (the tiled kernel then runs).
@@ -368,8 +451,17 @@ int sg3_upfirdn2d_stream(const float* x, float* y, int N, int C, int inH, int in
     const int copyBytes = (aligned(x, xs, 16) && inW % 4 == 0) ? 16 : (aligned(x, xs, 8) && inW % 2 == 0) ? 8 : 0;
     if (!copyBytes) return SG3_E_NOKERNEL;                                          // odd row pitch: the tiled kernel
     p.vecStore = aligned(y, ys, 16) ? 2 : aligned(y, ys, 8) ? 1 : 0;
-#define SG3_UFS(U, D, K) return copyBytes == 16 ? ufs::launch<U, D, K, 16>(p, fx, fy, padx0, pady0, stream) \
-                                                : ufs::launch<U, D, K, 8>(p, fx, fy, padx0, pady0, stream)
+    // TMA needs 16-byte aligned rows / planes with positive pitches; everything else takes per-lane cp.async pieces
+    const bool tma = down == 1 && copyBytes == 16 && xs[0] > 0 && xs[1] > 0 && xs[2] > 0 && !ufs_tma_disabled();
+#define SG3_UFS(U, D, K)                                                                                                    \
+    do {                                                                                                                    \
+        if (tma) {                                                                                                          \
+            const int rc = ufs::launch_tma<U, D, K>(p, fx, fy, padx0, pady0, stream);                                       \
+            if (rc != SG3_E_NOKERNEL) return rc;                                                                            \
+        }                                                                                                                   \
+        return copyBytes == 16 ? ufs::launch<U, D, K, 16>(p, fx, fy, padx0, pady0, stream)                                  \
+                               : ufs::launch<U, D, K, 8>(p, fx, fy, padx0, pady0, stream);                                  \
+    } while (0)
     if (up == 2) {
         if (kp <= 2) SG3_UFS(2, 1, 2);
         if (kp <= 4) SG3_UFS(2, 1, 4);

@@ -432,6 +432,39 @@ def test_upfirdn2d_stream_kernel(ops, case):
     assert rel_err(y.cpu().numpy(), ref) < TOL32
 
 
+def test_upfirdn2d_stream_kernel_cp_async_staging():
+    """Tensors TMA can address stage their rows by TMA; SG3_UPFIRDN_NO_TMA=1 (read once per process) keeps the 16-byte cp.async
+    staging for them: same results.  Runs the aligned cases of the table above in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import sg3_b200
+from oracle import sg3_oracle as orc
+sys.path.insert(0, %r)
+from test_ops_gpu import UPFIRDN_STREAM, cu
+from conftest import rel_err
+n = 0
+for name, taps, up, down, padding, flip, shape, view in UPFIRDN_STREAM:
+    if view is not None or shape[3] %% 4 != 0:
+        continue
+    rng = np.random.RandomState(len(name) + taps)
+    f = rng.randn(taps).astype(np.float32)
+    x = rng.randn(*shape).astype(np.float32)
+    y = sg3_b200.upfirdn2d.upfirdn2d(cu(x), cu(f), up=up, down=down, padding=padding, flip_filter=flip, gain=up * up)
+    ref = orc.upfirdn2d(x, f, up=up, down=down, padding=padding, flip_filter=flip, gain=up * up)
+    assert rel_err(y.cpu().numpy(), ref) < 2e-5, name
+    n += 1
+print('cases', n)
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SG3_UPFIRDN_NO_TMA='1')
+    res = subprocess.run([sys.executable, '-c', code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:]
+    assert 'cases' in res.stdout and int(res.stdout.strip().split()[-1]) >= 8
+
+
 def test_upfirdn2d_rank1_dense_filters_run_separable(ops):
     """`setup_filter([1, 3, 3, 1])` returns the dense 4 x 4 outer product (upfirdn2d.py:103-105); the op factors it back and runs
     the separable kernel: filter2d / upsample2d / downsample2d with their default paddings, against the oracle's dense evaluation."""
