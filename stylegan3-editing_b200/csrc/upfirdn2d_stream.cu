@@ -38,6 +38,9 @@ namespace ufs {
 #ifndef UFS_CG16
 #define UFS_CG16 1
 #endif
+#ifndef UFS_L2PF
+#define UFS_L2PF ""          // e.g. ".L2::256B": L2 prefetch size of the cp.async copies
+#endif
 constexpr int kWarps = UFS_WARPS;
 constexpr int kV = 4;                // output columns per lane
 constexpr int kMaxNT = 16, kMaxWin = 16;       // taps per output (even), y window rows
@@ -105,11 +108,11 @@ __device__ __forceinline__ void cp_async(float* dst, const float* src, bool zero
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     if (BYTES == 16 && CG)
-        asm volatile("{\n\t.reg .pred z;\n\tsetp.ne.b32 z, %2, 0;\n\tcp.async.cg.shared.global [%0], [%1], 16, z;\n\t}" ::"r"(d), "l"(src), "r"((int)zero) : "memory");
+        asm volatile("{\n\t.reg .pred z;\n\tsetp.ne.b32 z, %2, 0;\n\tcp.async.cg.shared.global" UFS_L2PF " [%0], [%1], 16, z;\n\t}" ::"r"(d), "l"(src), "r"((int)zero) : "memory");
     else if (BYTES == 16)
-        asm volatile("{\n\t.reg .pred z;\n\tsetp.ne.b32 z, %2, 0;\n\tcp.async.ca.shared.global [%0], [%1], 16, z;\n\t}" ::"r"(d), "l"(src), "r"((int)zero) : "memory");
+        asm volatile("{\n\t.reg .pred z;\n\tsetp.ne.b32 z, %2, 0;\n\tcp.async.ca.shared.global" UFS_L2PF " [%0], [%1], 16, z;\n\t}" ::"r"(d), "l"(src), "r"((int)zero) : "memory");
     else
-        asm volatile("{\n\t.reg .pred z;\n\tsetp.ne.b32 z, %2, 0;\n\tcp.async.ca.shared.global [%0], [%1], 8, z;\n\t}" ::"r"(d), "l"(src), "r"((int)zero) : "memory");
+        asm volatile("{\n\t.reg .pred z;\n\tsetp.ne.b32 z, %2, 0;\n\tcp.async.ca.shared.global" UFS_L2PF " [%0], [%1], 8, z;\n\t}" ::"r"(d), "l"(src), "r"((int)zero) : "memory");
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* q) { return (uint32_t)__cvta_generic_to_shared(q); }
