@@ -392,10 +392,12 @@ class PipelinedSynthesis:
     Run back to back, each leaves the other's resource unused.  Here the batch is split into micro-batches and the network is
     software-pipelined over two streams: the convolutions go to a HIGH-priority stream, the stencils to a normal one, chained per
     micro-batch by events -- while the stencil of layer k works on micro-batch m, the convolution of micro-batch m+1 (or of layer
-    k+1 on micro-batch m-1) runs on the same SMs.  Co-residency is arranged, not hoped for: the conv kernels are persistent (one CTA
-    per SM) and are given a shared-memory budget (`sg3_modconv_set_smem_budget`) that lets one conv CTA (192 threads, 64 registers)
-    sit next to three of the four stencil CTAs an SM holds (4 warps, 128 registers, 28 KB each), and the block scheduler serves the
-    high-priority stream first, so a pending conv CTA takes the first stencil slot that retires.
+    k+1 on micro-batch m-1) may run.  With `conv_smem_budget=CONV_SMEM_BUDGET` co-residency is arranged, not hoped for: the conv
+    kernels are persistent (one CTA per SM) and get a shared-memory budget (`sg3_modconv_set_smem_budget`) that lets one conv CTA
+    (192 threads, 64 registers) sit next to three of the four stencil CTAs an SM holds (4 warps, 128 registers, 28 KB each), and the
+    block scheduler serves the high-priority stream first, so a pending conv CTA takes the first stencil slot that retires.  The
+    residency trace confirms that this happens -- and that it buys nothing (profiles/r02_overlap.md), so the default keeps the full
+    conv kernels and only overlaps kernel tails and launch gaps (+2 % on config R at batch 32).
 
     Every op is per sample, so the result equals the plain forward up to the batch-global style RMS of networks_stylegan3.py:42,
     which cancels under demodulation except for its 1e-8 epsilon (same statement as for batch sharding across GPUs).
@@ -403,10 +405,13 @@ class PipelinedSynthesis:
 
     CONV_SMEM_BUDGET = 138 * 1024       # 228 KB per SM - 3 x (28 KB + 1 KB reserved) stencil CTAs - 1 KB reserved - barriers
 
-    def __init__(self, synthesis, micro_batches=2, conv_smem_budget=None):
+    def __init__(self, synthesis, micro_batches=2, conv_smem_budget=0):
+        # conv_smem_budget: 0 (default) = the conv kernels keep their full TMA ring, the two streams overlap at kernel tails only;
+        # CONV_SMEM_BUDGET = one conv CTA fits next to three stencil CTAs per SM (true co-residency).  Measured on B200
+        # (profiles/r02_overlap.md): co-residency is never faster -- both kernels lean on the shared-memory data pipe -- so it is off.
         self.synthesis = synthesis
         self.micro_batches = int(micro_batches)
-        self.budget = self.CONV_SMEM_BUDGET if conv_smem_budget is None else int(conv_smem_budget)
+        self.budget = int(conv_smem_budget)
         self._streams = {}
 
     def _get_streams(self, device):

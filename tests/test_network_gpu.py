@@ -423,7 +423,8 @@ def test_pipelined_synthesis_matches_plain_forward(pkg, name, math):
             ref = G.synthesis(ws, noise_mode='const', force_fp32=True)
         tol = 1e-5 if math == 'fp32' else 1e-2
         for M in (2, 3, 8):
-            pipe = networks.PipelinedSynthesis(G.synthesis, micro_batches=M)
+            pipe = networks.PipelinedSynthesis(G.synthesis, micro_batches=M,
+                                               conv_smem_budget=networks.PipelinedSynthesis.CONV_SMEM_BUDGET if M == 2 else 0)
             img = pipe(ws, noise_mode='const', force_fp32=True)
             torch.cuda.synchronize()
             assert img.shape == ref.shape and img.dtype == torch.float32

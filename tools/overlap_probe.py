@@ -61,7 +61,7 @@ def main():
     out = torch.empty_like(ref)
     stats0 = torch.cuda.memory_stats()
     for M in (() if args.skip_net else (2, 4, 8)):
-        for budget, tag in ((None, 'budget default'), (0, 'no budget (no co-residency)')):
+        for budget, tag in ((networks.PipelinedSynthesis.CONV_SMEM_BUDGET, 'budget 138 KB (co-resident)'), (0, 'no budget (no co-residency)')):
             if budget == 0 and M != 2:
                 continue
             pipe = networks.PipelinedSynthesis(G.synthesis, micro_batches=M, conv_smem_budget=budget)
@@ -83,7 +83,7 @@ def main():
     half = B // 2
     x = torch.randn([half, L.in_channels, int(L.in_size[1]), int(L.in_size[0])], device=dev)
     w = ws[:half, 1]
-    pipe = networks.PipelinedSynthesis(G.synthesis)
+    pipe = networks.PipelinedSynthesis(G.synthesis, conv_smem_budget=networks.PipelinedSynthesis.CONV_SMEM_BUDGET)
     conv_s, act_s = pipe._get_streams(dev)
     with torch.no_grad():
         t0 = L.conv_part(x, w, **kw)
