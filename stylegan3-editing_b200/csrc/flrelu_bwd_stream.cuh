@@ -185,7 +185,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DOWN == 2 ? 5 : 4) kernel(c
     loadSigns(0);
 
     // ---- stage U + V for group g ----
-    auto stageUV = [&](int g, auto EYc) {
+    // codes4[j]: the lane's four 2-bit codes of row j of the group, combined from the raw bytes by the CALLER before it starts the
+    // next input prefetch: the byte loads and the input-row loads share a scoreboard, so a combine placed after the prefetch (where
+    // the compiler put it when it lived in here) waited a full memory latency per group for loads it does not need -- one SHF
+    // carried 17 % of all stall samples of the kernel (ncu source view, L10 backward).
+    auto stageUV = [&](int g, auto EYc, const unsigned (&codes4)[4]) {
         constexpr int EY = decltype(EYc)::value;
         // window row r (0..7) = input row 2g + r of the strip; pair (r, r+1) lives in E (r even) or O (r odd)
         float2 acc[2][2][2];                   // [row pair jp: rows (jp, jp+2)][column block][px]
@@ -221,12 +225,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DOWN == 2 ? 5 : 4) kernel(c
         }
         // activation (sign lookup or lrelu/clamp) and repack to (column, column+1) pairs per row
         float2 rowv[4][2];                                  // [row j][column pair]
-        unsigned codes4[4] = {0u, 0u, 0u, 0u};              // the lane's four 2-bit codes of each row
-        if (MODE == SG3_SIGNS_READ) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) codes4[j] = (sLo[j] | (sHi[j] << 8)) >> (2 * ((Xs - ex + p.sx) & 3));
-            loadSigns(g + 1);                               // consumed a whole group from now: the bytes come from HBM
-        }
+        if (MODE == SG3_SIGNS_READ) loadSigns(g + 1);       // consumed a whole group from now: the bytes come from HBM
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int jp = j & 1, hi = j >> 1;
@@ -355,9 +354,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, DOWN == 2 ? 5 : 4) kernel(c
     auto run = [&](auto EYc) {
         for (int g = 0; g < numGroups; g++) {
             __syncwarp();                                   // previous stage H / U are done with the ring slot about to be overwritten
+            unsigned codes4[4] = {0u, 0u, 0u, 0u};
+            if (MODE == SG3_SIGNS_READ) {                   // bytes loaded during the previous group (see stageUV)
+#pragma unroll
+                for (int j = 0; j < 4; j++) codes4[j] = (sLo[j] | (sHi[j] << 8)) >> (2 * ((Xs - ex + p.sx) & 3));
+            }
             while (nextPair <= g + 3) producePair();
             __syncwarp();
-            stageUV(g, EYc);
+            stageUV(g, EYc, codes4);
             __syncwarp();
             stageH(g);
         }
