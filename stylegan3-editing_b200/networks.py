@@ -483,6 +483,6 @@ class PipelinedSynthesis:
             del x, t_prev
         finally:
             capi.lib().sg3_modconv_set_smem_budget(prev)
-        main.wait_stream(act_s)
-        main.wait_stream(conv_s)
+            main.wait_stream(act_s)                                      # also on an exception: later work on `main` stays ordered
+            main.wait_stream(conv_s)
         return out
