@@ -66,6 +66,13 @@ __device__ __forceinline__ float tf32_rna(float v)
     return __uint_as_float(r);
 }
 
+// explicit global stores for the epilogue's walking pointers (an opaque pointer update would otherwise demote them to generic ST)
+__device__ __forceinline__ void st_plane(float* q, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(q), "f"(v) : "memory"); }
+__device__ __forceinline__ void st_plane(__half* q, float v)
+{
+    asm volatile("st.global.b16 [%0], %1;" ::"l"(q), "h"(__half_as_ushort(__float2half_rn(v))) : "memory");
+}
+
 template <bool HALF, bool X3>
 __global__ void __launch_bounds__(X3 ? kThreadsX3 : kThreads, 1)
 modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const TcParams p)
@@ -215,15 +222,40 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int pix = p0 + 32 * warp + lane;
             typedef typename std::conditional<HALF, __half, float>::type OutT;
-            OutT* yn = (OutT*)p.y + ((size_t)n * p.O) * (size_t)p.P;
+            // The store loop is the critical path of the HBM-bound layers: ONE warp owns 32 pixels of a tile and has to issue every
+            // store of their BN channels itself.  With the address (64-bit multiply) and two bound checks evaluated per element this
+            // was ~19 instructions per store -- 2000 dependent instructions per warp and tile, and the ncu source view showed the MMA
+            // and TMA warps asleep on their barriers while the epilogue warps crawled (L13: 0.64 of HBM).  Now: one pointer per
+            // 32-channel block walking down the channel planes, the bound check hoisted to a warp-uniform block count.
+            const size_t planeStep = (size_t)p.P;
+            OutT* yb = (OutT*)p.y + ((size_t)n * p.O + o0) * planeStep + pix;          // channel o0, this thread's pixel
+            const bool pixOk = pix < p.P;
             for (int c = 0; c < p.BN; c += 32) {
                 uint32_t r[32];
                 tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + as * p.accCols + (uint32_t)c, r);
-                if (pix < p.P) {
+                const int nvalid = min(p.BN - c, p.O - o0 - c);                          // channels of this block that exist (uniform)
+                if (pixOk) {
+                    // two pointers (even / odd channels) walking down the planes; the empty asm keeps ptxas from turning the walk
+                    // back into 32 independent 64-bit multiplies (which it hoists, at 64 registers and ~400 IMADs per tile)
+                    OutT* q0 = yb + (size_t)c * planeStep;
+                    OutT* q1 = q0 + planeStep;
+                    const size_t step2 = 2 * planeStep;
+                    if (nvalid >= 32) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const int o = o0 + c + j;
-                        if (c + j < p.BN && o < p.O) st_as<OutT>(yn + (size_t)o * p.P + pix, __uint_as_float(r[j]));
+                        for (int j = 0; j < 32; j += 2) {
+                            st_plane(q0, __uint_as_float(r[j]));
+                            st_plane(q1, __uint_as_float(r[j + 1]));
+                            q0 += step2; q1 += step2;
+                            asm volatile("" : "+l"(q0), "+l"(q1));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            if (j < nvalid) st_plane(q0, __uint_as_float(r[j]));
+                            if (j + 1 < nvalid) st_plane(q1, __uint_as_float(r[j + 1]));
+                            q0 += step2; q1 += step2;
+                            asm volatile("" : "+l"(q0), "+l"(q1));
+                        }
                     }
                 }
             }
