@@ -432,6 +432,41 @@ def test_upfirdn2d_stream_kernel(ops, case):
     assert rel_err(y.cpu().numpy(), ref) < TOL32
 
 
+@pytest.mark.parametrize('seed', list(range(24)))
+def test_upfirdn2d_stream_random_sweep(ops, seed):
+    """Random separable cases through the public op: factor (up 2 / down 2 / same rate), 1-24 taps, paddings from crops to wide
+    borders, odd heights, widths of every alignment class (16-byte rows -> TMA or cp.async 16, 8-byte rows -> cp.async 8, odd rows ->
+    the tiled kernel), one or several strips / row chunks, views with a row pitch -- all against the oracle."""
+    from oracle import sg3_oracle as orc
+    rng = np.random.RandomState(1000 + seed)
+    mode = seed % 3
+    up, down = ((2, 1), (1, 2), (1, 1))[mode]
+    taps = int(rng.randint(1, 25 if up == 2 else 13))
+    n, c = int(rng.randint(1, 3)), int(rng.randint(1, 4))
+    h = int(rng.randint(20, 140)) if seed % 4 else int(rng.randint(260, 420))
+    w = int(rng.choice([rng.randint(5, 40) * 4, rng.randint(10, 80) * 2, rng.randint(21, 160)]))
+    if seed % 5 == 0:
+        w = int(rng.randint(70, 110)) * 4                      # several strips
+    lo = -min(6, (min(h, w) * up) // 4)
+    pad = [int(v) for v in rng.randint(lo, 16, size=4)]
+    while (w * up + pad[0] + pad[1] - taps) < down or (h * up + pad[2] + pad[3] - taps) < down:
+        pad = [v + 2 for v in pad]
+    f = rng.randn(taps).astype(np.float32)
+    x = rng.randn(n, c, h, w).astype(np.float32)
+    xt = cu(x)
+    if seed % 6 == 1:                                          # a view with a row pitch and an offset base
+        pitch, ofs = w + int(rng.randint(1, 9)), int(rng.randint(0, 3))
+        buf = torch.full([n, c, h, pitch + 4], float('nan'), device='cuda')
+        buf[..., ofs:ofs + w] = xt
+        xt = buf[..., ofs:ofs + w]
+    flip = bool(seed & 1)
+    gain = float(rng.choice([1.0, up * up, 0.37]))
+    y = ops.upfirdn2d.upfirdn2d(xt, cu(f), up=up, down=down, padding=pad, flip_filter=flip, gain=gain)
+    ref = orc.upfirdn2d(x, f, up=up, down=down, padding=pad, flip_filter=flip, gain=gain)
+    assert y.shape == ref.shape, (up, down, taps, pad, x.shape)
+    assert rel_err(y.cpu().numpy(), ref) < TOL32, (up, down, taps, pad, x.shape)
+
+
 def test_upfirdn2d_stream_kernel_cp_async_staging():
     """Tensors TMA can address stage their rows by TMA; SG3_UPFIRDN_NO_TMA=1 (read once per process) keeps the 16-byte cp.async
     staging for them: same results.  Runs the aligned cases of the table above in a child process."""
