@@ -368,3 +368,52 @@ def test_bench_reference_arm_config_and_workload_harness_import():
     assert d.ndim == 0 and a.grad is not None and float(lp(a.detach(), a.detach())) == 0.0
     m = workloads.random_landmarks_transforms(3, torch.Generator().manual_seed(0), 'cpu')
     assert tuple(m.shape) == (3, 3, 3)
+
+
+def test_rank1_factoring_of_dense_filters():
+    """upfirdn2d._rank1_factors: outer-product filters (what setup_filter makes of short 1-D filters) are factored back into their
+    1-D taps so that the separable kernel runs them; anything else stays dense."""
+    import sg3_b200
+    ufd = sg3_b200.upfirdn2d
+    f = ufd.setup_filter([1, 3, 3, 1])                       # dense 4 x 4, normalised
+    assert f.ndim == 2
+    tx, ty = ufd._rank1_factors(ufd.host_taps(f))
+    assert np.allclose(np.outer(ty, tx), f.numpy(), rtol=0, atol=1e-7)
+    g = np.outer([1.0, -2.0, 0.5], [0.25, 4.0, 1.0, -3.0, 2.0]).astype(np.float32)       # asymmetric shapes and signs
+    tx, ty = ufd._rank1_factors(g)
+    assert tx.shape == (5,) and ty.shape == (3,) and np.allclose(np.outer(ty, tx), g, atol=1e-6)
+    rng = np.random.RandomState(0)
+    assert ufd._rank1_factors(rng.randn(4, 4).astype(np.float32)) is None             # full rank
+    assert ufd._rank1_factors(np.zeros((3, 3), np.float32)) is None                   # no pivot
+    assert ufd._rank1_factors(np.ones((1, 5), np.float32)) is None                    # 1-D shaped filters take their own path
+    near = np.outer([1, 2, 1], [1, 2, 1]).astype(np.float32)
+    near[0, 0] += 1e-3                                                                  # almost rank 1 is not rank 1
+    assert ufd._rank1_factors(near) is None
+
+
+def test_tf32_rounding_switch_logic():
+    """filtered_lrelu.tf32_rounded_outputs / round_for_tf32_convs: pure host state (the kernel side is covered on the GPU)."""
+    import sg3_b200
+    from sg3_b200 import modulated_conv
+    fl = sg3_b200.filtered_lrelu
+    old = fl.round_for_tf32_convs
+    fl.round_for_tf32_convs = False                           # an earlier drop-in test may have patched modulated_conv2d
+    assert fl._rounding_wanted() is False
+    with fl.tf32_rounded_outputs(True):
+        assert fl._rounding_wanted() is True
+        with fl.tf32_rounded_outputs(False):
+            assert fl._rounding_wanted() is False
+        assert fl._rounding_wanted() is True
+    assert fl._rounding_wanted() is False
+    try:
+        fl.round_for_tf32_convs = True                        # what patch_modulated_conv() sets
+        modulated_conv.set_math('tf32')
+        assert fl._rounding_wanted() is True
+        modulated_conv.set_math('fp32')
+        assert fl._rounding_wanted() is False
+        modulated_conv.set_math('fp32x3')
+        assert fl._rounding_wanted() is False
+    finally:
+        fl.round_for_tf32_convs = old
+        modulated_conv.set_math(None)
+    assert sg3_b200.capi.FLRELU_ROUND_TF32 == 1
