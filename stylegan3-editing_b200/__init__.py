@@ -28,9 +28,9 @@ def install():
     return dropin.install()
 
 
-def patch_modulated_conv(target=None):
+def patch_modulated_conv(target=None, round_activations=True):
     """Also route the reference's module-level `modulated_conv2d` (pure PyTorch + cuDNN, networks_stylegan3.py:24-63) to the
     fused prologue + tcgen05 contraction; `target` = None (the imported `models.stylegan3.networks_stylegan3`), a module, or a
     generator object (covers unpickled generators).  See dropin.patch_modulated_conv."""
     from . import dropin
-    return dropin.patch_modulated_conv(target)
+    return dropin.patch_modulated_conv(target, round_activations=round_activations)

@@ -75,7 +75,7 @@ def install(override_existing=True):
     return sorted(mods)
 
 
-def patch_modulated_conv(target=None):
+def patch_modulated_conv(target=None, round_activations=True):
     """Point the reference's module-level `modulated_conv2d` (networks_stylegan3.py:24, looked up as a module global by
     `SynthesisLayer.forward`, :360) at this package's fused implementation (same signature).
 
@@ -85,6 +85,10 @@ def patch_modulated_conv(target=None):
       * a generator / any `torch.nn.Module`: every Python module that defines the class of one of its submodules and has a
         `modulated_conv2d` global is patched -- this covers pickled generators, whose source `torch_utils/persistence.py:191-229`
         re-imports under a private module name.
+    `round_activations`: once a module is patched, `filtered_lrelu.round_for_tf32_convs` is switched on -- in TF32 math mode every fused
+    filtered_lrelu forward then rounds its fp32 outputs to the nearest TF32 value, because the patched convolutions read them with
+    tensor cores that would truncate (2-3x lower image error, see filtered_lrelu.tf32_rounded_outputs).  It is a process-wide switch:
+    pass False (or reset the attribute) if the same process also calls filtered_lrelu for consumers that want unrounded fp32 values.
     Returns the names of the patched modules (empty list: nothing to patch)."""
     from .modulated_conv import modulated_conv2d
     mods = []
@@ -114,7 +118,7 @@ def patch_modulated_conv(target=None):
             m._sg3_b200_original_modulated_conv2d = m.modulated_conv2d
             m.modulated_conv2d = modulated_conv2d
             done.append(m.__name__)
-    if done:
+    if done and round_activations:
         # the patched layers' convolutions now read their inputs with TF32 tensor cores (when the math mode is 'tf32'): have the
         # stencils that produce those inputs round them to nearest (filtered_lrelu.tf32_rounded_outputs)
         from . import filtered_lrelu

@@ -166,7 +166,10 @@ def test_dropin_seam_with_a_real_torch_utils_package(pkg, tmp_path):
         layer = net.Layer()
         assert type(layer).__module__ == 'torch_utils.wrap'          # like torch_utils.persistence's Decorator subclass
         assert layer.forward()(None, None, None) == 'reference conv'
+        flag0 = pkg.filtered_lrelu.round_for_tf32_convs
         assert pkg.patch_modulated_conv(layer) == ['fakemodels.net']
+        assert pkg.filtered_lrelu.round_for_tf32_convs is True       # the patched convs read activations with TF32 tensor cores
+        pkg.filtered_lrelu.round_for_tf32_convs = flag0              # process-wide switch: leave it as it was for the other tests
         from sg3_b200.modulated_conv import modulated_conv2d
         assert layer.forward() is modulated_conv2d
         assert pkg.patch_modulated_conv(layer) == []                 # idempotent
