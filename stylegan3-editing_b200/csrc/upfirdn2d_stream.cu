@@ -6,16 +6,18 @@
 // traffic and a 27 % tile halo, and ends at 0.3 of the HBM roof.  This kernel follows flrelu_stream instead:
 //   * one WARP owns a strip of 128 output columns (lane = 4 adjacent columns: one 128-bit store per lane and row, a warp
 //     writes 512 contiguous bytes) and streams down a chunk of rows; warps never synchronise with each other;
-//   * input rows arrive in a per-warp shared-memory ring by cp.async (16-byte copies when the rows allow it, else 8-byte;
-//     columns and rows outside the image are zero-filled by the copy itself), 4-12 rows in flight per warp;
+//   * input rows arrive in a per-warp shared-memory ring, 4-12 rows in flight per warp: by TMA (cp.async.bulk.tensor behind one
+//     mbarrier per ring slot; the tensor map zero-fills everything outside the image) for the up-2 / same-rate kernels on tensors
+//     TMA can address, by per-lane cp.async pieces (16 bytes when the rows allow it, else 8; out-of-image pieces written as zeros
+//     by the ignore-src form) for the down-2 kernels and for rows that are not 16-byte multiples (see COPY below);
 //   * the x pass reads the lane's window with 128-bit (64-bit for up 2) shared-memory loads and leaves 4 values in registers;
 //   * the y pass keeps a sliding window of x-filtered rows in REGISTERS (static slots: the loop body is unrolled over one
 //     rotation of the window), so the intermediate image of the reference never exists anywhere.
 // All alignment cases are folded into the tap tables on the host: the staged row always starts at a column that is a multiple
 // of 4 (aligned copies and loads); the 0-3 columns between that and the first column a strip needs, and the polyphase branch of
 // each of a lane's 4 outputs, just shift the taps inside a slightly longer static tap range (zero taps outside the filter), and
-// the taps are kernel parameters, i.e. constant-bank operands of the FFMAs.  Same arithmetic as the two passes of the
-// reference (fp32 accumulation, gain applied once at the end).
+// the taps are kernel parameters, i.e. uniform-register operands of the packed FFMA2s.  Same arithmetic as the two passes of the
+// reference up to fp32 summation order (fp32 accumulation; the gain rides on the y taps).
 #include <cuda.h>
 #include <cuda_runtime.h>
 
