@@ -67,7 +67,10 @@ __device__ __forceinline__ float tf32_rna(float v)
 }
 
 // explicit global stores for the epilogue's walking pointers (an opaque pointer update would otherwise demote them to generic ST)
-__device__ __forceinline__ void st_plane(float* q, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(q), "f"(v) : "memory"); }
+#ifndef SG3_CONV_ST
+#define SG3_CONV_ST "st.global"          // tuning: e.g. "st.global.cs" (streaming stores)
+#endif
+__device__ __forceinline__ void st_plane(float* q, float v) { asm volatile(SG3_CONV_ST ".f32 [%0], %1;" ::"l"(q), "f"(v) : "memory"); }
 __device__ __forceinline__ void st_plane(__half* q, float v)
 {
     asm volatile("st.global.b16 [%0], %1;" ::"l"(q), "h"(__half_as_ushort(__float2half_rn(v))) : "memory");
@@ -400,8 +403,11 @@ bool sg3_make_tensor_map(CUtensorMap* m, CUtensorMapDataType type, int rank, con
     cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
     for (int i = 0; i < rank; i++) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; i++) gs[i] = stridesBytes[i];
+#ifndef SG3_TMA_PROMO
+#define SG3_TMA_PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_128B      // tuning: L2 promotion size of every tensor map
+#endif
     return enc(m, type, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
-               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               SG3_TMA_PROMO, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 namespace {
