@@ -159,7 +159,9 @@ int sg3_upfirdn2d_sep(const void* x, void* y, const float* fx, const float* fy,
  * tensor-core contraction sees unbiased operands; round_tf32 = 2: wmod is written as float16 [N][O][ldw] (ldw % 8 == 0),
  * the weight operand of the fp16 tensor-core contraction (what the reference's w.to(x.dtype) produces for fp16 layers);
  * round_tf32 = 3 (layout 0): wmod is f32 [N][2][O][ldw], plane 0 = the weights rounded to TF32, plane 1 = the TF32-rounded
- * residual -- the weight operand of the 3xTF32 contraction (mathMode 2).
+ * residual -- the weight operand of the 3xTF32 contraction (mathMode 2);  round_tf32 = 4: like 1, with the weights first scaled by
+ * 1 + 3.52e-4 = the expected relative loss of an fp32 activation that the tensor core truncates to TF32 (2^-11 / (2 ln 2) for a
+ * log-uniform mantissa): removes the systematic part of the TF32 operand error for free (any layout that 1 accepts).
  * scratch: >= 4 bytes of device memory (batch-global style norm).
  *
  * sg3_modconv_fwd: y[n][o][p] = sum_{i,tap} wmod[n][o][i][tap] * x[n][i][p + tap - pad]

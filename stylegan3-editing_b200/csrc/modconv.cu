@@ -121,6 +121,10 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
             else if (gainMode == 2) v *= gain[i];
             else if (gainMode == 3) v *= gain[(size_t)n * I + i];
             if (roundTf32 == 2) { dstH[q] = __float2half_rn(v); continue; }       // what the reference's w.to(x.dtype) does (:61)
+            // 4: the tensor core will TRUNCATE the fp32 activations this weight multiplies (10 of 23 mantissa bits survive): a
+            // multiplicative bias of -2^-11 * E[1/m] = -2^-11 / (2 ln 2) = -3.52e-4 for a log-uniform mantissa m, the same sign on
+            // every term of the sum.  It is folded into the weight before the weight itself is rounded (to nearest).
+            if (roundTf32 == 4) v *= 1.0f + 3.5217e-4f;
             v = roundTf32 ? round_tf32(v) : v;
             if (transpose == 2) dst[(size_t)(q - i * kk) * tapStep + i] = v;
             else if (transpose == 3) dst[((size_t)(kk - 1 - (q - i * kk)) * I + i) * ldw] = v;
@@ -301,8 +305,8 @@ SG3_EXPORT int sg3_modconv_weights(const float* w, const float* s, const float* 
                                    int N, int I, int O, int k, int ldw, int demodulate, int round_tf32_flag, int transpose, void* stream)
 {
     if (!w || !s || !wmod || !scratch || N < 1 || I < 1 || O < 1 || k < 1) return SG3_E_INVALID;
-    if (transpose < 0 || transpose > 3 || round_tf32_flag < 0 || round_tf32_flag > 3) return SG3_E_INVALID;
-    if (round_tf32_flag >= 2 && transpose != 0) return SG3_E_INVALID;
+    if (transpose < 0 || transpose > 3 || round_tf32_flag < 0 || round_tf32_flag > 4) return SG3_E_INVALID;
+    if ((round_tf32_flag == 2 || round_tf32_flag == 3) && transpose != 0) return SG3_E_INVALID;
     if (transpose == 1 ? (k != 1 || ldw < O) : transpose == 2 ? (ldw < I) : transpose == 3 ? (ldw < O) : (ldw < I * k * k)) return SG3_E_INVALID;
     if (gainMode < 0 || gainMode > 3 || (gainMode && !input_gain)) return SG3_E_INVALID;
     if ((int64_t)N * I > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;

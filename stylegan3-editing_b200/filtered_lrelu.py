@@ -214,9 +214,11 @@ _quiet_fallback = False
 # cuDNN's TF32 kernels round them to nearest when they load them, which halves the operand error.  The modulated-conv kernels of
 # this package read activations straight from HBM by TMA, so the rounding is done where the activation is produced: inside
 # `tf32_rounded_outputs(True)` the fused forward kernel rounds every fp32 output to the nearest TF32 value (two integer
-# operations per value, hidden under the FMA pipe).  `networks.SynthesisLayer` switches it on for the layers whose consumer is
-# a TF32 conv; `round_for_tf32_convs = True` (set by `sg3_b200.patch_modulated_conv()`) does the same for the reference's own
-# layer code whenever the conv math mode is 'tf32'.  Never applied in the backward pass (gradients pass straight through).
+# operations per value, ~2 % of the stencil time).  This is the 'round' policy of `modulated_conv.set_tf32_activation_policy`; the
+# default policy ('compensate') leaves the activations alone and folds the expected truncation loss into the conv weights.  Under
+# 'round', `networks.SynthesisLayer` switches the rounding on for the layers whose consumer is a TF32 conv, and
+# `round_for_tf32_convs = True` (set by `sg3_b200.patch_modulated_conv()`) does the same for the reference's own layer code.
+# Never applied in the backward pass (gradients pass straight through).
 
 _round_tf32 = False
 round_for_tf32_convs = False
@@ -243,8 +245,8 @@ def _rounding_wanted():
     if _round_tf32:
         return True
     if round_for_tf32_convs:
-        from .modulated_conv import _math_mode
-        return _math_mode() == 'tf32'
+        from .modulated_conv import _math_mode, tf32_activation_policy
+        return _math_mode() == 'tf32' and tf32_activation_policy() == 'round'
     return False
 
 

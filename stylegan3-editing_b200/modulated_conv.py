@@ -15,6 +15,16 @@ import torch
 from . import capi
 
 _default_math = None      # None -> follow torch.backends.cudnn.allow_tf32
+
+# How the fp32 activations of a TF32 tensor-core conv are treated.  The tensor core truncates them (cuDNN's TF32 kernels round to
+# nearest when they load them; ours read them straight from HBM by TMA):
+#   'compensate'  (default) the expected truncation loss (a factor 1 - 3.52e-4 on every product) is folded into the modulated weights
+#                 by the weight prologue -- free, and measured as accurate as rounding (tiny generators: image error 7.1e-3 / 6.2e-3
+#                 with plain truncation, 3.1e-3 / 2.3e-3 compensated, 2.3e-3 / 3.3e-3 rounded; cuDNN: 3.2e-3);
+#   'round'       the filtered_lrelu that produces the activations rounds them to the nearest TF32 value
+#                 (filtered_lrelu.tf32_rounded_outputs; exact, ~2 % of the stencil time);
+#   'truncate'    nothing.
+_tf32_policy = 'compensate'
 _pitched_output = True    # 3x3 tensor-core convs write a 16-byte row pitch (see conv_forward); False: contiguous outputs
 
 
@@ -25,6 +35,17 @@ def set_math(mode):
     _default_math = mode
 
 
+def set_tf32_activation_policy(policy):
+    """'compensate' | 'round' | 'truncate' (see the comment at `_tf32_policy`)."""
+    global _tf32_policy
+    assert policy in ('compensate', 'round', 'truncate')
+    _tf32_policy = policy
+
+
+def tf32_activation_policy():
+    return _tf32_policy
+
+
 def _math_mode():
     if _default_math is not None:
         return _default_math
@@ -32,13 +53,14 @@ def _math_mode():
 
 
 def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, transpose=False, tap_major=False, half=False,
-                    split=False, dgrad_taps=False):
+                    split=False, dgrad_taps=False, compensate=False):
     """[N, O, ldw >= I*k*k] float32 modulated (+demodulated, +input-gain) weights, rows zero padded  (:39-56).
     transpose=True (1x1 only): [N, I, ldw >= O], the weight operand of the input-gradient GEMM.
     tap_major=True: [N, k*k, O, ldw >= I], the operand of the 3x3 tensor-core kernel.
     half=True: float16 [N, O, ldw] (what `w.to(x.dtype)` of :61 produces for fp16 layers), operand of the fp16 tensor-core kernel.
     split=True: [N, 2, O, ldw], TF32 head and TF32 tail of every weight, operand of the 3xTF32 kernel (math='fp32x3').
-    dgrad_taps=True: [N, k*k, I, ldw >= O], taps flipped and channels transposed: the operand of the k x k input-gradient conv."""
+    dgrad_taps=True: [N, k*k, I, ldw >= O], taps flipped and channels transposed: the operand of the k x k input-gradient conv.
+    compensate=True (with round_tf32): weights scaled by 1 + 3.52e-4, the expected truncation loss of the activations (see `_tf32_policy`)."""
     capi.require_cuda(w, 'modulated_conv2d')
     O, I, kh, kw = w.shape
     assert kh == kw
@@ -82,7 +104,7 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, tr
     with torch.cuda.device(w.device):
         rc = capi.lib().sg3_modconv_weights(w.data_ptr(), s.data_ptr(), g.data_ptr() if g is not None else None, mode,
                                             wmod.data_ptr(), scratch.data_ptr(), N, I, O, kh, ldw, int(bool(demodulate)),
-                                            3 if split else (2 if half else int(bool(round_tf32))), layout, capi.stream_ptr(w.device))
+                                            3 if split else (2 if half else ((4 if compensate else 1) if round_tf32 else 0)), layout, capi.stream_ptr(w.device))
     capi.check(rc, 'sg3_modconv_weights')
     return wmod
 
@@ -182,7 +204,8 @@ class _ModConv(torch.autograd.Function):
         if math in ('tf32', 'fp32x3') and not tc_supported(I, O, x32.shape[2], x32.shape[3], k, padding):
             math = 'fp32'                  # shapes without a tensor-core kernel run the exact SIMT contraction
         wmod = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, round_tf32=(math == 'tf32'),
-                               tap_major=(math == 'tf32' and k > 1), split=(math == 'fp32x3'))
+                               tap_major=(math == 'tf32' and k > 1), split=(math == 'fp32x3'),
+                               compensate=(math == 'tf32' and _tf32_policy == 'compensate'))
         y = conv_forward(x32, wmod, O, k, padding, math)
         if y is None and math in ('tf32', 'fp32x3'):
             # the shape has a tensor-core kernel but this tensor does not (unaligned view, tensor-map encode failure):

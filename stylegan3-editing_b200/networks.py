@@ -17,7 +17,7 @@ import scipy.special
 import torch
 
 from . import bias_act, filtered_lrelu
-from .modulated_conv import modulated_conv2d, _math_mode
+from .modulated_conv import modulated_conv2d, _math_mode, tf32_activation_policy
 
 __all__ = ['FullyConnectedLayer', 'MappingNetwork', 'SynthesisInput', 'SynthesisLayer', 'SynthesisNetwork',
            'Generator', 'GraphedSynthesis', 'PipelinedSynthesis', 'modulated_conv2d', 'CONFIG_R', 'CONFIG_T']
@@ -228,8 +228,9 @@ class SynthesisLayer(torch.nn.Module):
     def act_part(self, x):
         """bias -> filtered leaky ReLU at the temporary sampling rate   (reference :361-368)."""
         dtype = x.dtype
-        # the next layer's convolution reads this output with TF32 tensor cores (which truncate): round to nearest here
-        rnd = (not self.is_torgb) and dtype == torch.float32 and _math_mode() == 'tf32'
+        # policy 'round': the next layer's convolution reads this output with TF32 tensor cores (which truncate): round to nearest
+        # here.  (The default policy compensates the truncation in the conv's weight prologue instead, see modulated_conv.py.)
+        rnd = (not self.is_torgb) and dtype == torch.float32 and _math_mode() == 'tf32' and tf32_activation_policy() == 'round'
         with filtered_lrelu.tf32_rounded_outputs(rnd):
             x = filtered_lrelu.filtered_lrelu(
                 x=x, fu=self.up_filter, fd=self.down_filter, b=self.bias.to(x.dtype), up=self.up_factor, down=self.down_factor,

@@ -411,6 +411,9 @@ def test_tf32_rounding_switch_logic():
     try:
         fl.round_for_tf32_convs = True                        # what patch_modulated_conv() sets
         modulated_conv.set_math('tf32')
+        assert modulated_conv.tf32_activation_policy() == 'compensate'
+        assert fl._rounding_wanted() is False                 # default policy: the conv weights carry the correction instead
+        modulated_conv.set_tf32_activation_policy('round')
         assert fl._rounding_wanted() is True
         modulated_conv.set_math('fp32')
         assert fl._rounding_wanted() is False
@@ -418,5 +421,6 @@ def test_tf32_rounding_switch_logic():
         assert fl._rounding_wanted() is False
     finally:
         fl.round_for_tf32_convs = old
+        modulated_conv.set_tf32_activation_policy('compensate')
         modulated_conv.set_math(None)
     assert sg3_b200.capi.FLRELU_ROUND_TF32 == 1

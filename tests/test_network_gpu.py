@@ -97,25 +97,23 @@ def test_tiny_generator_fp32(pkg, name):
 
 @pytest.mark.parametrize('name', ['tinyR', 'tinyT'])
 def test_tiny_generator_tf32(pkg, name):
+    """TF32 tensor-core convs.  The tensor core truncates its fp32 activations; the three policies of
+    modulated_conv.set_tf32_activation_policy: 'compensate' (default: the expected truncation loss is folded into the weights),
+    'round' (the producing stencil rounds its outputs to the nearest TF32 value), 'truncate' (nothing).  Measured on B200: 3.1e-3 /
+    2.3e-3 (tinyR / tinyT) compensated, 2.3e-3 / 3.3e-3 rounded, 7.1e-3 / 6.2e-3 truncated; the reference's cuDNN TF32 path: 3.2e-3 (tinyT)."""
+    from sg3_b200 import modulated_conv as mc
     G, g = _build(pkg, name)
-    pkg.modulated_conv.set_math('tf32')
+    mc.set_math('tf32')
+    errs = {}
     try:
-        img = G.synthesis(cu(g.z[f'{name}/ws']), noise_mode='const', force_fp32=True)
-        err = rel_err(img.cpu().numpy(), g.z[f'{name}/img'])
-        assert err < 5e-3          # measured 2.3e-3 (tinyR) / 3.3e-3 (tinyT); the reference's cuDNN TF32 path: 3.2e-3 on tinyT
-        # The layers round their outputs to the nearest TF32 value for the tensor-core conv that consumes them (which would
-        # truncate): compare with the same network when the rounding is switched off -- it must not be the worse of the two
-        # by more than noise -- and check that the switch actually changes the stored activations of a layer.
-        import sg3_b200.networks as nw
-        orig = nw._math_mode
-        nw._math_mode = lambda: 'fp32-no-rounding'          # act_part then leaves the outputs alone; the convs still run TF32
-        try:
-            img0 = G.synthesis(cu(g.z[f'{name}/ws']), noise_mode='const', force_fp32=True)
-        finally:
-            nw._math_mode = orig
-        err0 = rel_err(img0.cpu().numpy(), g.z[f'{name}/img'])
-        print(f'{name}: TF32 image error with rounded activations {err:.2e}, truncated {err0:.2e}')
-        assert err < 1.25 * err0 + 1e-4
+        for policy in ('compensate', 'round', 'truncate'):
+            mc.set_tf32_activation_policy(policy)
+            img = G.synthesis(cu(g.z[f'{name}/ws']), noise_mode='const', force_fp32=True)
+            errs[policy] = rel_err(img.cpu().numpy(), g.z[f'{name}/img'])
+        print(name, {k: f'{v:.2e}' for k, v in errs.items()})
+        assert errs['compensate'] < 5e-3 and errs['round'] < 5e-3 and errs['truncate'] < 1e-2
+        assert errs['compensate'] < errs['truncate'] and errs['round'] < errs['truncate']
+        # the 'round' switch of the fused kernel: TF32-representable outputs within half a TF32 ulp of the unrounded ones
         x = torch.randn(2, 8, 20, 20, device='cuda')
         L = getattr(G.synthesis, G.synthesis.layer_names[3])
         fl = pkg.filtered_lrelu
@@ -123,12 +121,19 @@ def test_tiny_generator_tf32(pkg, name):
         y0 = fl.filtered_lrelu(x, **kw)
         with fl.tf32_rounded_outputs(True):
             y1 = fl.filtered_lrelu(x, **kw)
-        bits = y1.view(torch.int32)
-        assert int((bits & 0x1fff).abs().max()) == 0                              # TF32-representable
-        assert float((y1 - y0).abs().max()) <= float(y0.abs().max()) * 2.0 ** -11   # within half a TF32 ulp
+        assert int((y1.view(torch.int32) & 0x1fff).abs().max()) == 0
+        assert float((y1 - y0).abs().max()) <= float(y0.abs().max()) * 2.0 ** -11
         assert not torch.equal(y0, y1)
+        # the 'compensate' switch of the weight prologue: weights scaled by 1 + 3.52e-4 before their own rounding
+        w = torch.randn(24, 40, 1, 1, device='cuda')
+        sty = torch.randn(2, 40, device='cuda')
+        w1 = mc.modconv_weights(w, sty, round_tf32=True)
+        w4 = mc.modconv_weights(w, sty, round_tf32=True, compensate=True)
+        ratio = (w4[:, :, :40] / w1[:, :, :40]).double().mean().item()
+        assert abs(ratio - (1 + 3.5217e-4)) < 1e-4
     finally:
-        pkg.modulated_conv.set_math(None)
+        mc.set_tf32_activation_policy('compensate')
+        mc.set_math(None)
 
 
 @pytest.mark.parametrize('name', ['tinyR', 'tinyT'])
