@@ -189,6 +189,15 @@ int sg3_modconv_weights(const float* w, const float* s, const float* input_gain,
  * dw [N][O][ldw] must be zeroed by the caller. */
 int sg3_modconv_wgrad(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, void* stream);
 
+/* The same for 3x3 kernels (pad 0 or 2; TF32 tcgen05, the row range split across CTAs, fp32 atomics) -- replaces the grouped
+ * weight-gradient convolution the reference runs through conv2d_gradfix.py:103-129 for networks_stylegan3.py:59-62:
+ *   dw[n][ky*3+kx][o][i] += sum_oy sum_ox dy[n][o][oy][ox] * x[n][i][oy+ky-pad][ox+kx-pad]      (x = 0 outside the image)
+ * dy [N][O][OH][dyPitch], x [N][I][H][xPitch] with OH = H + 2 pad - 2; row pitches in floats, multiples of 4, 0 = dense (then
+ * the width itself must be a multiple of 4); dw [N][9][O][ldw >= I] (tap-major like weight layout 2) zeroed by the caller.
+ * SG3_E_NOKERNEL when a pitch or base pointer is not TMA-addressable. */
+int sg3_modconv_wgrad3(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int pad, int ldw,
+                       int dyPitch, int xPitch, void* stream);
+
 int sg3_modconv_tc_supported(int I, int O, int H, int W, int k, int pad);
 
 /* Backward of sg3_modconv_weights for 1x1 kernels (the chain rule of networks_stylegan3.py:39-56, ~35 eager kernels per layer

@@ -61,6 +61,7 @@ _PROTOS = {
     'sg3_modconv_weights_bwd': (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     'sg3_modconv_tc_supported': (_I, [_I, _I, _I, _I, _I, _I]),
     'sg3_modconv_wgrad': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    'sg3_modconv_wgrad3': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'sg3_modconv_fwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'sg3_modconv_set_smem_budget': (_I, [_I]),
     'sg3_modconv_fwd_pitched': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -9,6 +9,8 @@
 #include "common.cuh"
 
 int sg3_modconv_wgrad_tc(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, cudaStream_t stream);
+int sg3_modconv_wgrad3_tc(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int pad, int ldw,
+                          int dyPitch, int xPitch, cudaStream_t stream);
 int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw,
                         int xPitch, int yPitch, cudaStream_t stream);
 int sg3_modconv_tc3_supported(int I, int O, int H, int W, int k, int pad);
@@ -383,4 +385,11 @@ SG3_EXPORT int sg3_modconv_wgrad(const float* dy, const float* x, float* dw, int
 {
     if (!dy || !x || !dw || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || ldw < I) return SG3_E_INVALID;
     return sg3_modconv_wgrad_tc(dy, x, dw, N, I, O, H, W, ldw, (cudaStream_t)stream);
+}
+
+SG3_EXPORT int sg3_modconv_wgrad3(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int pad, int ldw,
+                                  int dyPitch, int xPitch, void* stream)
+{
+    if (!dy || !x || !dw || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || pad < 0 || ldw < I || dyPitch < 0 || xPitch < 0) return SG3_E_INVALID;
+    return sg3_modconv_wgrad3_tc(dy, x, dw, N, I, O, H, W, pad, ldw, dyPitch, xPitch, (cudaStream_t)stream);
 }

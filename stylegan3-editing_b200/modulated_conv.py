@@ -345,15 +345,45 @@ def _weights_formula(w, s, demodulate, input_gain, N):
     return w
 
 
+def _tma_rows(t):
+    """`t` itself when its rows are TMA-addressable (row-pitched view or dense, 16-byte pitch and base), else a row-pitched copy."""
+    if _row_pitched(t) and t.stride(2) % 4 == 0 and t.data_ptr() % 16 == 0:
+        return t
+    buf = empty_row_pitched(t.shape, t.dtype, t.device)
+    buf.copy_(t)
+    return buf
+
+
+def conv3x3_weight_grad(x, dy, padding):
+    """Per-sample weight gradient of the 3x3 conv on the tcgen05 kernel (`sg3_modconv_wgrad3`, TF32 operands, fp32 accumulation):
+    dW[n, o, i, ky, kx] = sum dy[n, o, oy, ox] * x[n, i, oy + ky - pad, ox + kx - pad] -- what the reference gets from the grouped
+    `conv2d_weight` of conv2d_gradfix.py:103-129.  x [N, I, H, W], dy [N, O, H + 2 pad - 2, W + 2 pad - 2], float32 (dense or
+    row-pitched views; anything else is copied into a row-pitched buffer).  Returns [N, O, I, 3, 3] (a permuted view of the
+    tap-major buffer the kernel accumulates into) or None when the library has no kernel for the call."""
+    N, I, H, W = x.shape
+    O = dy.shape[1]
+    xp, dyp = _tma_rows(x), _tma_rows(dy)
+    ldw = (I + 3) // 4 * 4
+    dWt = torch.zeros([N, 9, O, ldw], dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = capi.lib().sg3_modconv_wgrad3(dyp.data_ptr(), xp.data_ptr(), dWt.data_ptr(), N, I, O, H, W, int(padding), ldw,
+                                           dyp.stride(2), xp.stride(2), capi.stream_ptr(x.device))
+    if rc == capi.SG3_E_NOKERNEL:
+        return None
+    capi.check(rc, 'sg3_modconv_wgrad3')
+    return dWt[..., :I].reshape(N, 3, 3, O, I).permute(0, 3, 4, 1, 2)
+
+
 def _native_backward_3x3(x, w, s, input_gain, dy, demodulate, padding, need):
     """dx of the 3x3 modulated conv on the tcgen05 kernel: the input gradient of a stride-1 convolution is the convolution of
     dy with the flipped, channel-transposed taps and padding 2 - pad -- the SAME implicit-GEMM kernel with the weight prologue
     writing layout 3.  dy arrives from the filtered_lrelu backward kernel as a row-pitched view (its width, e.g. 1046, is not a
-    TMA pitch), otherwise it is copied into one.  dw / ds: the per-sample weight gradient is one library (cuDNN) grouped
-    weight-gradient call, then autograd through the small weight expression.  None when the kernel has no plan for the shape."""
+    TMA pitch), otherwise it is copied into one.  dw / ds: the per-sample weight gradient is the tcgen05 kernel of
+    `conv3x3_weight_grad`, then autograd through the small weight expression.  None when the kernels have no plan for the shape."""
     N, I, H, W = x.shape
     O = w.shape[0]
     dx = dw = ds = None
+    dy_p = None
     if need[0]:
         if not (_row_pitched(dy) and dy.stride(2) % 4 == 0 and dy.data_ptr() % 16 == 0):
             buf = empty_row_pitched(dy.shape, dy.dtype, dy.device)
@@ -371,10 +401,9 @@ def _native_backward_3x3(x, w, s, input_gain, dy, demodulate, padding, need):
         if dx is None:
             return None
     if need[1] or need[2]:
-        dyc = dy.contiguous()
-        with torch.backends.cudnn.flags(allow_tf32=True):
-            dW = torch.nn.grad.conv2d_weight(x.reshape(1, N * I, H, W), [N * O, I, 3, 3], dyc.reshape(1, N * O, *dyc.shape[2:]),
-                                             padding=padding, groups=N).reshape(N, O, I, 3, 3)
+        dW = conv3x3_weight_grad(x, dy if dy_p is None else dy_p, padding)
+        if dW is None:
+            return None
         with torch.enable_grad():
             ws = w.detach().requires_grad_(need[1])
             ss = s.detach().requires_grad_(need[2])

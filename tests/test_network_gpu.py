@@ -614,6 +614,56 @@ def test_native_3x3_input_gradient(pkg):
                 g = cu(dy)
             n0 = pkg.capi.lib().sg3_launch_count()
             dx, dw, ds = torch.autograd.grad(y, [xt, wt, st], g)
-            assert pkg.capi.lib().sg3_launch_count() - n0 == 3          # weight prologue (2) + the tensor-core conv (1)
+            # weight prologue (2) + the tensor-core dgrad conv (1) + the tensor-core weight gradient (1): no library convolution
+            assert pkg.capi.lib().sg3_launch_count() - n0 == 4
             assert rel_err(dx.cpu().numpy(), dx_ref) < 2e-3, (N, I, O, H, pad, pitched)
             assert rel_err(dw.cpu().numpy(), dw_ref) < 2e-3 and rel_err(ds.cpu().numpy(), ds_ref) < 2e-3
+
+
+@pytest.mark.parametrize('shape', [
+    # N, I, O, H, W, pad
+    (2, 40, 24, 24, 24, 2),          # OW = 26: dy goes through a row-pitched copy
+    (1, 96, 130, 20, 36, 2),         # two o tiles, two i tiles of 48
+    (2, 33, 64, 20, 20, 0),          # padding 0 (dgrad-style geometry), one ragged i tile
+    (1, 51, 32, 150, 64, 2),         # tall: the row range is split across CTAs (fp32 atomics)
+    (1, 16, 16, 9, 132, 2),          # five column chunks, the last one ragged
+    (3, 7, 5, 12, 38, 2),            # W % 4 != 0: x is re-pitched too; tiny channel counts
+    (1, 200, 51, 16, 16, 2),         # five i tiles
+])
+def test_wgrad3_vs_oracle(pkg, shape):
+    """3x3 weight gradient on the tcgen05 kernel (sg3_modconv_wgrad3: TMA dy tiles, SIMT-shifted x copies, nine TMEM accumulators)
+    vs the CPU oracle's conv2d_wgrad; TF32 operands, fp32 accumulation: 2e-3 of max |dw| (stated separately from fp32 parity)."""
+    from oracle import sg3_oracle as orc
+    N, I, O, H, W, pad = shape
+    rng = np.random.RandomState(sum(shape))
+    x = rng.randn(N, I, H, W).astype(np.float32)
+    dy = rng.randn(N, O, H + 2 * pad - 2, W + 2 * pad - 2).astype(np.float32)
+    ref = orc.conv2d_wgrad(x, dy, 3, padding=pad)
+    n0 = pkg.capi.lib().sg3_launch_count()
+    got = pkg.modulated_conv.conv3x3_weight_grad(cu(x), cu(dy), pad)
+    assert got is not None and pkg.capi.lib().sg3_launch_count() - n0 == 1
+    assert tuple(got.shape) == ref.shape
+    assert rel_err(got.cpu().numpy(), ref) < 2e-3, shape
+    # structured input: a single bright pixel of x and of dy picks exactly one tap (catches a shifted or transposed tap index)
+    x1 = np.zeros_like(x); dy1 = np.zeros_like(dy)
+    x1[0, I - 1, H // 2, W // 2] = 1.0
+    for ky in range(3):
+        for kx in range(3):
+            dy1[:] = 0
+            oy, ox = H // 2 - ky + pad, W // 2 - kx + pad
+            dy1[0, O - 1, oy, ox] = 1.0
+            g1 = pkg.modulated_conv.conv3x3_weight_grad(cu(x1), cu(dy1), pad).cpu().numpy()
+            want = np.zeros_like(ref); want[0, O - 1, I - 1, ky, kx] = 1.0
+            assert np.array_equal(g1, want), (shape, ky, kx)
+
+
+def test_wgrad3_rejects_unaddressable(pkg):
+    """The C entry point reports NOKERNEL (not a wrong answer) for pitches / pointers TMA cannot address."""
+    L = pkg.capi.lib()
+    x = torch.zeros(1, 8, 10, 12, device='cuda'); dy = torch.zeros(1, 8, 12, 16, device='cuda'); dw = torch.zeros(1, 9, 8, 8, device='cuda')
+    st = pkg.capi.stream_ptr(x.device)
+    assert L.sg3_modconv_wgrad3(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), 1, 8, 8, 10, 12, 2, 8, 0, 0, st) == pkg.capi.SG3_E_NOKERNEL   # OW = 14
+    assert L.sg3_modconv_wgrad3(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), 1, 8, 8, 10, 12, 2, 8, 16, 0, st) == 0
+    assert L.sg3_modconv_wgrad3(dy.data_ptr(), x.data_ptr() + 4, dw.data_ptr(), 1, 8, 8, 10, 12, 2, 8, 16, 0, st) == pkg.capi.SG3_E_NOKERNEL
+    assert L.sg3_modconv_wgrad3(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), 1, 8, 8, 10, 12, 1, 8, 16, 0, st) == pkg.capi.SG3_E_NOKERNEL   # pad 1
+    torch.cuda.synchronize()
