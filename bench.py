@@ -56,6 +56,9 @@ def parse_args():
                          'forward (configs[1]); restyle: ReStyle-pSp inversion, 5 steps, batch 8 (configs[3]); pti: PTI fine-tuning, '
                          '64 frames, batch 4 per GPU, NCCL gradient all-reduce (configs[4])')
     ap.add_argument('--frames', type=int, default=64, help='--config pti: global number of frames')
+    ap.add_argument('--generator', default='R', choices=['R', 'T'],
+                    help='--config pti: the generator being fine-tuned (R = the FFHQ model of configs[4]; T = the 3x3-conv "landscape" '
+                         'model, models/stylegan3/model.py:30-40)')
     ap.add_argument('--eager', action='store_true', help='--config restyle: no CUDA-graph replay of the synthesis calls')
     args = ap.parse_args()
     if args.config == 'T':

@@ -17,6 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 R1024 = dict(z_dim=512, c_dim=0, w_dim=512, img_resolution=1024, img_channels=3,
              channel_base=65536, channel_max=1024, conv_kernel=1, use_radial_filters=True)
+T1024 = dict(z_dim=512, c_dim=0, w_dim=512, img_resolution=1024, img_channels=3,
+             channel_base=32768, channel_max=512, conv_kernel=3, use_radial_filters=False)
 
 
 def _setup(args):
@@ -193,7 +195,8 @@ def run_pti(args, ClockSampler):
     B = 4 if args.batch == 32 else args.batch               # run_pti_video.py:43 batch_size = 4
     frames_total = args.frames
     torch.manual_seed(100 + rank)                            # deliberately different init per rank: the broadcast must fix it
-    G = networks.Generator(**R1024).to(dev)
+    gen_name = getattr(args, 'generator', 'R')
+    G = networks.Generator(**(T1024 if gen_name == 'T' else R1024)).to(dev)
     sharding.broadcast_parameters(G)
     gen = torch.Generator().manual_seed(7)
     z = torch.randn(frames_total, 512, generator=gen)
@@ -279,7 +282,7 @@ def run_pti(args, ClockSampler):
         return
     losses = [float(l) for l in losses]
     out = dict(
-        metric='PTI fine-tuning of StyleGAN3-R 1024^2 over video frames, frames/sec (forward + backward + Adam)',
+        metric=f'PTI fine-tuning of StyleGAN3-{gen_name} 1024^2 over video frames, frames/sec (forward + backward + Adam)',
         value=world * B * args.steps / (ms_total * 1e-3), unit='frames/s', n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
         ms_per_step=ms_total / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
         dtype='f32 (tf32 tensor-core conv)', data='synthetic',
