@@ -193,7 +193,8 @@ int sg3_modconv_wgrad(const float* dy, const float* x, float* dw, int N, int I, 
  * weight-gradient convolution the reference runs through conv2d_gradfix.py:103-129 for networks_stylegan3.py:59-62:
  *   dw[n][ky*3+kx][o][i] += sum_oy sum_ox dy[n][o][oy][ox] * x[n][i][oy+ky-pad][ox+kx-pad]      (x = 0 outside the image)
  * dy [N][O][OH][dyPitch], x [N][I][H][xPitch] with OH = H + 2 pad - 2; row pitches in floats, multiples of 4, 0 = dense (then
- * the width itself must be a multiple of 4); dw [N][9][O][ldw >= I] (tap-major like weight layout 2) zeroed by the caller.
+ * the width itself must be a multiple of 4); dw [N][9][O][ldw >= I] (tap-major like weight layout 2; ldw % 4 == 0, 16-byte aligned)
+ * zeroed by the caller.
  * SG3_E_NOKERNEL when a pitch or base pointer is not TMA-addressable. */
 int sg3_modconv_wgrad3(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int pad, int ldw,
                        int dyPitch, int xPitch, void* stream);

@@ -288,6 +288,7 @@ struct WgParams {
     int BN, tmemCols;
     int tilesO, tilesI, splits, kPerSplit;   // k-tiles (32 pixels) per split
     int kTilesTotal;
+    int vec;               // dw rows are 16-byte aligned (ldw % 4 == 0, aligned base): 128-bit reductions
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -358,10 +359,21 @@ modconv_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_con
             uint32_t r[32];
             tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + (uint32_t)c, r);
             if (o < p.O) {
+                // 128-bit reductions (REDG.E.ADD.F32x4): rows are ldw = 4k floats apart and i0 + c is a multiple of 16; the columns in
+                // [I, ldw) receive the zero products of TMA's zero-filled channel rows.  (Scalar reductions, one row per lane, were
+                // most of this kernel on the low-resolution layers: measured on the 3x3 sibling, profiles/r02_wgrad3.md.)
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
+                for (int j = 0; j < 32; j += 4) {
                     const int i = i0 + c + j;
-                    if (c + j < p.BN && i < p.I) atomicAdd(row + i, __uint_as_float(r[j]));
+                    if (p.vec) {
+                        if (c + j < p.BN && i < p.ldw)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + i), "f"(__uint_as_float(r[j])),
+                                         "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])) : "memory");
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (c + j + q < p.BN && i + q < p.I) atomicAdd(row + i + q, __uint_as_float(r[j + q]));
+                    }
                 }
             }
         }
@@ -528,6 +540,7 @@ int sg3_modconv_wgrad_tc(const float* dy, const float* x, float* dw, int N, int 
     if (((uintptr_t)x & 15) || ((uintptr_t)dy & 15)) return SG3_E_NOKERNEL;
     WgParams p;
     p.dw = dw; p.N = N; p.I = I; p.O = O; p.P = (int)P; p.ldw = ldw;
+    p.vec = (ldw % 4 == 0 && ((uintptr_t)dw & 15) == 0) ? 1 : 0;
     const int nt = (I + 255) / 256;
     int bn = ((I + nt - 1) / nt + 15) & ~15;
     if (bn < 16) bn = 16;

@@ -247,6 +247,7 @@ int sg3_modconv_wgrad3_tc(const float* dy, const float* x, float* dw, int N, int
     const int xp = xPitch > 0 ? xPitch : W, dyp = dyPitch > 0 ? dyPitch : OW;
     if (xp < W || dyp < OW || xp % 4 != 0 || dyp % 4 != 0 || ldw < I) return SG3_E_NOKERNEL;        // TMA: 16-byte row pitches
     if (((uintptr_t)x & 15) || ((uintptr_t)dy & 15)) return SG3_E_NOKERNEL;
+    if (ldw % 4 != 0 || ((uintptr_t)dw & 15)) return SG3_E_NOKERNEL;                                  // 128-bit reductions into dw
     if (N < 1 || I < 1 || O < 1) return SG3_E_INVALID;
 
     Wg3Params p;

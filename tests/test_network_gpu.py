@@ -667,3 +667,21 @@ def test_wgrad3_rejects_unaddressable(pkg):
     assert L.sg3_modconv_wgrad3(dy.data_ptr(), x.data_ptr() + 4, dw.data_ptr(), 1, 8, 8, 10, 12, 2, 8, 16, 0, st) == pkg.capi.SG3_E_NOKERNEL
     assert L.sg3_modconv_wgrad3(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), 1, 8, 8, 10, 12, 1, 8, 16, 0, st) == pkg.capi.SG3_E_NOKERNEL   # pad 1
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize('I,O,P,ldw', [(33, 20, (12, 16), 33), (33, 20, (12, 16), 36), (161, 102, (24, 40), 192), (70, 130, (9, 12), 71)])
+def test_wgrad1_c_abi_vs_oracle(pkg, I, O, P, ldw):
+    """1x1 weight gradient through the C ABI (sg3_modconv_wgrad): rows of dw that are 16-byte aligned take 128-bit reductions
+    (red.global.add.v4.f32), any other ldw the scalar atomics; both against the oracle, padding columns [I, ldw) stay zero."""
+    from oracle import sg3_oracle as orc
+    rng = np.random.RandomState(I + O + ldw)
+    N, (H, W) = 2, P
+    x = rng.randn(N, I, H, W).astype(np.float32)
+    dy = rng.randn(N, O, H, W).astype(np.float32)
+    ref = orc.conv2d_wgrad(x, dy, 1, padding=0).reshape(N, O, I)
+    xt, dyt = cu(x), cu(dy)
+    dw = torch.zeros(N, O, ldw, device='cuda')
+    rc = pkg.capi.lib().sg3_modconv_wgrad(dyt.data_ptr(), xt.data_ptr(), dw.data_ptr(), N, I, O, H, W, ldw, pkg.capi.stream_ptr(xt.device))
+    assert rc == 0
+    assert rel_err(dw[:, :, :I].cpu().numpy(), ref) < 2e-3
+    assert float(dw[:, :, I:].abs().max()) == 0.0 if ldw > I else True
