@@ -288,6 +288,7 @@ struct WgParams {
     int BN, tmemCols;
     int tilesO, tilesI, splits, kPerSplit;   // k-tiles (32 pixels) per split
     int kTilesTotal;
+    int stages;            // operand ring depth
     int vec;               // dw rows are 16-byte aligned (ldw % 4 == 0, aligned base): 128-bit reductions
 };
 
@@ -299,7 +300,7 @@ modconv_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_con
     __shared__ uint32_t tmemBase;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int stageBytes = A_STAGE_BYTES + p.BN * BK * 4;
-    const int stages = p.BN > 128 ? 4 : 6;
+    const int stages = p.stages;
     const uint32_t tiles = (smem_u32(smem) + 1023u) & ~1023u;
 
     long long t = blockIdx.x;
@@ -487,7 +488,9 @@ int launch_fwd_tc(const void* x, const void* wmod, void* y, int N, int I, int O,
         const uint32_t box[3] = {(uint32_t)kst, (uint32_t)bn, 1};
         if (!sg3_make_tensor_map(&mapW, dt, 3, wmod, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return SG3_E_NOKERNEL;
     }
-    // operand stages: 4 x 48 KB or 6 x <= 32 KB; X3: 3 x <= 64 KB
+    // operand stages: 4 x 48 KB or 6 x <= 32 KB; X3: 3 x <= 64 KB.  Measured (tools/prof_conv.py 32 R, alternating A/B runs): a deeper
+    // ring for the narrow top layers (8 x 24 KB at BN = 64, 10 x 18 KB at BN = 16) is SLOWER (L12 4.17 -> 4.58 ms, L13 / L14 unchanged):
+    // more row streams in flight in DRAM, as for the stencil kernels.
     p.stages = X3 ? 3 : (bn > 128 ? 4 : 6);
     SG3_TRACE_SET(p);
     const int stageBytes = (X3 ? 2 : 1) * (A_STAGE_BYTES + bn * BK * 4);
@@ -566,6 +569,7 @@ int sg3_modconv_wgrad_tc(const float* dy, const float* x, float* dw, int N, int 
     if (!make_map3(&mapDY, dy, (uint64_t)P, (uint64_t)O, (uint64_t)N, (uint64_t)P * 4, (uint64_t)P * O * 4, BK, BM)) return SG3_E_NOKERNEL;
     if (!make_map3(&mapX, x, (uint64_t)P, (uint64_t)I, (uint64_t)N, (uint64_t)P * 4, (uint64_t)P * I * 4, BK, (uint32_t)bn)) return SG3_E_NOKERNEL;
     const int stages = bn > 128 ? 4 : 6;
+    p.stages = stages;
     const int smemBytes = stages * (A_STAGE_BYTES + bn * BK * 4) + 1024;
     static Sg3DeviceOnce once;
     const cudaError_t attrErr = once.run([] { return cudaFuncSetAttribute(modconv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
