@@ -157,7 +157,8 @@ int sg3_upfirdn2d_sep(const void* x, void* y, const float* fx, const float* fy,
  * 2 = [I], 3 = [N][I].  wmod is f32 [N][O][ldw] with row pitch ldw >= I*k*k floats (zero padded;
  * the tensor-core path needs ldw % 4 == 0); round_tf32 = 1: each value is rounded to the nearest TF32 so the
  * tensor-core contraction sees unbiased operands; round_tf32 = 2: wmod is written as float16 [N][O][ldw] (ldw % 8 == 0),
- * the weight operand of the fp16 tensor-core contraction (what the reference's w.to(x.dtype) produces for fp16 layers);
+ * the weight operand of the fp16 tensor-core contraction (what the reference's w.to(x.dtype) produces for fp16 layers); with
+ * transpose = 2 as float16 [N][k*k][O][ldw >= I], the operand of the fp16 3x3 kernel;
  * round_tf32 = 3 (layout 0): wmod is f32 [N][2][O][ldw], plane 0 = the weights rounded to TF32, plane 1 = the TF32-rounded
  * residual -- the weight operand of the 3xTF32 contraction (mathMode 2);  round_tf32 = 4: like 1, with the weights first scaled by
  * 1 + 3.52e-4 = the expected relative loss of an fp32 activation that the tensor core truncates to TF32 (2^-11 / (2 ln 2) for a
@@ -168,7 +169,8 @@ int sg3_upfirdn2d_sep(const void* x, void* y, const float* fx, const float* fy,
  * x [N][I][H][W] contiguous, y [N][O][H+2pad-k+1][W+2pad-k+1] contiguous, dtype f32.
  * mathMode 0: FP32 SIMT (exact fp32 accumulate);  1: TF32 tcgen05 implicit GEMM;  2: 3xTF32 tcgen05 GEMM (k = 1 only: both
  * operands split into TF32 head + tail, three MMAs per K step, fp32-accurate to ~1e-6; wmod from round_tf32 = 3).
- * dtype f16 (mathMode 1, k = 1, H*W % 8 == 0): x, y and wmod are float16, kind::f16 MMAs with fp32 accumulation.
+ * dtype f16 (mathMode 1; k = 1 with H*W % 8 == 0, or k = 3 with pad 0 / 2 and a row pitch of x that is a multiple of 8 -- pass it
+ * through sg3_modconv_fwd_pitched when W is not): x, y and wmod are float16, kind::f16 MMAs with fp32 accumulation.
  * ---------------------------------------------------------------------- */
 int sg3_modconv_weights(const float* w, const float* s, const float* input_gain, int gainMode,
                         float* wmod, float* scratch,
@@ -216,7 +218,8 @@ int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
  * consumes y stages its input by TMA even when OW * 4 is not a multiple of 16 (every 3x3 layer of config T: OW = 38 ... 1046).
  * xPitch: lets the same kernel compute the 3x3 INPUT GRADIENT from a dy whose width is not a multiple of 4 (dy comes out of the
  * filtered_lrelu backward kernel with a padded pitch): dX = sg3_modconv_fwd_pitched(dY, wmod in layout 3, pad' = 2 - pad).
- * Implemented by the 3x3 tensor-core kernel (mathMode 1, k = 3); other paths answer SG3_E_NOKERNEL for real pitches. */
+ * Implemented by the 3x3 tensor-core kernels (mathMode 1, k = 3; f32 pitches are multiples of 4 elements, f16 pitches of 8);
+ * other paths answer SG3_E_NOKERNEL for real pitches. */
 int sg3_modconv_fwd_pitched(const void* x, const float* wmod, void* y,
                             int N, int I, int O, int H, int W, int k, int pad, int ldw, int xPitch, int yPitch,
                             int mathMode, int dtype, void* stream);

@@ -13,6 +13,8 @@ int sg3_modconv_wgrad3_tc(const float* dy, const float* x, float* dw, int N, int
                           int dyPitch, int xPitch, cudaStream_t stream);
 int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw,
                         int xPitch, int yPitch, cudaStream_t stream);
+int sg3_modconv_fwd_tc3_f16(const void* x, const void* wtap, void* y, int N, int I, int O, int H, int W, int pad, int ldw,
+                            int xPitch, int yPitch, cudaStream_t stream);
 int sg3_modconv_tc3_supported(int I, int O, int H, int W, int k, int pad);
 int sg3_modconv_fwd_tc_f16(const void* x, const void* wmod, void* y, int N, int I, int O, int H, int W, int k, int pad, int ldw, cudaStream_t stream);
 int sg3_modconv_fwd_tc_x3(const float* x, const float* wmod, float* y, int N, int I, int O, int H, int W, int k, int pad, int ldw,
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
                                     : wmod + ((size_t)n * O + o) * ldw;
         const size_t dstStep = transpose == 1 ? (size_t)ldw : 1;
         const size_t tapStep = (size_t)O * ldw;
-        __half* dstH = reinterpret_cast<__half*>(wmod) + ((size_t)n * O + o) * ldw;       // fp16 operand form (layout 0 only)
+        // fp16 operand form: layout 0 (1x1 kernel) or layout 2 (tap-major, the fp16 3x3 kernel)
+        __half* dstH = reinterpret_cast<__half*>(wmod) + (transpose == 2 ? ((size_t)n * kk * O + o) * ldw : ((size_t)n * O + o) * ldw);
         if (roundTf32 == 3) {
             // 3xTF32 operand form (layout 0 only): [N][2][O][ldw], plane 0 = TF32 head, plane 1 = TF32 tail of the residual
             float* hi = wmod + ((size_t)(2 * n) * O + o) * ldw;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
         }
         if (transpose == 0 && roundTf32 != 2)
             for (int q = cnt + threadIdx.x; q < ldw; q += blockDim.x) dst[q] = 0.f;   // row padding (TMA pitch)
-        if (roundTf32 == 2)
+        if (roundTf32 == 2 && transpose == 0)
             for (int q = cnt + threadIdx.x; q < ldw; q += blockDim.x) dstH[q] = __float2half_rn(0.f);
         for (int q = threadIdx.x; q < cnt; q += blockDim.x) {
             const int i = q / kk;
@@ -122,7 +125,11 @@ __global__ void __launch_bounds__(256) modconv_weights_kernel(
             if (gainMode == 1) v *= gain[0];
             else if (gainMode == 2) v *= gain[i];
             else if (gainMode == 3) v *= gain[(size_t)n * I + i];
-            if (roundTf32 == 2) { dstH[q] = __float2half_rn(v); continue; }       // what the reference's w.to(x.dtype) does (:61)
+            if (roundTf32 == 2) {                                                // what the reference's w.to(x.dtype) does (:61)
+                if (transpose == 2) dstH[(size_t)(q - i * kk) * tapStep + i] = __float2half_rn(v);
+                else dstH[q] = __float2half_rn(v);
+                continue;
+            }
             // 4: the tensor core will TRUNCATE the fp32 activations this weight multiplies (10 of 23 mantissa bits survive): a
             // multiplicative bias of -2^-11 * E[1/m] = -2^-11 / (2 ln 2) = -3.52e-4 for a log-uniform mantissa m, the same sign on
             // every term of the sum.  It is folded into the weight before the weight itself is rounded (to nearest).
@@ -308,7 +315,8 @@ SG3_EXPORT int sg3_modconv_weights(const float* w, const float* s, const float* 
 {
     if (!w || !s || !wmod || !scratch || N < 1 || I < 1 || O < 1 || k < 1) return SG3_E_INVALID;
     if (transpose < 0 || transpose > 3 || round_tf32_flag < 0 || round_tf32_flag > 4) return SG3_E_INVALID;
-    if ((round_tf32_flag == 2 || round_tf32_flag == 3) && transpose != 0) return SG3_E_INVALID;
+    if (round_tf32_flag == 3 && transpose != 0) return SG3_E_INVALID;
+    if (round_tf32_flag == 2 && transpose != 0 && transpose != 2) return SG3_E_INVALID;
     if (transpose == 1 ? (k != 1 || ldw < O) : transpose == 2 ? (ldw < I) : transpose == 3 ? (ldw < O) : (ldw < I * k * k)) return SG3_E_INVALID;
     if (gainMode < 0 || gainMode > 3 || (gainMode && !input_gain)) return SG3_E_INVALID;
     if ((int64_t)N * I > INT32_MAX || (int64_t)I * k * k > INT32_MAX) return SG3_E_TOOLARGE;
@@ -334,9 +342,12 @@ SG3_EXPORT int sg3_modconv_fwd_pitched(const void* x, const float* wmod, void* y
     if (!x || !wmod || !y || N < 1 || I < 1 || O < 1 || H < 1 || W < 1 || k < 1 || pad < 0) return SG3_E_INVALID;
     const bool tapMajor = mathMode == 1 && k > 1;             // the tensor-core kernels for k > 1 read tap-major weights
     if (ldw < (tapMajor ? I : I * k * k)) return SG3_E_INVALID;
-    if (dtype == SG3_F16 && (yPitch != 0 || xPitch != 0)) return SG3_E_NOKERNEL;
-    if (dtype == SG3_F16)        // fp16 activations and fp16 weights (prologue format 2): tensor cores only, 1x1 kernels
-        return mathMode == 1 ? sg3_modconv_fwd_tc_f16(x, wmod, y, N, I, O, H, W, k, pad, ldw, (cudaStream_t)stream) : SG3_E_NOKERNEL;
+    if (dtype == SG3_F16) {      // fp16 activations and fp16 weights (prologue format 2; tap-major for k = 3): tensor cores only
+        if (mathMode != 1) return SG3_E_NOKERNEL;
+        if (k == 3) return sg3_modconv_fwd_tc3_f16(x, wmod, y, N, I, O, H, W, pad, ldw, xPitch, yPitch, (cudaStream_t)stream);
+        if (yPitch != 0 || xPitch != 0) return SG3_E_NOKERNEL;
+        return sg3_modconv_fwd_tc_f16(x, wmod, y, N, I, O, H, W, k, pad, ldw, (cudaStream_t)stream);
+    }
     if (dtype != SG3_F32) return SG3_E_NOKERNEL;
     const int OH = H + 2 * pad - k + 1, OW = W + 2 * pad - k + 1;
     if (OH < 1 || OW < 1) return SG3_E_INVALID;

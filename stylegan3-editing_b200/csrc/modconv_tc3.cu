@@ -24,8 +24,14 @@
 // allocator + MMA issuer.  Persistent over tiles.  The kernel can double-buffer the accumulator (accStages = 2) when two
 // stages fit in 512 TMEM columns, but the planner below never asks for it: one large single-buffered tile measured faster.
 // Every mbarrier wait is bounded (trap instead of hang).
+//
+// HALF (fp16 layers, networks_stylegan3.py:61 with x.dtype == float16): fp16 activations / weights / output, kind::f16 MMAs,
+// fp32 accumulation.  Same bytes everywhere: a chunk is 64 input channels of 2 bytes, an X box is [64 i][64 px] in the standard
+// SWIZZLE_128B MN-major form (8-channel atoms 1024 B apart, 64-pixel blocks one box apart), K = 16 per instruction.  Box starts
+// are 16-byte = 8-pixel aligned, so NPX is a multiple of 64, a tile keeps NPX - 8 columns and the padding-2 offset is 8.
 #include <cuda.h>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tensor_map.h"
@@ -34,14 +40,14 @@
 
 namespace {
 
-constexpr int BK3 = 32;                 // input channels per chunk
+constexpr int BK3 = 32;                 // input channels per chunk (fp32; fp16: 64 -- 128-byte K rows either way)
 constexpr int kMaxWSlots = 36;          // W ring slots; one slot = one tap of one chunk: [wRows <= 128 o][32 i] fp32
 constexpr int kThreads3 = 192;
 constexpr int STAGE_PITCH = 36;         // transpose staging: [32 channels][36] (16-byte rows: float4 writes, conflict-free)
 constexpr int kAccPitchAlign = 32;      // accumulator pitch granularity in TMEM columns (tcgen05.ld.x32 start columns)
 
 struct Tc3Params {
-    float* y;
+    void* y;                   // float, or __half (HALF)
     int N, I, O, H, W, OH, OW, pad;
     int yPitch;                // floats between output rows (>= OW): a 16-byte multiple lets the stencil that follows use TMA
     int NPX, R, CW;            // pixels per MMA (multiple of 32), output rows per tile, accumulator pitch (>= NPX + 4)
@@ -57,9 +63,13 @@ struct Tc3Params {
     long long totalTiles;
 };
 
+template <bool HALF>
 __global__ void __launch_bounds__(kThreads3, 1)
 modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapW, const Tc3Params p)
 {
+    constexpr int BKC = HALF ? 64 : BK3;               // input channels per chunk
+    constexpr int BOXPX = HALF ? 64 : 32;              // pixels per X box (one 128-byte swizzle row)
+    constexpr uint32_t BOXBYTES = BKC * 128u;
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) uint64_t barWFull[kMaxWSlots], barWEmpty[kMaxWSlots], barXFull[2], barXEmpty[2], barAccFull[2], barAccEmpty[2];
     __shared__ uint32_t tmemBase;
@@ -97,7 +107,7 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
         oy0 = ty * p.R;
         o0 = to * 128;
     };
-    const int boxesPerRow = p.NPX >> 5;
+    const int boxesPerRow = p.NPX / BOXPX;
     const uint32_t rowBytes = (uint32_t)p.NPX * 128u;                  // [32 ch][NPX px] of one input row
 
     if (warp == 4) {
@@ -118,22 +128,24 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                 const uint32_t xDst = xRing + xg * (uint32_t)p.xGroupBytes;
                 for (int rr = 0; rr < p.R + 2; rr++)
                     for (int j = 0; j < boxesPerRow; j++)
-                        tma_load_4d_elect(xDst + rr * rowBytes + j * 4096u, &mapX, xfull, xs + 32 * j, oy0 - p.pad + rr, c * BK3, n);
+                        tma_load_4d_elect(xDst + rr * rowBytes + j * BOXBYTES, &mapX, xfull, xs + BOXPX * j, oy0 - p.pad + rr, c * BKC, n);
                 for (int tap = 0; tap < 9; tap++, wIt++) {
                     const uint32_t ws = wIt % (uint32_t)p.wSlots, round = wIt / (uint32_t)p.wSlots;
                     if (round > 0) mbar_wait(smem_u32(&barWEmpty[ws]), (round - 1) & 1);
                     const uint32_t wfull = smem_u32(&barWFull[ws]);
                     mbar_expect_tx_elect(wfull, reuseW ? 0u : (uint32_t)p.wSlotBytes);    // resident: hand the slot over as is
-                    if (!reuseW) tma_load_4d_elect(wRing + ws * (uint32_t)p.wSlotBytes, &mapW, wfull, c * BK3, o0, tap, n);
+                    if (!reuseW) tma_load_4d_elect(wRing + ws * (uint32_t)p.wSlotBytes, &mapW, wfull, c * BKC, o0, tap, n);
                 }
             }
         }
     } else if (warp == 5) {
         // ---------------- MMA issuer: the whole warp runs the loop, one elected lane issues (tc_common.cuh) ----------------
         // D = F32, A = B = TF32, A K-major (bit 15 = 0), B MN-major (bit 16 = 1), N = NPX, M = 128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (1u << 16) |
+        // (HALF: A = B = F16 -> format fields 0; B in the standard SWIZZLE_128B MN-major form: LBO = one box, SBO = one 8-channel atom)
+        const uint32_t idesc = (1u << 4) | (HALF ? 0u : (2u << 7) | (2u << 10)) | (0u << 15) | (1u << 16) |
                                ((uint32_t)(p.NPX >> 3) << 17) | ((uint32_t)((p.m64 ? 64 : 128) >> 4) << 24);
-        const uint64_t dA = umma_desc(wRing, 16, 1024), dB = umma_desc(xRing, BK3 * 128, 512, kLayoutSw128Base32);
+        const uint64_t dA = umma_desc(wRing, 16, 1024);
+        const uint64_t dB = HALF ? umma_desc(xRing, BOXBYTES, 1024) : umma_desc(xRing, BK3 * 128, 512, kLayoutSw128Base32);
         const uint32_t aLo0 = (uint32_t)dA, aHi = (uint32_t)(dA >> 32), bLo0 = (uint32_t)dB, bHi = (uint32_t)(dB >> 32);
         const uint32_t rowStep = rowBytes >> 4, groupStep = (uint32_t)p.xGroupBytes >> 4;
         uint32_t xIt = 0, wIt = 0, tc = 0;
@@ -156,9 +168,12 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                         const uint32_t aLo = aLo0 + ws * ((uint32_t)p.wSlotBytes >> 4);
                         const uint32_t first = (c == 0 && ky == 0 && kx < 2) ? 0u : 1u;     // first touch of an accumulator
                         const uint32_t dOff = (uint32_t)((kx & 1) * p.CW + (kx == 0 ? 2 : 0));
-                        for (int oyl = 0; oyl < p.R; oyl++)
-                            umma_tf32_x4<2, 64>(acc + dOff + (uint32_t)(2 * oyl * p.CW), aLo, aHi,
-                                                bLoG + (uint32_t)(oyl + ky) * rowStep, bHi, idesc, first);
+                        for (int oyl = 0; oyl < p.R; oyl++) {
+                            if (HALF) umma_f16_x4<2, 128>(acc + dOff + (uint32_t)(2 * oyl * p.CW), aLo, aHi,
+                                                          bLoG + (uint32_t)(oyl + ky) * rowStep, bHi, idesc, first);
+                            else umma_tf32_x4<2, 64>(acc + dOff + (uint32_t)(2 * oyl * p.CW), aLo, aHi,
+                                                     bLoG + (uint32_t)(oyl + ky) * rowStep, bHi, idesc, first);
+                        }
                         umma_commit_elect(smem_u32(&barWEmpty[ws]));
                         if (++ws == (uint32_t)p.wSlots) { ws = 0; wPhase ^= 1; }
                     }
@@ -213,10 +228,11 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                     const int col = c0 + lane;
                     const int ox = tx * p.S + col - p.colBase;
                     if (col >= p.colBase && col < colEnd && ox < p.OW) {
-                        float* yp = p.y + (((size_t)n * p.O + o0 + warp) * p.OH + oy) * (size_t)p.yPitch + ox;
+                        typedef typename std::conditional<HALF, __half, float>::type OutT;
+                        OutT* yp = (OutT*)p.y + (((size_t)n * p.O + o0 + warp) * p.OH + oy) * (size_t)p.yPitch + ox;
                         const float* sp = stage + warp * STAGE_PITCH + lane;
                         for (int r = warp; r < nrows; r += 4) {
-                            *yp = *sp;
+                            st_as<OutT>(yp, *sp);
                             yp += 4 * chStep;
                             sp += 4 * STAGE_PITCH;
                         }
@@ -241,15 +257,16 @@ constexpr int kSmemLimit3 = 224 * 1024;       // + 2 KB of static barriers stays
 
 // Pick (NPX, R, accumulator stages, W slots) for a layer: minimise an estimate of the per-layer time
 // max(MMA clocks, operand bytes / 40 B/clk) over the tile shapes that fit TMEM (512 columns) and shared memory.
-bool plan_tc3(Tc3Params& p, int smemLimit)
+bool plan_tc3(Tc3Params& p, int smemLimit, bool half)
 {
+    const int lose = half ? 8 : 4;          // columns of a tile that only serve as halo (box starts are 16-byte aligned)
     // Per-tile time model fitted on B200 (tools/run_tc3_sweep.sh): a fixed 1700 clk of pipeline hand-over, the K loop
     // (tensor core or operand stream, whichever is slower) and -- the accumulator is single-buffered -- the serial
     // epilogue at ~530 clk per 32-column block.  Double-buffered accumulators only fit tiles of <= 96 pixels and
     // measured slower than one large tile for every StyleGAN3-T layer, so they are not planned.
     double best = 1e300;
     bool found = false;
-    for (int npx = 64; npx <= 224; npx += 32) {
+    for (int npx = 64; npx <= 224; npx += half ? 64 : 32) {
         for (int r = 1; r <= 4; r++) {
             const int cw = (npx + 4 + kAccPitchAlign - 1) / kAccPitchAlign * kAccPitchAlign, stageCols = 2 * r * cw;
             // the last 32-column epilogue load of the last accumulator must stay inside the allocation
@@ -261,7 +278,7 @@ bool plan_tc3(Tc3Params& p, int smemLimit)
             if (wSlots < 3) continue;
             const bool resident = wSlots >= 9 * p.kChunks;
             if (resident) wSlots = 9 * p.kChunks;
-            const int s = npx - 4;
+            const int s = npx - lose;
             const long long tiles = (long long)((p.OW + s - 1) / s) * ((p.OH + r - 1) / r);
             const double perMma = npx / 2.0 > 32.0 + npx / 4.0 ? npx / 2.0 : 32.0 + npx / 4.0;       // tools/tc_mma_bench.cu
             const double mma = 36.0 * r * perMma;
@@ -294,32 +311,38 @@ int sg3_modconv_tc3_supported(int I, int O, int H, int W, int k, int pad)
     return 0;
 }
 
-// x [N][I][H][xPitch >= W]; wtap [N][9][O][ldw] (tap = ky * 3 + kx, i contiguous, ldw % 4 == 0, ldw >= I); y [N][O][OH][yPitch >= OW].
+// x [N][I][H][xPitch >= W]; wtap [N][9][O][ldw] (tap = ky * 3 + kx, i contiguous, ldw >= I); y [N][O][OH][yPitch >= OW].
+// HALF: all three are fp16.  Pitches / ldw in elements, 16-byte multiples (4 floats, 8 halves).
 // The kernel only sees x through its tensor map, so a padded input row pitch costs nothing: TMA needs the PITCH to be a
 // 16-byte multiple, not W (columns >= W are outside the map's extent and read as zero like any other out-of-image column).
-int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw,
-                        int xPitch, int yPitch, cudaStream_t stream)
+namespace {
+
+template <bool HALF>
+int launch_tc3(const void* x, const void* wtap, void* y, int N, int I, int O, int H, int W, int pad, int ldw,
+               int xPitch, int yPitch, cudaStream_t stream)
 {
+    constexpr int esz = HALF ? 2 : 4, gran = 16 / esz, bkc = HALF ? 64 : BK3;
     const int xp = xPitch > 0 ? xPitch : W;
-    if (xp < W || xp % 4 != 0) return SG3_E_NOKERNEL;
-    if (sg3_modconv_tc3_supported(I, O, H, xp, 3, pad) != 0 || W + 2 * pad - 2 < 1) return SG3_E_NOKERNEL;
-    if (ldw % 4 != 0 || ldw < I) return SG3_E_NOKERNEL;
+    if (xp < W || xp % gran != 0) return SG3_E_NOKERNEL;
+    if (pad != 0 && pad != 2) return SG3_E_NOKERNEL;
+    if (H + 2 * pad - 2 < 1 || W + 2 * pad - 2 < 1) return SG3_E_NOKERNEL;
+    if (ldw % gran != 0 || ldw < I) return SG3_E_NOKERNEL;
     if (((uintptr_t)x & 15) || ((uintptr_t)wtap & 15)) return SG3_E_NOKERNEL;
     Tc3Params p;
     p.y = y; p.N = N; p.I = I; p.O = O; p.H = H; p.W = W; p.pad = pad;
     p.OH = H + 2 * pad - 2; p.OW = W + 2 * pad - 2;
     p.yPitch = yPitch > 0 ? yPitch : p.OW;
     if (p.yPitch < p.OW) return SG3_E_INVALID;
-    p.kChunks = (I + BK3 - 1) / BK3;
-    p.xoff = pad == 2 ? 4 : 0;
-    p.colBase = pad == 2 ? 4 : 2;
+    p.kChunks = (I + bkc - 1) / bkc;
+    p.xoff = pad == 2 ? (HALF ? 8 : 4) : 0;
+    p.colBase = p.xoff + (pad == 2 ? 0 : 2);
     p.m64 = O <= 64 ? 1 : 0;
     p.wRows = O >= 128 ? 128 : (O + 7) & ~7;
-    p.wSlotBytes = p.wRows * BK3 * 4;
+    p.wSlotBytes = p.wRows * 128;                       // [wRows o][one 128-byte K row]
     // co-scheduling with the stencil kernel (sg3_modconv_set_smem_budget): plan inside a smaller shared-memory budget
     const int budget = sg3_conv_smem_budget();
     // (a budget too small for any tile plan is ignored: the kernel then simply does not share its SM)
-    if (!(budget > 0 && budget < kSmemLimit3 && plan_tc3(p, budget)) && !plan_tc3(p, kSmemLimit3)) return SG3_E_NOKERNEL;
+    if (!(budget > 0 && budget < kSmemLimit3 && plan_tc3(p, budget, HALF)) && !plan_tc3(p, kSmemLimit3, HALF)) return SG3_E_NOKERNEL;
     p.tilesX = (p.OW + p.S - 1) / p.S;
     p.tilesY = (p.OH + p.R - 1) / p.R;
     p.tilesO = (O + 127) / 128;
@@ -327,29 +350,44 @@ int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int 
     const long long ctas = p.totalTiles < sg3_sm_count() ? p.totalTiles : sg3_sm_count();
 
     alignas(64) CUtensorMap mapX, mapW;
+    const CUtensorMapDataType dt = HALF ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     {
         const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)I, (uint64_t)N};
-        const uint64_t strides[3] = {(uint64_t)xp * 4, (uint64_t)xp * H * 4, (uint64_t)xp * H * I * 4};
-        const uint32_t box[4] = {32, 1, BK3, 1};
-        if (!sg3_make_tensor_map(&mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
+        const uint64_t strides[3] = {(uint64_t)xp * esz, (uint64_t)xp * H * esz, (uint64_t)xp * H * I * esz};
+        const uint32_t box[4] = {HALF ? 64u : 32u, 1, (uint32_t)bkc, 1};
+        if (!sg3_make_tensor_map(&mapX, dt, 4, x, dims, strides, box, HALF ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B))
             return SG3_E_NOKERNEL;
     }
     {
         const uint64_t dims[4] = {(uint64_t)I, (uint64_t)O, 9, (uint64_t)N};
-        const uint64_t strides[3] = {(uint64_t)ldw * 4, (uint64_t)ldw * O * 4, (uint64_t)ldw * O * 9 * 4};
-        const uint32_t box[4] = {BK3, (uint32_t)p.wRows, 1, 1};
-        if (!sg3_make_tensor_map(&mapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, wtap, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+        const uint64_t strides[3] = {(uint64_t)ldw * esz, (uint64_t)ldw * O * esz, (uint64_t)ldw * O * 9 * esz};
+        const uint32_t box[4] = {(uint32_t)bkc, (uint32_t)p.wRows, 1, 1};
+        if (!sg3_make_tensor_map(&mapW, dt, 4, wtap, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
             return SG3_E_NOKERNEL;
     }
     const int smemBytes = 2 * p.xGroupBytes + p.wSlots * p.wSlotBytes + 4 * 32 * STAGE_PITCH * 4 + 1024;
     static Sg3DeviceOnce once;
     const cudaError_t attrErr = once.run([] {
-        cudaError_t e = cudaFuncSetAttribute(modconv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
+        cudaError_t e = cudaFuncSetAttribute(modconv_tc3_kernel<HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit3);
         // same carve-out as the stencil kernels, so that both can be resident on one SM (see modconv_tc.cu)
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(modconv_tc3_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(modconv_tc3_kernel<HALF>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         return e;
     });
     if (attrErr != cudaSuccess) return (int)attrErr;
-    modconv_tc3_kernel<<<(unsigned)ctas, kThreads3, smemBytes, stream>>>(mapX, mapW, p);
+    modconv_tc3_kernel<HALF><<<(unsigned)ctas, kThreads3, smemBytes, stream>>>(mapX, mapW, p);
     return sg3_launch_status();
+}
+
+}  // namespace
+
+int sg3_modconv_fwd_tc3(const float* x, const float* wtap, float* y, int N, int I, int O, int H, int W, int pad, int ldw,
+                        int xPitch, int yPitch, cudaStream_t stream)
+{
+    return launch_tc3<false>(x, wtap, y, N, I, O, H, W, pad, ldw, xPitch, yPitch, stream);
+}
+
+int sg3_modconv_fwd_tc3_f16(const void* x, const void* wtap, void* y, int N, int I, int O, int H, int W, int pad, int ldw,
+                            int xPitch, int yPitch, cudaStream_t stream)
+{
+    return launch_tc3<true>(x, wtap, y, N, I, O, H, W, pad, ldw, xPitch, yPitch, stream);
 }

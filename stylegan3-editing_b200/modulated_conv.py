@@ -57,7 +57,8 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, tr
     """[N, O, ldw >= I*k*k] float32 modulated (+demodulated, +input-gain) weights, rows zero padded  (:39-56).
     transpose=True (1x1 only): [N, I, ldw >= O], the weight operand of the input-gradient GEMM.
     tap_major=True: [N, k*k, O, ldw >= I], the operand of the 3x3 tensor-core kernel.
-    half=True: float16 [N, O, ldw] (what `w.to(x.dtype)` of :61 produces for fp16 layers), operand of the fp16 tensor-core kernel.
+    half=True: float16 [N, O, ldw] (what `w.to(x.dtype)` of :61 produces for fp16 layers), operand of the fp16 tensor-core kernel;
+    with tap_major=True: float16 [N, k*k, O, ldw >= I], operand of the fp16 3x3 kernel.
     split=True: [N, 2, O, ldw], TF32 head and TF32 tail of every weight, operand of the 3xTF32 kernel (math='fp32x3').
     dgrad_taps=True: [N, k*k, I, ldw >= O], taps flipped and channels transposed: the operand of the k x k input-gradient conv.
     compensate=True (with round_tf32): weights scaled by 1 + 3.52e-4, the expected truncation loss of the activations (see `_tf32_policy`)."""
@@ -85,8 +86,12 @@ def modconv_weights(w, s, demodulate=True, input_gain=None, round_tf32=False, tr
         assert not transpose and not tap_major and not half
         ldw = (I * kh * kw + 31) // 32 * 32
         wmod = torch.empty([N, 2, O, ldw], dtype=torch.float32, device=w.device)
+    elif half and tap_major:                       # operand of the fp16 3x3 tensor-core kernel: [N, k*k, O, ldw >= I] float16
+        assert not transpose
+        ldw = (I + 63) // 64 * 64
+        wmod = torch.empty([N, kh * kw, O, ldw], dtype=torch.float16, device=w.device)
     elif half:
-        assert not transpose and not tap_major
+        assert not transpose
         ldw = (I * kh * kw + 63) // 64 * 64
         wmod = torch.empty([N, O, ldw], dtype=torch.float16, device=w.device)
     elif tap_major:
@@ -187,12 +192,17 @@ class _ModConv(torch.autograd.Function):
     def forward(ctx, x, w, s, input_gain, demodulate, padding, math):
         O, I, k, _ = w.shape
         xin = x.contiguous()
-        if (xin.dtype == torch.float16 and math == 'tf32' and k == 1 and padding == 0
-                and (xin.shape[2] * xin.shape[3]) % 8 == 0):
-            # fp16 layer (reference :61 casts the weights to fp16 and runs an fp16 cuDNN conv): fp16 tensor-core kernel,
-            # no up / down casts of the activations
-            wmod = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, half=True)
-            y = conv_forward(xin, wmod, O, k, padding, 'tf32')
+        if (xin.dtype == torch.float16 and math == 'tf32'
+                and ((k == 1 and padding == 0 and (xin.shape[2] * xin.shape[3]) % 8 == 0) or (k == 3 and padding in (0, 2)))):
+            # fp16 layer (reference :61 casts the weights to fp16 and runs an fp16 cuDNN conv): fp16 tensor-core kernels,
+            # no up / down casts of the activations.  The 3x3 kernel reads x by TMA: rows must be 16 bytes = 8 pixels apart
+            # (every config-T width is 4 mod 8, so x goes through one row-pitched copy).
+            xk = xin
+            if k == 3 and (xin.shape[3] % 8 != 0 or xin.data_ptr() % 16 != 0):
+                xk = empty_row_pitched(xin.shape, xin.dtype, xin.device, align=8)
+                xk.copy_(xin)
+            wmod = modconv_weights(w, s, demodulate=demodulate, input_gain=input_gain, half=True, tap_major=(k == 3))
+            y = conv_forward(xk, wmod, O, k, padding, 'tf32')
             if y is not None:
                 ctx.save_for_backward(x, w, s, input_gain)
                 ctx.cfg = (demodulate, padding, math)

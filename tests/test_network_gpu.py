@@ -685,3 +685,39 @@ def test_wgrad1_c_abi_vs_oracle(pkg, I, O, P, ldw):
     assert rc == 0
     assert rel_err(dw[:, :, :I].cpu().numpy(), ref) < 2e-3
     assert float(dw[:, :, I:].abs().max()) == 0.0 if ldw > I else True
+
+
+@pytest.mark.parametrize('shape', [
+    # N, I, O, H, W, pad
+    (2, 40, 24, 24, 24, 2),          # one chunk of 64 channels (40 real), M = 64 path, OW = 26
+    (1, 96, 130, 20, 36, 2),         # two o tiles, two chunks, W % 8 == 4 (row-pitched copy of x) like every config-T layer
+    (2, 33, 64, 20, 24, 0),          # padding 0
+    (1, 200, 51, 30, 148, 2),        # four chunks, three column tiles of 56 / 120 / 184 kept columns
+    (1, 64, 32, 70, 276, 2),         # wide rows
+])
+def test_modconv_tc3_f16_vs_oracle(pkg, shape):
+    """fp16 3x3 tensor-core contraction (kind::f16, fp32 accumulation, fp16 store) through the public op vs the oracle on the same
+    fp16-rounded activations; the weights go through the fp16 prologue (what `w.to(x.dtype)` does in the reference, :61).
+    Tolerance 2e-3 of max |ref| (fp16 weight and output rounding)."""
+    from oracle import sg3_oracle as orc
+    N, I, O, H, W, pad = shape
+    rng = np.random.RandomState(sum(shape))
+    x = rng.randn(N, I, H, W).astype(np.float16)
+    w = rng.randn(O, I, 3, 3).astype(np.float32)
+    s = (rng.randn(N, I) + 1).astype(np.float32)
+    ref = orc.modulated_conv2d(x.astype(np.float32), w, s, demodulate=True, padding=pad)
+    n0 = pkg.capi.lib().sg3_launch_count()
+    y = pkg.modulated_conv.modulated_conv2d(cu(x), cu(w), cu(s), demodulate=True, padding=pad, math='tf32')
+    assert pkg.capi.lib().sg3_launch_count() - n0 == 3            # weight prologue (2) + ONE fp16 tensor-core conv, no casts
+    assert y.dtype == torch.float16 and tuple(y.shape) == ref.shape
+    assert rel_err(y.float().cpu().numpy(), ref) < 2e-3, shape
+
+
+def test_modconv_half_tap_major_weights(pkg):
+    """fp16 tap-major prologue output = the fp32 tap-major output rounded to fp16."""
+    rng = np.random.RandomState(8)
+    w, s = rng.randn(37, 70, 3, 3).astype(np.float32), rng.randn(3, 70).astype(np.float32)
+    a = pkg.modulated_conv.modconv_weights(cu(w), cu(s), True, torch.tensor(0.7).cuda(), tap_major=True)
+    b = pkg.modulated_conv.modconv_weights(cu(w), cu(s), True, torch.tensor(0.7).cuda(), tap_major=True, half=True)
+    assert b.dtype == torch.float16 and tuple(b.shape) == (3, 9, 37, 128)
+    assert torch.equal(a[..., :70].half(), b[..., :70])
