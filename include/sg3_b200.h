@@ -209,6 +209,12 @@ int sg3_modconv_tc_supported(int I, int O, int H, int W, int k, int pad);
 int sg3_modconv_weights_bwd(const float* dwmod, const float* w, const float* s, const float* input_gain, int gainMode,
                             float* dw, float* ds, float* scratch, int N, int I, int O, int ldw, int demodulate, void* stream);
 
+/* The same chain rule for k x k kernels (3x3: config T), reading the TAP-MAJOR gradient sg3_modconv_wgrad3 accumulates:
+ * dwmod [N][k*k][O][ldw >= I] -> dw [O][I][k][k], ds [N][I].  scratch: >= (1 + N*I) floats.  I*k*k <= 4608 (512 channels x 9 taps),
+ * otherwise SG3_E_NOKERNEL (the caller then differentiates the weight expression with autograd, as the reference does). */
+int sg3_modconv_weights_bwd_taps(const float* dwmod, const float* w, const float* s, const float* input_gain, int gainMode,
+                                 float* dw, float* ds, float* scratch, int N, int I, int O, int k, int ldw, int demodulate, void* stream);
+
 int sg3_modconv_fwd(const void* x, const float* wmod, void* y,
                     int N, int I, int O, int H, int W, int k, int pad, int ldw,
                     int mathMode, int dtype, void* stream);

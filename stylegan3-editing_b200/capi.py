@@ -59,6 +59,7 @@ _PROTOS = {
                                 _I, _I, _I, _I, _I, _I, _I, _F, _I, _P]),
     'sg3_modconv_weights': (_I, [_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     'sg3_modconv_weights_bwd': (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    'sg3_modconv_weights_bwd_taps': (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'sg3_modconv_tc_supported': (_I, [_I, _I, _I, _I, _I, _I]),
     'sg3_modconv_wgrad': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'sg3_modconv_wgrad3': (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

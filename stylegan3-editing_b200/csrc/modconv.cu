@@ -217,6 +217,83 @@ __global__ void __launch_bounds__(256) modconv_weights_bwd_kernel(
     }
 }
 
+// The same chain rule for k x k kernels (3x3: config T).  One CTA per output channel; the I * kk weights of the channel are
+// flattened as q = i * kk + tap (the layout of w itself); thread t owns q = t, t + 256, ... (up to KPT of them).  The incoming
+// gradient is TAP-MAJOR, dWf[n][tap][o][i] with row pitch ldw -- what sg3_modconv_wgrad3 accumulates.  Differences from the 1x1
+// kernel: the style / gain index is q / kk, the pre-normalisation runs over I * kk values (:41), nothing else.
+template <int KPT>
+__global__ void __launch_bounds__(256) modconv_weights_bwd_taps_kernel(
+    const float* __restrict__ dWf, const float* __restrict__ w, const float* __restrict__ s, const float* __restrict__ gain, int gainMode,
+    const float* __restrict__ scratch, float* __restrict__ dw, float* __restrict__ dsn,
+    int N, int I, int O, int kk, int ldw, int demodulate)
+{
+    __shared__ float red[32];
+    const int o = blockIdx.x;
+    const int cnt = I * kk;
+    const float* wo = w + (size_t)o * cnt;
+    float wreg[KPT], dwn[KPT];
+    int ii[KPT], src[KPT];                    // input channel of q, and its offset inside one sample's tap-major gradient
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < KPT; u++) {
+        const int q = threadIdx.x + 256 * u;
+        const int i = q / kk;
+        ii[u] = i;
+        src[u] = ((q - i * kk) * O + o) * ldw + i;
+        wreg[u] = q < cnt ? wo[q] : 0.f;
+        dwn[u] = 0.f;
+        acc += wreg[u] * wreg[u];
+    }
+    float rw = 1.f, rs = 1.f;
+    if (demodulate) {
+        acc = block_sum(acc, red);
+        rw = rsqrtf(acc / (float)cnt);
+        rs = scratch[0];
+    }
+    for (int n = 0; n < N; n++) {
+        const float* sn = s + (size_t)n * I;
+        const float* dr = dWf + (size_t)n * kk * O * ldw;
+        float Wm[KPT], dW[KPT];
+        float q2 = 0.f, dd = 0.f;
+#pragma unroll
+        for (int u = 0; u < KPT; u++) {
+            const bool ok = threadIdx.x + 256 * u < cnt;
+            const int i = ii[u];
+            float g = 1.f;
+            if (ok) g = gainMode == 1 ? gain[0] : gainMode == 2 ? gain[i] : gainMode == 3 ? gain[(size_t)n * I + i] : 1.f;
+            Wm[u] = ok ? (wreg[u] * rw) * (sn[i] * rs) : 0.f;
+            dW[u] = ok ? dr[src[u]] * g : 0.f;
+            q2 += Wm[u] * Wm[u];
+            dd += dW[u] * Wm[u];
+        }
+        float d = 1.f, c = 0.f;
+        if (demodulate) {
+            q2 = block_sum(q2, red) + 1e-8f;
+            dd = block_sum(dd, red);
+            d = rsqrtf(q2);
+            c = dd * d / q2;                      // dd q^-3/2
+        }
+#pragma unroll
+        for (int u = 0; u < KPT; u++) {
+            if (threadIdx.x + 256 * u < cnt) {
+                const int i = ii[u];
+                const float dWm = dW[u] * d - Wm[u] * c;
+                dwn[u] += dWm * (sn[i] * rs);
+                atomicAdd(dsn + (size_t)n * I + i, dWm * (wreg[u] * rw));
+            }
+        }
+    }
+    float dot = 0.f;
+#pragma unroll
+    for (int u = 0; u < KPT; u++) dot += dwn[u] * wreg[u];
+    if (demodulate) dot = block_sum(dot, red);
+#pragma unroll
+    for (int u = 0; u < KPT; u++) {
+        const int q = threadIdx.x + 256 * u;
+        if (q < cnt) dw[(size_t)o * cnt + q] = demodulate ? rw * dwn[u] - wreg[u] * rw * rw * rw * dot / (float)cnt : dwn[u];
+    }
+}
+
 // ds = rs dsn - s rs^3 (sum_{n,i} dsn s) / (N I)   (demodulate), else ds = dsn.  One CTA.
 __global__ void __launch_bounds__(1024) modconv_style_bwd_kernel(const float* __restrict__ dsn, const float* __restrict__ s,
                                                                  const float* __restrict__ scratch, float* __restrict__ ds, int count, int demodulate)
@@ -390,6 +467,27 @@ SG3_EXPORT int sg3_modconv_tc_supported(int I, int O, int H, int W, int k, int p
     if (I < 1 || O < 1 || H < 1 || W < 1 || k < 1 || pad < 0) return SG3_E_INVALID;
     if (k == 1) return (pad == 0 && ((int64_t)H * W) % 4 == 0) ? 0 : SG3_E_NOKERNEL;
     return sg3_modconv_tc3_supported(I, O, H, W, k, pad);
+}
+
+SG3_EXPORT int sg3_modconv_weights_bwd_taps(const float* dwmod, const float* w, const float* s, const float* input_gain, int gainMode,
+                                            float* dw, float* ds, float* scratch, int N, int I, int O, int k, int ldw, int demodulate,
+                                            void* stream)
+{
+    if (!dwmod || !w || !s || !dw || !ds || !scratch || N < 1 || I < 1 || O < 1 || k < 1 || ldw < I) return SG3_E_INVALID;
+    if (gainMode < 0 || gainMode > 3 || (gainMode && !input_gain)) return SG3_E_INVALID;
+    const int kk = k * k;
+    constexpr int kKpt = 18;                                   // 256 x 18 = 4608 = 512 input channels x 9 taps
+    if ((int64_t)I * kk > 256 * kKpt) return SG3_E_NOKERNEL;
+    if ((int64_t)N * I > INT32_MAX || (int64_t)kk * O * ldw > INT32_MAX) return SG3_E_TOOLARGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    // scratch: [0] = rs, [1 .. 1 + N*I) = dsn accumulator (zeroed here)
+    cudaError_t e = cudaMemsetAsync(scratch + 1, 0, (size_t)N * I * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+    if (demodulate) style_norm_kernel<<<1, 1024, 0, st>>>(s, N * I, scratch);
+    modconv_weights_bwd_taps_kernel<kKpt><<<(unsigned)O, 256, 0, st>>>(dwmod, w, s, input_gain, gainMode, scratch, dw, scratch + 1,
+                                                                         N, I, O, kk, ldw, demodulate);
+    modconv_style_bwd_kernel<<<1, 1024, 0, st>>>(scratch + 1, s, scratch, ds, N * I, demodulate);
+    return sg3_launch_status(demodulate ? 3 : 2);
 }
 
 SG3_EXPORT int sg3_modconv_wgrad(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, void* stream)

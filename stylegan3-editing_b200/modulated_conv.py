@@ -364,12 +364,8 @@ def _tma_rows(t):
     return buf
 
 
-def conv3x3_weight_grad(x, dy, padding):
-    """Per-sample weight gradient of the 3x3 conv on the tcgen05 kernel (`sg3_modconv_wgrad3`, TF32 operands, fp32 accumulation):
-    dW[n, o, i, ky, kx] = sum dy[n, o, oy, ox] * x[n, i, oy + ky - pad, ox + kx - pad] -- what the reference gets from the grouped
-    `conv2d_weight` of conv2d_gradfix.py:103-129.  x [N, I, H, W], dy [N, O, H + 2 pad - 2, W + 2 pad - 2], float32 (dense or
-    row-pitched views; anything else is copied into a row-pitched buffer).  Returns [N, O, I, 3, 3] (a permuted view of the
-    tap-major buffer the kernel accumulates into) or None when the library has no kernel for the call."""
+def _wgrad3_taps(x, dy, padding):
+    """Tap-major per-sample weight gradient [N, 9, O, ldw] (and ldw) from `sg3_modconv_wgrad3`, or None (no kernel for the call)."""
     N, I, H, W = x.shape
     O = dy.shape[1]
     xp, dyp = _tma_rows(x), _tma_rows(dy)
@@ -381,7 +377,42 @@ def conv3x3_weight_grad(x, dy, padding):
     if rc == capi.SG3_E_NOKERNEL:
         return None
     capi.check(rc, 'sg3_modconv_wgrad3')
-    return dWt[..., :I].reshape(N, 3, 3, O, I).permute(0, 3, 4, 1, 2)
+    return dWt, ldw
+
+
+def conv3x3_weight_grad(x, dy, padding):
+    """Per-sample weight gradient of the 3x3 conv on the tcgen05 kernel (`sg3_modconv_wgrad3`, TF32 operands, fp32 accumulation):
+    dW[n, o, i, ky, kx] = sum dy[n, o, oy, ox] * x[n, i, oy + ky - pad, ox + kx - pad] -- what the reference gets from the grouped
+    `conv2d_weight` of conv2d_gradfix.py:103-129.  x [N, I, H, W], dy [N, O, H + 2 pad - 2, W + 2 pad - 2], float32 (dense or
+    row-pitched views; anything else is copied into a row-pitched buffer).  Returns [N, O, I, 3, 3] (a permuted view of the
+    tap-major buffer the kernel accumulates into) or None when the library has no kernel for the call."""
+    N, I = x.shape[:2]
+    O = dy.shape[1]
+    res = _wgrad3_taps(x, dy, padding)
+    if res is None:
+        return None
+    return res[0][..., :I].reshape(N, 3, 3, O, I).permute(0, 3, 4, 1, 2)
+
+
+def _weights_backward_taps(dWt, w, s, input_gain, demodulate, ldw):
+    """Chain rule through the weight prologue for k x k kernels on one kernel pair (`sg3_modconv_weights_bwd_taps`): tap-major
+    gradient wrt the per-sample weights [N, k*k, O, ldw] -> (dw [O, I, k, k], ds [N, I]).  None when the library has no kernel."""
+    O, I, k, _ = w.shape
+    N = s.shape[0]
+    w2 = w.detach().float().contiguous()
+    s2 = s.detach().float().contiguous()
+    mode, g = _gain_arg(input_gain, N, I)
+    dw = torch.empty([O, I, k, k], dtype=torch.float32, device=w.device)
+    ds = torch.empty([N, I], dtype=torch.float32, device=w.device)
+    scratch = torch.empty([1 + N * I], dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        rc = capi.lib().sg3_modconv_weights_bwd_taps(dWt.data_ptr(), w2.data_ptr(), s2.data_ptr(), g.data_ptr() if g is not None else None,
+                                                     mode, dw.data_ptr(), ds.data_ptr(), scratch.data_ptr(), N, I, O, k, ldw,
+                                                     int(bool(demodulate)), capi.stream_ptr(w.device))
+    if rc == capi.SG3_E_NOKERNEL:
+        return None
+    capi.check(rc, 'sg3_modconv_weights_bwd_taps')
+    return dw, ds
 
 
 def _native_backward_3x3(x, w, s, input_gain, dy, demodulate, padding, need):
@@ -389,7 +420,8 @@ def _native_backward_3x3(x, w, s, input_gain, dy, demodulate, padding, need):
     dy with the flipped, channel-transposed taps and padding 2 - pad -- the SAME implicit-GEMM kernel with the weight prologue
     writing layout 3.  dy arrives from the filtered_lrelu backward kernel as a row-pitched view (its width, e.g. 1046, is not a
     TMA pitch), otherwise it is copied into one.  dw / ds: the per-sample weight gradient is the tcgen05 kernel of
-    `conv3x3_weight_grad`, then autograd through the small weight expression.  None when the kernels have no plan for the shape."""
+    `sg3_modconv_wgrad3`, then the chain rule through the weight prologue on one kernel pair (`sg3_modconv_weights_bwd_taps`;
+    autograd through the weight expression beyond 512 input channels).  None when the kernels have no plan for the shape."""
     N, I, H, W = x.shape
     O = w.shape[0]
     dx = dw = ds = None
@@ -411,9 +443,16 @@ def _native_backward_3x3(x, w, s, input_gain, dy, demodulate, padding, need):
         if dx is None:
             return None
     if need[1] or need[2]:
-        dW = conv3x3_weight_grad(x, dy if dy_p is None else dy_p, padding)
-        if dW is None:
+        res = _wgrad3_taps(x, dy if dy_p is None else dy_p, padding)
+        if res is None:
             return None
+        dWt, ldw = res
+        fused = _weights_backward_taps(dWt, w, s, input_gain, demodulate, ldw)
+        if fused is not None:
+            dw = fused[0].to(w.dtype) if need[1] else None
+            ds = fused[1].to(s.dtype) if need[2] else None
+            return dx, dw, ds
+        dW = dWt[..., :I].reshape(N, 3, 3, O, I).permute(0, 3, 4, 1, 2)          # more than 512 input channels: autograd through the expression
         with torch.enable_grad():
             ws = w.detach().requires_grad_(need[1])
             ss = s.detach().requires_grad_(need[2])
