@@ -424,3 +424,39 @@ def test_tf32_rounding_switch_logic():
         modulated_conv.set_tf32_activation_policy('compensate')
         modulated_conv.set_math(None)
     assert sg3_b200.capi.FLRELU_ROUND_TF32 == 1
+
+
+def test_row_pitched_helpers():
+    """Host logic of the TMA hand-over buffers: `empty_row_pitched` pads rows to 16 bytes (4 floats / 8 halves) and zeroes the padding,
+    `_row_pitched` recognises exactly those views, `_tma_rows` copies only what TMA cannot address."""
+    import torch
+    from sg3_b200 import modulated_conv as mc
+    t = mc.empty_row_pitched([2, 3, 5, 38], torch.float32, 'cpu')
+    assert tuple(t.shape) == (2, 3, 5, 38) and t.stride() == (3 * 5 * 40, 5 * 40, 40, 1) and mc._row_pitched(t)
+    assert float(t.as_strided((2, 3, 5, 2), t.stride(), 38).abs().max()) == 0.0          # the padding columns
+    h = mc.empty_row_pitched([1, 2, 4, 1044], torch.float16, 'cpu', align=8)
+    assert h.stride(2) == 1048 and mc._row_pitched(h)
+    dense = torch.zeros(1, 2, 4, 40)
+    assert mc._row_pitched(dense) and mc._tma_rows(dense) is dense
+    assert not mc._row_pitched(dense.transpose(2, 3))
+    odd = torch.arange(2 * 3 * 4 * 6, dtype=torch.float32).reshape(2, 3, 4, 6)            # width 6: rows are 24 bytes apart
+    p = mc._tma_rows(odd)
+    assert p is not odd and p.stride(2) == 8 and torch.equal(p, odd)
+
+
+def test_conv_backward_entry_points_validate_before_launching(pkg):
+    """Argument checks of the new C entry points run on the host before any CUDA call: invalid -> SG3_E_INVALID, shapes / pitches
+    without a kernel -> SG3_E_NOKERNEL (the Python op then falls back), never a launch with bad geometry."""
+    L = pkg.capi.lib()
+    E_INVALID, E_NOKERNEL = pkg.capi.SG3_E_INVALID, pkg.capi.SG3_E_NOKERNEL
+    a = 4096                                                    # any non-null, 16-byte aligned address: nothing is dereferenced
+    assert L.sg3_modconv_wgrad3(None, a, a, 1, 8, 8, 10, 12, 2, 8, 16, 0, None) == E_INVALID
+    assert L.sg3_modconv_wgrad3(a, a, a, 1, 8, 8, 10, 12, 2, 4, 16, 0, None) == E_INVALID        # ldw < I
+    assert L.sg3_modconv_wgrad3(a, a, a, 1, 8, 8, 10, 12, 1, 8, 16, 0, None) == E_NOKERNEL       # padding 1
+    assert L.sg3_modconv_wgrad3(a, a, a, 1, 8, 8, 10, 12, 2, 8, 0, 0, None) == E_NOKERNEL        # OW = 14: not a 16-byte pitch
+    assert L.sg3_modconv_wgrad3(a, a + 4, a, 1, 8, 8, 10, 12, 2, 8, 16, 0, None) == E_NOKERNEL   # x off the TMA alignment
+    assert L.sg3_modconv_wgrad3(a, a, a + 8, 1, 8, 8, 10, 12, 2, 8, 16, 0, None) == E_NOKERNEL   # dw off the 128-bit reduction alignment
+    assert L.sg3_modconv_weights_bwd_taps(a, a, a, None, 0, a, a, a, 1, 513, 8, 3, 516, 1, None) == E_NOKERNEL   # > 512 channels x 9 taps
+    assert L.sg3_modconv_weights_bwd_taps(a, a, a, None, 1, a, a, a, 1, 8, 8, 3, 8, 1, None) == E_INVALID        # gain mode without a gain
+    assert L.sg3_modconv_weights(a, a, None, 0, a, a, 1, 8, 8, 3, 72, 1, 3, 2, None) == E_INVALID                 # 3xTF32 planes are layout 0 only
+    assert L.sg3_modconv_weights(a, a, None, 0, a, a, 1, 8, 8, 3, 72, 1, 2, 3, None) == E_INVALID                 # fp16 has no dgrad-tap layout
