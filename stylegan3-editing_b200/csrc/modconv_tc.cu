@@ -309,9 +309,10 @@ modconv_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_con
     const int to = (int)(t % p.tilesO);
     const int n = (int)(t / p.tilesO);
     const int o0 = to * BM, i0 = ti * p.BN;
-    const int kt0 = sp * p.kPerSplit;
-    const int kt1 = min(kt0 + p.kPerSplit, p.kTilesTotal);
-    const int nk = kt1 - kt0;                                // >= 1 by construction
+    // contiguous k-tile range per split.  (Measured: interleaving the splits -- tiles sp, sp + splits, ... so that co-running CTAs read
+    // adjacent pieces of every channel row -- changes nothing: 4.2 TB/s on the top layers either way, tools/prof_wgrad1.py.)
+    const int kt0 = sp * p.kPerSplit, ktStep = 1;
+    const int nk = min(kt0 + p.kPerSplit, p.kTilesTotal) - kt0;          // >= 1 by construction
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStages; s++) { mbar_init(smem_u32(&barFull[s]), 1); mbar_init(smem_u32(&barEmpty[s]), 1); }
@@ -334,8 +335,8 @@ modconv_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_con
             const uint32_t full = smem_u32(&barFull[s]);
             mbar_expect_tx_elect(full, (uint32_t)stageBytes);
             const uint32_t aDst = tiles + s * stageBytes;
-            tma_load_3d_elect(aDst, &mapDY, full, (kt0 + it) * BK, o0, n);                    // [128 o][32 px]
-            tma_load_3d_elect(aDst + A_STAGE_BYTES, &mapX, full, (kt0 + it) * BK, i0, n);     // [BN i][32 px]
+            tma_load_3d_elect(aDst, &mapDY, full, (kt0 + it * ktStep) * BK, o0, n);                    // [128 o][32 px]
+            tma_load_3d_elect(aDst + A_STAGE_BYTES, &mapX, full, (kt0 + it * ktStep) * BK, i0, n);     // [BN i][32 px]
         }
     } else if (warp == 5) {
         // D=F32, A=B=TF32, both K-major, N = BN, M = 128
