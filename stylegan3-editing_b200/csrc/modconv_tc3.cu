@@ -58,6 +58,10 @@ struct Tc3Params {
     int wSlots, xGroupBytes;
     int wRows, wSlotBytes;     // rows of a W slot (min(128, ceil8(O))) and its size
     int resident;              // the ring holds every (chunk, tap) of the layer: W is reloaded only when (n, o-tile) changes
+    int kxStack;               // O == 32: the three kx taps of a ky are stacked along M (rows kx * 32 + o of one M = 128 MMA): 12 instead
+                               // of 36 MMAs per row and chunk; the kx shifts move to the epilogue; one accumulator per row, two stages
+                               // side by side in the TMEM columns.  wLoadBytes = bytes TMA delivers per W slot (96 rows; slots are 128).
+    int wLoadBytes;
     int m64;                   // O <= 64: M = 64 MMAs; their accumulator occupies lanes 32q .. 32q+15 of TMEM (measured,
                                // tools/tc_m64_probe.cu), a second one fits at lane offset 16 in the SAME columns -> two stages
     long long totalTiles;
@@ -129,12 +133,13 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                 for (int rr = 0; rr < p.R + 2; rr++)
                     for (int j = 0; j < boxesPerRow; j++)
                         tma_load_4d_elect(xDst + rr * rowBytes + j * BOXBYTES, &mapX, xfull, xs + BOXPX * j, oy0 - p.pad + rr, c * BKC, n);
-                for (int tap = 0; tap < 9; tap++, wIt++) {
+                const int nTapLoads = p.kxStack ? 3 : 9;                  // kxStack: one box of [3 taps][32 o] rows per ky
+                for (int tap = 0; tap < nTapLoads; tap++, wIt++) {
                     const uint32_t ws = wIt % (uint32_t)p.wSlots, round = wIt / (uint32_t)p.wSlots;
                     if (round > 0) mbar_wait(smem_u32(&barWEmpty[ws]), (round - 1) & 1);
                     const uint32_t wfull = smem_u32(&barWFull[ws]);
-                    mbar_expect_tx_elect(wfull, reuseW ? 0u : (uint32_t)p.wSlotBytes);    // resident: hand the slot over as is
-                    if (!reuseW) tma_load_4d_elect(wRing + ws * (uint32_t)p.wSlotBytes, &mapW, wfull, c * BKC, o0, tap, n);
+                    mbar_expect_tx_elect(wfull, reuseW ? 0u : (uint32_t)p.wLoadBytes);    // resident: hand the slot over as is
+                    if (!reuseW) tma_load_4d_elect(wRing + ws * (uint32_t)p.wSlotBytes, &mapW, wfull, c * BKC, o0, p.kxStack ? 3 * tap : tap, n);
                 }
             }
         }
@@ -159,6 +164,25 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                 mbar_wait(smem_u32(&barXFull[xg]), (xIt >> 1) & 1);
                 const uint32_t bLoG = bLo0 + xg * groupStep;
                 uint32_t ws = wIt % (uint32_t)p.wSlots, wPhase = (wIt / (uint32_t)p.wSlots) & 1;
+                if (p.kxStack) {
+                    // A = [3 kx][32 o] rows of tap row ky (M = 128, the last 32 rows are never read back), one accumulator per output row
+#pragma unroll 1
+                    for (int ky = 0; ky < 3; ky++) {
+                        mbar_wait(smem_u32(&barWFull[ws]), wPhase);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t aLo = aLo0 + ws * ((uint32_t)p.wSlotBytes >> 4);
+                        const uint32_t first = (c == 0 && ky == 0) ? 0u : 1u;
+                        for (int oyl = 0; oyl < p.R; oyl++) {
+                            if (HALF) umma_f16_x4<2, 128>(acc + (uint32_t)(oyl * p.CW), aLo, aHi, bLoG + (uint32_t)(oyl + ky) * rowStep, bHi, idesc, first);
+                            else umma_tf32_x4<2, 64>(acc + (uint32_t)(oyl * p.CW), aLo, aHi, bLoG + (uint32_t)(oyl + ky) * rowStep, bHi, idesc, first);
+                        }
+                        umma_commit_elect(smem_u32(&barWEmpty[ws]));
+                        if (++ws == (uint32_t)p.wSlots) { ws = 0; wPhase ^= 1; }
+                    }
+                    wIt += 3;
+                    umma_commit_elect(smem_u32(&barXEmpty[xg]));
+                    continue;
+                }
 #pragma unroll 1
                 for (int ky = 0; ky < 3; ky++) {
 #pragma unroll
@@ -196,6 +220,63 @@ modconv_tc3_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             mbar_wait(smem_u32(&barAccFull[as]), use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t acc = tmem + ((uint32_t)(32 * warp) << 16) + (p.m64 ? 0u : as * (uint32_t)p.accStageCols);
+            if (p.kxStack) {
+                // Warp kx (0..2) holds D_kx[o = lane][j]; output column c = sum_kx D_kx[c - 2 + kx].  Each warp stages its block already
+                // shifted to output columns (the 2 - kx values that come from the previous block travel in registers), the store phase
+                // adds the three planes.  Plane kx = rows 32 kx .. 32 kx + 31 of the staging buffer.
+                typedef typename std::conditional<HALF, __half, float>::type OutT;
+                const int colEnd = p.colBase + p.S;
+                const size_t chStep = (size_t)p.OH * p.yPitch;
+                float* st = stage + (32 * warp + lane) * STAGE_PITCH;
+                for (int oyl = 0; oyl < p.R; oyl++) {
+                    const int oy = oy0 + oyl;
+                    if (oy >= p.OH) break;
+                    float prev0 = 0.f, prev1 = 0.f;                         // D[c0 - 2], D[c0 - 1] of this lane
+                    for (int c0 = 0; c0 < colEnd; c0 += 32) {
+                        if (warp < 3) {
+                            uint32_t e[32];
+                            tmem_ld32(acc + (uint32_t)(oyl * p.CW + c0), e);
+                            if (warp == 2) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(st + j) = make_float4(__uint_as_float(e[j]), __uint_as_float(e[j + 1]),
+                                                                                     __uint_as_float(e[j + 2]), __uint_as_float(e[j + 3]));
+                            } else if (warp == 1) {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(st + j) = make_float4(j == 0 ? prev1 : __uint_as_float(e[j - 1]), __uint_as_float(e[j]),
+                                                                                     __uint_as_float(e[j + 1]), __uint_as_float(e[j + 2]));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; j += 4)
+                                    *reinterpret_cast<float4*>(st + j) = make_float4(j == 0 ? prev0 : __uint_as_float(e[j - 2]),
+                                                                                     j == 0 ? prev1 : __uint_as_float(e[j - 1]),
+                                                                                     __uint_as_float(e[j]), __uint_as_float(e[j + 1]));
+                            }
+                            prev0 = __uint_as_float(e[30]);
+                            prev1 = __uint_as_float(e[31]);
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");          // three planes staged
+                        const int col = c0 + lane;
+                        const int ox = tx * p.S + col - p.colBase;
+                        if (col >= p.colBase && col < colEnd && ox < p.OW) {
+                            OutT* yp = (OutT*)p.y + (((size_t)n * p.O + warp) * p.OH + oy) * (size_t)p.yPitch + ox;
+                            const float* sp = stage + warp * STAGE_PITCH + lane;
+#pragma unroll
+                            for (int r = 0; r < 8; r++) {                       // channels warp, warp + 4, ..., warp + 28
+                                st_as<OutT>(yp, sp[0] + sp[32 * STAGE_PITCH] + sp[64 * STAGE_PITCH]);
+                                yp += 4 * chStep;
+                                sp += 4 * STAGE_PITCH;
+                            }
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");          // block stored: the staging buffer is free again
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&barAccEmpty[as]));
+                continue;
+            }
             const int nrows = min(128, p.O - o0);                 // valid channels of this tile
             // channel held by this lane: M = 128 -> lane 32w + l; M = 64 -> lanes 16 as .. 16 as + 15 of each warp hold rows 16w ..
             const int laneRow = p.m64 ? 16 * warp + (lane & 15) : 32 * warp + lane;
@@ -266,30 +347,34 @@ bool plan_tc3(Tc3Params& p, int smemLimit, bool half)
     // measured slower than one large tile for every StyleGAN3-T layer, so they are not planned.
     double best = 1e300;
     bool found = false;
+    const int tapSlots = p.kxStack ? 3 : 9;                      // W ring slots one chunk consumes
     for (int npx = 64; npx <= 224; npx += half ? 64 : 32) {
         for (int r = 1; r <= 4; r++) {
-            const int cw = (npx + 4 + kAccPitchAlign - 1) / kAccPitchAlign * kAccPitchAlign, stageCols = 2 * r * cw;
+            // kxStack: one accumulator of npx columns per row, two stages side by side; otherwise an even / odd pair per row
+            const int cw = p.kxStack ? npx : (npx + 4 + kAccPitchAlign - 1) / kAccPitchAlign * kAccPitchAlign;
+            const int stageCols = p.kxStack ? r * cw : 2 * r * cw;
             // the last 32-column epilogue load of the last accumulator must stay inside the allocation
-            const int need = (2 * r - 1) * cw + ((cw + 31) & ~31);
+            const int need = p.kxStack ? 2 * stageCols : (2 * r - 1) * cw + ((cw + 31) & ~31);
             if (need > 512) continue;
             const int xGroup = (r + 2) * npx * 128;
             int wSlots = (smemLimit - 1024 - 4 * 32 * STAGE_PITCH * 4 - 2 * xGroup) / p.wSlotBytes;
             if (wSlots > kMaxWSlots) wSlots = kMaxWSlots;
             if (wSlots < 3) continue;
-            const bool resident = wSlots >= 9 * p.kChunks;
-            if (resident) wSlots = 9 * p.kChunks;
+            const bool resident = wSlots >= tapSlots * p.kChunks;
+            if (resident) wSlots = tapSlots * p.kChunks;
             const int s = npx - lose;
             const long long tiles = (long long)((p.OW + s - 1) / s) * ((p.OH + r - 1) / r);
             const double perMma = npx / 2.0 > 32.0 + npx / 4.0 ? npx / 2.0 : 32.0 + npx / 4.0;       // tools/tc_mma_bench.cu
-            const double mma = 36.0 * r * perMma;
-            const double load = ((resident ? 0.0 : 9.0 * p.wSlotBytes) + (double)xGroup) / 80.0;     // operand stream at ~80 B/clk/SM (fitted; 40 over-penalised wide tiles)
+            const double mma = 4.0 * tapSlots * r * perMma;
+            const double load = ((resident ? 0.0 : (double)tapSlots * p.wLoadBytes) + (double)xGroup) / 80.0;     // operand stream at ~80 B/clk/SM (fitted; 40 over-penalised wide tiles)
             const double epi = 530.0 * r * ((p.colBase + s + 31) / 32);
             const double kloop = p.kChunks * (mma > load ? mma : load);
-            // M = 64 (two accumulator stages): the epilogue of a tile overlaps the K loop of the next one
-            const double cost = (double)tiles * (1700.0 + (p.m64 ? (kloop > epi ? kloop : epi) : kloop + epi));
+            // two accumulator stages (M = 64 in the lanes, kxStack in the columns): the epilogue of a tile overlaps the K loop of the next one
+            const bool overlap = p.m64 || p.kxStack;
+            const double cost = (double)tiles * (1700.0 + (overlap ? (kloop > epi ? kloop : epi) : kloop + epi));
             if (cost < best) {
                 best = cost; found = true;
-                p.NPX = npx; p.R = r; p.CW = cw; p.S = s; p.accStages = p.m64 ? 2 : 1; p.accStageCols = stageCols;
+                p.NPX = npx; p.R = r; p.CW = cw; p.S = s; p.accStages = overlap ? 2 : 1; p.accStageCols = stageCols;
                 p.wSlots = wSlots; p.xGroupBytes = xGroup; p.resident = resident ? 1 : 0;
                 int cols = 32;
                 while (cols < need) cols <<= 1;
@@ -336,9 +421,17 @@ int launch_tc3(const void* x, const void* wtap, void* y, int N, int I, int O, in
     p.kChunks = (I + bkc - 1) / bkc;
     p.xoff = pad == 2 ? (HALF ? 8 : 4) : 0;
     p.colBase = p.xoff + (pad == 2 ? 0 : 2);
-    p.m64 = O <= 64 ? 1 : 0;
-    p.wRows = O >= 128 ? 128 : (O + 7) & ~7;
-    p.wSlotBytes = p.wRows * 128;                       // [wRows o][one 128-byte K row]
+#ifdef SG3_NO_KXSTACK
+    p.kxStack = 0;                                      // tuning / A-B builds
+#else
+    p.kxStack = O == 32 ? 1 : 0;                        // taps 3 ky .. 3 ky + 2 of the tap-major weights are 96 consecutive rows
+#endif
+    p.m64 = (!p.kxStack && O <= 64) ? 1 : 0;
+    p.wRows = p.kxStack ? 32 : (O >= 128 ? 128 : (O + 7) & ~7);
+    // [rows][one 128-byte K row].  kxStack: 96 rows per slot; the M = 128 MMA reads 32 rows past them (the next slot, or the staging
+    // buffer behind the ring: inside the allocation), which only feed accumulator rows 96 .. 127 that nobody reads
+    p.wSlotBytes = p.kxStack ? 96 * 128 : p.wRows * 128;
+    p.wLoadBytes = p.wSlotBytes;
     // co-scheduling with the stencil kernel (sg3_modconv_set_smem_budget): plan inside a smaller shared-memory budget
     const int budget = sg3_conv_smem_budget();
     // (a budget too small for any tile plan is ignored: the kernel then simply does not share its SM)
@@ -361,7 +454,7 @@ int launch_tc3(const void* x, const void* wtap, void* y, int N, int I, int O, in
     {
         const uint64_t dims[4] = {(uint64_t)I, (uint64_t)O, 9, (uint64_t)N};
         const uint64_t strides[3] = {(uint64_t)ldw * esz, (uint64_t)ldw * O * esz, (uint64_t)ldw * O * 9 * esz};
-        const uint32_t box[4] = {(uint32_t)bkc, (uint32_t)p.wRows, 1, 1};
+        const uint32_t box[4] = {(uint32_t)bkc, (uint32_t)p.wRows, p.kxStack ? 3u : 1u, 1};
         if (!sg3_make_tensor_map(&mapW, dt, 4, wtap, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
             return SG3_E_NOKERNEL;
     }

@@ -337,6 +337,9 @@ TC3_CASES = [
     (2, 96, 128, 96, 128, 2),      # streamed weights (3 chunks x 9 taps do not fit the ring), full 128-channel block
     (1, 64, 256, 75, 100, 2),      # odd number of pixel tiles, two channel blocks
     (3, 512, 512, 36, 36, 2),      # T-1024 L0 at batch 3: 16 chunks, four channel blocks
+    (1, 51, 32, 40, 276, 2),       # O = 32: the three kx taps stacked along M (T-1024 L12 channel counts), several column tiles
+    (2, 32, 32, 70, 148, 2),       # O = 32, one chunk (T-1024 L13), ragged last row block
+    (1, 160, 32, 33, 532, 2),      # O = 32, five chunks: the stacked weights are streamed, not resident
 ]
 
 
@@ -597,7 +600,7 @@ def test_native_3x3_input_gradient(pkg):
     oracle's input gradient; both forward paddings; dy handed over contiguous (re-pitched by a copy) and as a row-pitched view."""
     from oracle import sg3_oracle as orc
     rng = np.random.RandomState(23)
-    for (N, I, O, H, pad) in ((2, 40, 24, 24, 2), (1, 96, 130, 20, 2), (2, 33, 64, 20, 0)):        # W % 4 == 0 as in every config-T layer
+    for (N, I, O, H, pad) in ((2, 40, 24, 24, 2), (1, 96, 130, 20, 2), (2, 33, 64, 20, 0), (1, 32, 40, 24, 2)):   # W % 4 == 0 as in every config-T layer; I = 32: the dgrad conv stacks kx
         x = rng.randn(N, I, H, H).astype(np.float32)
         w = rng.randn(O, I, 3, 3).astype(np.float32)
         s = (rng.randn(N, I) + 1).astype(np.float32)
