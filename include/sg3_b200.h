@@ -192,7 +192,7 @@ int sg3_modconv_weights(const float* w, const float* s, const float* input_gain,
 int sg3_modconv_wgrad(const float* dy, const float* x, float* dw, int N, int I, int O, int H, int W, int ldw, void* stream);
 
 /* The same for 3x3 kernels (pad 0 or 2; TF32 tcgen05, the row range split across CTAs, fp32 atomics) -- replaces the grouped
- * weight-gradient convolution the reference runs through conv2d_gradfix.py:103-129 for networks_stylegan3.py:59-62:
+ * weight-gradient convolution the reference runs through conv2d_gradfix.py:153-174 for networks_stylegan3.py:59-62:
  *   dw[n][ky*3+kx][o][i] += sum_oy sum_ox dy[n][o][oy][ox] * x[n][i][oy+ky-pad][ox+kx-pad]      (x = 0 outside the image)
  * dy [N][O][OH][dyPitch], x [N][I][H][xPitch] with OH = H + 2 pad - 2; row pitches in floats, multiples of 4, 0 = dense (then
  * the width itself must be a multiple of 4); dw [N][9][O][ldw >= I] (tap-major like weight layout 2; ldw % 4 == 0, 16-byte aligned)

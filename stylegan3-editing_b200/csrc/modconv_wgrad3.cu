@@ -1,5 +1,5 @@
 // modconv_wgrad3.cu -- TF32 tcgen05/TMEM weight gradient of the 3x3 modulated conv (StyleGAN3 config T; the grouped
-// convolution of networks_stylegan3.py:59-62 differentiated wrt the per-sample weights; conv2d_gradfix.py:103-129 is what the
+// convolution of networks_stylegan3.py:59-62 differentiated wrt the per-sample weights; conv2d_gradfix.py:153-174 is what the
 // reference runs for it).
 //
 //   dW[n][ky][kx][o][i] = sum_oy sum_ox  dY[n][o][oy][ox] * X[n][i][oy + ky - pad][ox + kx - pad]        (X = 0 outside the image)

@@ -383,7 +383,7 @@ def _wgrad3_taps(x, dy, padding):
 def conv3x3_weight_grad(x, dy, padding):
     """Per-sample weight gradient of the 3x3 conv on the tcgen05 kernel (`sg3_modconv_wgrad3`, TF32 operands, fp32 accumulation):
     dW[n, o, i, ky, kx] = sum dy[n, o, oy, ox] * x[n, i, oy + ky - pad, ox + kx - pad] -- what the reference gets from the grouped
-    `conv2d_weight` of conv2d_gradfix.py:103-129.  x [N, I, H, W], dy [N, O, H + 2 pad - 2, W + 2 pad - 2], float32 (dense or
+    `conv2d_weight` of conv2d_gradfix.py:153-174.  x [N, I, H, W], dy [N, O, H + 2 pad - 2, W + 2 pad - 2], float32 (dense or
     row-pitched views; anything else is copied into a row-pitched buffer).  Returns [N, O, I, 3, 3] (a permuted view of the
     tap-major buffer the kernel accumulates into) or None when the library has no kernel for the call."""
     N, I = x.shape[:2]

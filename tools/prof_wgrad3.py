@@ -1,5 +1,5 @@
 """Time the 3x3 weight gradient at the StyleGAN3-T 1024^2 layer shapes: the tcgen05 kernel (sg3_modconv_wgrad3) next to the
-library call it replaces (torch.nn.grad.conv2d_weight, groups = N, TF32 allowed = what conv2d_gradfix.py:103-129 runs).
+library call it replaces (torch.nn.grad.conv2d_weight, groups = N, TF32 allowed = what conv2d_gradfix.py:153-174 runs).
 
     python tools/prof_wgrad3.py [N] [first layer prefix]
 """
